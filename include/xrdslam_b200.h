@@ -1,0 +1,180 @@
+/*
+ * xrdslam_b200 -- C-ABI of the B200-native render-and-optimise hot path.
+ *
+ * This is the drop-in boundary.  Every entry point is
+ * `extern "C"`, takes plain pointers / sizes / POD structs, never allocates,
+ * never frees, never synchronises the stream: one call = an asynchronous enqueue
+ * of sm_100a kernels on `stream` (a cudaStream_t passed as void*).  All buffers,
+ * including the workspace, are owned by the caller (torch on the Python side).
+ * Return value: XRD_OK (0) or a negative XrdStatus.  No exceptions, no exit().
+ *
+ * What each entry point replaces in the reference (paths relative to
+ * /root/reference, commit f0366f20):
+ *
+ *   xrd_coslam_step        slam/models/joint_encoding.py:158-163  get_outputs
+ *                          -> render_rays :250-344, run_network :483-507,
+ *                          query_color_sdf :463-481 (tcnn HashGrid + OneBlob via
+ *                          slam/model_components/encodings_coslam.py:39-75,
+ *                          decoders slam/model_components/decoder_coslam.py:139-163),
+ *                          sdf2weights :346-374, raw2outputs :376-406,
+ *                          get_loss_dict :94-147 (+ utils.py:100-186) and the
+ *                          autograd backward of all of it (loss.backward(),
+ *                          slam/algorithms/base_algorithm.py:266).
+ *   xrd_coslam_smoothness  slam/models/joint_encoding.py:165-197 smoothness
+ *                          (forward + gradient w.r.t. the hash table).
+ *   xrd_hashgrid_layout    tcnn GridEncodingTemplated ctor (level offsets), the
+ *                          config built at encodings_coslam.py:39-53.
+ *   xrd_linspace_f32       torch.linspace as used at joint_encoding.py:264-279.
+ *
+ * (NICE-SLAM / Vox-Fusion / Point-SLAM entry points are declared further down.)
+ */
+#ifndef XRDSLAM_B200_H_
+#define XRDSLAM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XRD_ABI_VERSION 1
+#define XRD_MAX_LEVELS 16
+
+typedef enum {
+  XRD_OK = 0,
+  XRD_E_SHAPE = -1,     /* inconsistent sizes / unsupported configuration   */
+  XRD_E_ARCH = -2,      /* device is not sm_100                              */
+  XRD_E_WORKSPACE = -3, /* workspace too small                               */
+  XRD_E_NOHIT = -4,     /* Vox-Fusion: no ray hit any voxel (reference: None) */
+  XRD_E_CUDA = -5,      /* a CUDA runtime call failed (see xrd_last_cuda_error) */
+  XRD_E_NULL = -6       /* a required pointer is NULL                        */
+} XrdStatus;
+
+int xrd_abi_version(void);
+/* cudaError_t of the last failing runtime call on this thread (0 if none). */
+int xrd_last_cuda_error(void);
+/* 0 if device `dev` is compute capability 10.x, XRD_E_ARCH otherwise. */
+int xrd_check_device(int dev);
+
+/* ---- shared ------------------------------------------------------------ */
+
+/* A batch of rays.  All pointers are DEVICE pointers, fp32, contiguous. */
+typedef struct {
+  int n_rays;
+  const float* rays_o;   /* [R,3] */
+  const float* rays_d;   /* [R,3] */
+  const float* target_s; /* [R,3] colour target, may be NULL (render only)   */
+  const float* target_d; /* [R]   depth target,  may be NULL                 */
+} XrdRays;
+
+/* torch.linspace(start, end, steps) for float32, bit-identical to ATen's CPU
+ * kernel (host function, writes `steps` floats to host memory `out`). */
+int xrd_linspace_f32(float start, float end, int steps, float* out);
+
+/* ---- Co-SLAM ------------------------------------------------------------ */
+
+/* Multi-resolution hash grid in tcnn's parameter layout: one flat fp32 array,
+ * level-major, entry-major, feature-minor, 2 features per entry. */
+typedef struct {
+  int n_levels;                        /* <= XRD_MAX_LEVELS (Co-SLAM: 16)      */
+  float scale[XRD_MAX_LEVELS];         /* grid_scale(level)                    */
+  uint32_t resolution[XRD_MAX_LEVELS]; /* grid_resolution(scale)               */
+  uint32_t size[XRD_MAX_LEVELS];       /* entries in level                     */
+  uint32_t offset[XRD_MAX_LEVELS];     /* first entry of level                 */
+  uint32_t hashed[XRD_MAX_LEVELS];     /* 1: coherent-prime hash, 0: dense     */
+  uint32_t n_entries;                  /* sum(size)                            */
+  double bbox_min[3];                  /* scene bound, float64 as the reference */
+  double bbox_max[3];
+  const float* table;                  /* DEVICE [n_entries*2]                 */
+} XrdHashGrid;
+
+/* Fill scale/resolution/size/offset/hashed/n_entries (host function). */
+int xrd_hashgrid_layout(XrdHashGrid* g, int n_levels, int log2_hashmap_size,
+                        int base_resolution, float per_level_scale);
+
+/* ColorSDFNet_v2 weights, torch nn.Linear layout [out,in], no bias. DEVICE. */
+typedef struct {
+  const float* w_sdf0; /* [32,80]  in = hash32 ++ oneblob48                  */
+  const float* w_sdf1; /* [16,32]  out = sdf ++ geo15                        */
+  const float* w_col0; /* [32,63]  in = oneblob48 ++ geo15                   */
+  const float* w_col1; /* [3,32]                                             */
+} XrdCoslamMlp;
+
+typedef struct {
+  int n_samples;      /* S: samples per ray actually marched (43 with depth) */
+  int n_sample_d;     /* 32 uniform samples in [near,far]                    */
+  int n_range_d;      /* 11 depth-guided samples                             */
+  int perturb;        /* stratified jitter on/off                            */
+  float trunc;        /* training_trunc * sc_factor (0.1)                    */
+  float depth_trunc;  /* cam_depth_trunc (100)                               */
+  float w_rgb, w_depth, w_sdf, w_fs; /* loss weights 5, 0.1, 1000, 10        */
+  /* DEVICE tables, normally produced with torch.linspace / xrd_linspace_f32: */
+  const float* lin_uniform;  /* [n_sample_d]  linspace(near, far)             */
+  const float* lin_range;    /* [n_range_d]   linspace(-range_d, range_d)     */
+  const float* lin_nodepth;  /* [n_range_d]   linspace(near, far)             */
+  const float* lin_full;     /* [n_samples]   used when target_d == NULL      */
+  uint64_t seed;             /* Philox seed when noise == NULL                */
+  int rays_per_tile;         /* 0 = library default                           */
+} XrdCoslamCfg;
+
+/* Per-ray / per-sample outputs (DEVICE, any may be NULL except losses when
+ * grads are requested). */
+typedef struct {
+  float* rgb;       /* [R,3] */
+  float* depth;     /* [R]   */
+  float* disp;      /* [R]   */
+  float* acc;       /* [R]   */
+  float* depth_var; /* [R]   */
+  float* z_vals;    /* [R,S] */
+  float* raw;       /* [R,S,4] rgb logits ++ sdf */
+  float* losses;    /* [4] rgb, depth, sdf, fs -- already multiplied by w_*  */
+} XrdCoslamOut;
+
+/* Gradients of (rgb+depth+sdf+fs) loss scaled by loss_scale[4] per term.
+ * d_table and d_w_* are ACCUMULATED into (caller zeroes them: mapping-pose Adam
+ * uses accum_step, Q11); d_rays_* are overwritten. */
+typedef struct {
+  float* d_table;  /* [n_entries*2] */
+  float* d_w_sdf0; /* [32,80] */
+  float* d_w_sdf1; /* [16,32] */
+  float* d_w_col0; /* [32,63] */
+  float* d_w_col1; /* [3,32]  */
+  float* d_rays_o; /* [R,3] or NULL */
+  float* d_rays_d; /* [R,3] or NULL */
+  float loss_scale[4]; /* upstream d total / d term (normally 1,1,1,1) */
+} XrdCoslamGrads;
+
+size_t xrd_coslam_workspace_bytes(int n_rays, int n_samples);
+
+/* One fused forward(+backward) pass.  noise: DEVICE [R,S] uniform(0,1) replacing
+ * torch.rand(z_vals.shape) (joint_encoding.py:292) or NULL for in-kernel Philox.
+ * grads == NULL -> forward only (render_img). */
+int xrd_coslam_step(const XrdRays* rays, const XrdHashGrid* grid,
+                    const XrdCoslamMlp* mlp, const XrdCoslamCfg* cfg,
+                    const float* noise, XrdCoslamOut* out,
+                    XrdCoslamGrads* grads, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+size_t xrd_coslam_smoothness_workspace_bytes(int sample_points);
+
+/* Smoothness / TV regulariser on the hash features (joint_encoding.py:165-197).
+ * smooth_rand: HOST [6] = torch.rand(3) ++ torch.rand((1,1,1,3)).  Writes
+ * weight*loss to DEVICE loss[0]; if d_table != NULL accumulates
+ * grad_scale*weight*dloss/dtable into it. */
+int xrd_coslam_smoothness(const XrdHashGrid* grid, int sample_points,
+                          double voxel_size, double margin, float weight,
+                          const float* smooth_rand, float* loss, float* d_table,
+                          float grad_scale, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* Hash-grid encoding only (used by the mesher path query_sdf(embed=True) and
+ * by the index-parity tests): x DEVICE [P,3] normalised coords ->
+ * feat [P,2*n_levels]; idx (optional) [P,n_levels,8] uint32 entry indices. */
+int xrd_hashgrid_encode(const XrdHashGrid* grid, const float* x, int n_points,
+                        float* feat, uint32_t* idx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XRDSLAM_B200_H_ */

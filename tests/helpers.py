@@ -1,0 +1,55 @@
+"""Shared builders for the parity tests (oracle <-> CUDA path)."""
+import numpy as np
+import torch
+
+BOUND = np.array([[-3, 3], [-4, 2.5], [-2, 2.5]], dtype=np.float64)
+
+
+def make_rays(R, seed=0, zero_depth_every=7):
+    g = torch.Generator().manual_seed(seed)
+    rays_o = (torch.rand(R, 3, generator=g) - 0.5) * 1.0
+    rays_d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g),
+                                           dim=-1)
+    rays_d = rays_d * (1.0 + 0.2 * torch.rand(R, 1, generator=g))
+    target_d = torch.rand(R, 1, generator=g) * 3 + 0.3
+    if zero_depth_every:
+        target_d[::zero_depth_every] = 0
+    target_s = torch.rand(R, 3, generator=g)
+    noise = torch.rand(R, 43, generator=g)
+    return rays_o, rays_d, target_s, target_d, noise
+
+
+def coslam_pair(device, table_amp=0.3, seed=1, **cfg):
+    """(oracle on CPU, B200 model on device) with identical parameters."""
+    from oracle.coslam import CoslamOracle
+    from xrdslam_b200.camera import Camera
+    from xrdslam_b200.joint_encoding import JointEncodingConfig
+    ora = CoslamOracle(BOUND)
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        ora.embed_fn.params.copy_(
+            (torch.rand(ora.embed_fn.params.shape, generator=g) * 2 - 1) *
+            table_amp)
+        for lin in (ora.sdf0, ora.sdf1, ora.col0, ora.col1):
+            lin.weight.copy_(torch.randn(lin.weight.shape, generator=g) *
+                             (1.0 / np.sqrt(lin.weight.shape[1])))
+    model = JointEncodingConfig(**cfg).setup(
+        camera=Camera(320., 320., 319.5, 239.5, 640, 480), bounding_box=BOUND)
+    with torch.no_grad():
+        model.embed_fn.params.copy_(ora.embed_fn.params)
+        model.decoder.sdf_net.model[0].weight.copy_(ora.sdf0.weight)
+        model.decoder.sdf_net.model[2].weight.copy_(ora.sdf1.weight)
+        model.decoder.color_net.model[0].weight.copy_(ora.col0.weight)
+        model.decoder.color_net.model[2].weight.copy_(ora.col1.weight)
+    model.to(device)
+    return ora, model
+
+
+def rel_err(a, b):
+    a = a.detach().double().cpu().reshape(-1)
+    b = b.detach().double().cpu().reshape(-1)
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def max_abs(a, b):
+    return float((a.detach().double().cpu() - b.detach().double().cpu()).abs().max())

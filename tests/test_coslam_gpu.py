@@ -1,0 +1,140 @@
+"""Parity of the fused Co-SLAM CUDA path (through the C-ABI) against the CPU
+oracle (oracle/coslam.py, itself pinned to the reference's JointEncoding)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import BOUND, coslam_pair, make_rays, max_abs, rel_err
+
+pytestmark = pytest.mark.gpu
+
+# fp32 kernel vs fp32 oracle: different summation order only
+TOL_OUT = 2e-5     # abs, rgb in [0,1], depth in metres
+TOL_LOSS = 2e-5    # rel
+TOL_GRAD = 2e-4    # rel l2 over the whole gradient tensor
+
+
+def test_hash_indices_bit_exact(cuda_dev):
+    import ctypes as C
+    from oracle.tcnn_restated import hashgrid_indices
+    from xrdslam_b200 import _cabi
+    ora, model = coslam_pair(cuda_dev)
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(20000, 3, generator=g) * 3 - 1  # in and outside [0,1]
+    x[:8] = torch.tensor([[0, 0, 0], [1, 1, 1], [0.5, 0.5, 0.5], [1, 0, 1],
+                          [-0.25, 0.3, 2.0], [1e-7, 1 - 1e-7, 0.999999],
+                          [-1e-4, 0.2, 0.3], [3.1, -2.2, 0.5]])
+    idx_o, _ = hashgrid_indices(x, ora.embed_fn.table)
+    xd = x.to(cuda_dev)
+    feat = torch.empty(x.shape[0], 32, device=cuda_dev)
+    idx = torch.empty(x.shape[0], 16, 8, dtype=torch.int32, device=cuda_dev)
+    grid = model._grid_struct(model.embed_fn.params.detach())
+    st = _cabi.lib().xrd_hashgrid_encode(C.byref(grid), xd.data_ptr(),
+                                         x.shape[0], feat.data_ptr(),
+                                         idx.data_ptr(), None)
+    _cabi.check('xrd_hashgrid_encode', st)
+    torch.cuda.synchronize()
+    got = idx.cpu().to(torch.int64) & 0xFFFFFFFF
+    assert torch.equal(got, idx_o)  # bit-exact
+    with torch.no_grad():
+        f_o = ora.embed_fn(x)
+    assert max_abs(feat, f_o) < 1e-6
+
+
+@pytest.mark.parametrize('R', [1, 5, 257, 1024])
+def test_step_parity(cuda_dev, R):
+    ora, model = coslam_pair(cuda_dev)
+    rays_o, rays_d, ts, td, noise = make_rays(R, seed=R)
+    rays_o.requires_grad_(True)
+    rays_d.requires_grad_(True)
+    out_o, ld_o, tot_o = ora.step(rays_o, rays_d, ts, td, noise, False, True)
+    tot_o.backward()
+
+    ro = rays_o.detach().to(cuda_dev).requires_grad_(True)
+    rd = rays_d.detach().to(cuda_dev).requires_grad_(True)
+    inp = dict(rays_o=ro, rays_d=rd, target_s=ts.to(cuda_dev),
+               target_d=td.to(cuda_dev), first=True, noise=noise.to(cuda_dev))
+    out = model(inp)
+    ld = model.get_loss_dict(out, inp, False, 0)
+    tot = sum(ld.values())
+    tot.backward()
+    torch.cuda.synchronize()
+
+    assert torch.equal(out['z_vals'].cpu(), out_o['z_vals'])  # bit-exact
+    for k in ('rgb', 'depth', 'acc_map', 'depth_var'):
+        assert max_abs(out[k], out_o[k]) < TOL_OUT, k
+    assert max_abs(out['raw'], out_o['raw']) < 5e-5
+    for k in ld_o:
+        a, b = float(ld[k]), float(ld_o[k])
+        assert abs(a - b) <= TOL_LOSS * max(abs(b), 1e-6), (k, a, b)
+    assert rel_err(model.embed_fn.params.grad, ora.embed_fn.params.grad) < TOL_GRAD
+    pairs = [(model.decoder.sdf_net.model[0], ora.sdf0),
+             (model.decoder.sdf_net.model[2], ora.sdf1),
+             (model.decoder.color_net.model[0], ora.col0),
+             (model.decoder.color_net.model[2], ora.col1)]
+    for m, o in pairs:
+        assert rel_err(m.weight.grad, o.weight.grad) < TOL_GRAD
+    assert rel_err(ro.grad, rays_o.grad) < TOL_GRAD
+    assert rel_err(rd.grad, rays_d.grad) < TOL_GRAD
+
+
+def test_smoothness_parity(cuda_dev):
+    ora, model = coslam_pair(cuda_dev)
+    rnd = torch.tensor([0.3, 0.7, 0.1, 0.9, 0.2, 0.5])
+    s_o = ora.smoothness(rnd.reshape(2, 3))
+    s_o.backward()
+    s = model.smoothness(32, 0.1, 0.05, rand=rnd)
+    s.backward()
+    torch.cuda.synchronize()
+    assert abs(float(s) - float(s_o)) <= 2e-5 * abs(float(s_o))
+    assert rel_err(model.embed_fn.params.grad, ora.embed_fn.params.grad) < TOL_GRAD
+
+
+def test_mapping_step_with_smoothness(cuda_dev):
+    ora, model = coslam_pair(cuda_dev)
+    R = 300
+    rays_o, rays_d, ts, td, noise = make_rays(R, seed=11)
+    rnd = torch.tensor([0.11, 0.52, 0.93, 0.4, 0.6, 0.8])
+    out_o, ld_o, tot_o = ora.step(rays_o, rays_d, ts, td, noise, True, False,
+                                  smooth_rand=rnd.reshape(2, 3))
+    tot_o.backward()
+    inp = dict(rays_o=rays_o.to(cuda_dev), rays_d=rays_d.to(cuda_dev),
+               target_s=ts.to(cuda_dev), target_d=td.to(cuda_dev), first=False,
+               noise=noise.to(cuda_dev), smooth_rand=rnd)
+    out = model(inp)
+    ld = model.get_loss_dict(out, inp, True, 0)
+    assert set(ld) == set(ld_o)
+    import functools
+    functools.reduce(torch.add, ld.values()).backward()
+    torch.cuda.synchronize()
+    for k in ld_o:
+        a, b = float(ld[k]), float(ld_o[k])
+        assert abs(a - b) <= TOL_LOSS * max(abs(b), 1e-9), (k, a, b)
+    assert rel_err(model.embed_fn.params.grad, ora.embed_fn.params.grad) < TOL_GRAD
+
+
+def test_render_only_no_depth(cuda_dev):
+    """target_d=None -> 256 uniform samples (joint_encoding.py:281-284)."""
+    ora, model = coslam_pair(cuda_dev, training_perturb=0)
+    ora.cfg.perturb = 0
+    rays_o, rays_d, _, _, _ = make_rays(37, seed=5)
+    with torch.no_grad():
+        out_o = ora.render_rays(rays_o, rays_d, None, None)
+        out = model(dict(rays_o=rays_o.to(cuda_dev), rays_d=rays_d.to(cuda_dev),
+                         target_s=None, target_d=None))
+    assert torch.equal(out['z_vals'].cpu(), out_o['z_vals'])
+    assert max_abs(out['rgb'], out_o['rgb']) < TOL_OUT
+    assert max_abs(out['depth'], out_o['depth']) < 5e-5
+
+
+def test_strict_nonunit_loss_grad(cuda_dev):
+    ora, model = coslam_pair(cuda_dev, strict_loss_grad=True)
+    rays_o, rays_d, ts, td, noise = make_rays(64, seed=2)
+    out_o, ld_o, _ = ora.step(rays_o, rays_d, ts, td, noise, False, True)
+    (2.0 * ld_o['rgb_loss'] + 0.5 * ld_o['sdf_loss'] + ld_o['fs_loss']).backward()
+    inp = dict(rays_o=rays_o.to(cuda_dev), rays_d=rays_d.to(cuda_dev),
+               target_s=ts.to(cuda_dev), target_d=td.to(cuda_dev), first=True,
+               noise=noise.to(cuda_dev))
+    ld = model.get_loss_dict(model(inp), inp, False, 0)
+    (2.0 * ld['rgb_loss'] + 0.5 * ld['sdf_loss'] + ld['fs_loss']).backward()
+    assert rel_err(model.embed_fn.params.grad, ora.embed_fn.params.grad) < TOL_GRAD

@@ -1,0 +1,140 @@
+"""ctypes binding of include/xrdslam_b200.h (the C-ABI shared library).
+
+The product path has NO fallback: if the library is missing or cannot be loaded
+this module raises at import of the symbol table, and every op raises
+``XrdError`` on a non-zero status.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libxrdslam_b200.so')
+
+XRD_MAX_LEVELS = 16
+_STATUS = {
+    0: 'XRD_OK',
+    -1: 'XRD_E_SHAPE',
+    -2: 'XRD_E_ARCH',
+    -3: 'XRD_E_WORKSPACE',
+    -4: 'XRD_E_NOHIT',
+    -5: 'XRD_E_CUDA',
+    -6: 'XRD_E_NULL',
+}
+XRD_E_NOHIT = -4
+
+
+class XrdError(RuntimeError):
+    def __init__(self, fn, status, cuda_err=0):
+        self.status = status
+        super().__init__(
+            f'{fn} failed: {_STATUS.get(status, status)}'
+            + (f' (cudaError {cuda_err})' if status == -5 else ''))
+
+
+fp = C.POINTER(C.c_float)
+vp = C.c_void_p
+
+
+class XrdRays(C.Structure):
+    _fields_ = [('n_rays', C.c_int), ('rays_o', vp), ('rays_d', vp),
+                ('target_s', vp), ('target_d', vp)]
+
+
+class XrdHashGrid(C.Structure):
+    _fields_ = [('n_levels', C.c_int),
+                ('scale', C.c_float * XRD_MAX_LEVELS),
+                ('resolution', C.c_uint32 * XRD_MAX_LEVELS),
+                ('size', C.c_uint32 * XRD_MAX_LEVELS),
+                ('offset', C.c_uint32 * XRD_MAX_LEVELS),
+                ('hashed', C.c_uint32 * XRD_MAX_LEVELS),
+                ('n_entries', C.c_uint32), ('bbox_min', C.c_double * 3),
+                ('bbox_max', C.c_double * 3), ('table', vp)]
+
+
+class XrdCoslamMlp(C.Structure):
+    _fields_ = [('w_sdf0', vp), ('w_sdf1', vp), ('w_col0', vp), ('w_col1', vp)]
+
+
+class XrdCoslamCfg(C.Structure):
+    _fields_ = [('n_samples', C.c_int), ('n_sample_d', C.c_int),
+                ('n_range_d', C.c_int), ('perturb', C.c_int),
+                ('trunc', C.c_float), ('depth_trunc', C.c_float),
+                ('w_rgb', C.c_float), ('w_depth', C.c_float),
+                ('w_sdf', C.c_float), ('w_fs', C.c_float),
+                ('lin_uniform', vp), ('lin_range', vp), ('lin_nodepth', vp),
+                ('lin_full', vp), ('seed', C.c_uint64),
+                ('rays_per_tile', C.c_int)]
+
+
+class XrdCoslamOut(C.Structure):
+    _fields_ = [('rgb', vp), ('depth', vp), ('disp', vp), ('acc', vp),
+                ('depth_var', vp), ('z_vals', vp), ('raw', vp), ('losses', vp)]
+
+
+class XrdCoslamGrads(C.Structure):
+    _fields_ = [('d_table', vp), ('d_w_sdf0', vp), ('d_w_sdf1', vp),
+                ('d_w_col0', vp), ('d_w_col1', vp), ('d_rays_o', vp),
+                ('d_rays_d', vp), ('loss_scale', C.c_float * 4)]
+
+
+_lib = None
+
+# name -> (restype, argtypes); every symbol include/xrdslam_b200.h declares
+SYMBOLS = {
+    'xrd_abi_version': (C.c_int, []),
+    'xrd_last_cuda_error': (C.c_int, []),
+    'xrd_check_device': (C.c_int, [C.c_int]),
+    'xrd_linspace_f32': (C.c_int, [C.c_float, C.c_float, C.c_int, fp]),
+    'xrd_hashgrid_layout':
+    (C.c_int, [C.POINTER(XrdHashGrid), C.c_int, C.c_int, C.c_int, C.c_float]),
+    'xrd_coslam_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int]),
+    'xrd_coslam_step': (C.c_int, [
+        C.POINTER(XrdRays),
+        C.POINTER(XrdHashGrid),
+        C.POINTER(XrdCoslamMlp),
+        C.POINTER(XrdCoslamCfg), vp,
+        C.POINTER(XrdCoslamOut),
+        C.POINTER(XrdCoslamGrads), vp, C.c_size_t, vp
+    ]),
+    'xrd_coslam_smoothness_workspace_bytes': (C.c_size_t, [C.c_int]),
+    'xrd_coslam_smoothness': (C.c_int, [
+        C.POINTER(XrdHashGrid), C.c_int, C.c_double, C.c_double, C.c_float, fp,
+        vp, vp, C.c_float, vp, C.c_size_t, vp
+    ]),
+    'xrd_hashgrid_encode':
+    (C.c_int, [C.POINTER(XrdHashGrid), vp, C.c_int, vp, vp, vp]),
+}
+
+
+def lib():
+    """Load the shared library (once) and type every exported symbol."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f'{LIB_PATH} not found: build it with '
+                '`python -m xrdslam_b200.build` (there is no CPU fallback)')
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            f = getattr(L, name)  # AttributeError if the .so lacks a symbol
+            f.restype = res
+            f.argtypes = args
+        if L.xrd_abi_version() != 1:
+            raise ImportError('xrdslam_b200 ABI version mismatch')
+        _lib = L
+    return _lib
+
+
+def check(fn_name, status):
+    if status != 0:
+        raise XrdError(fn_name, status, lib().xrd_last_cuda_error())
+
+
+def ptr(t):
+    """Device/host pointer of a (contiguous) torch tensor, or None."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), 'C-ABI needs contiguous tensors'
+    return t.data_ptr()
