@@ -13,7 +13,7 @@ def make_rays(R, seed=0, zero_depth_every=7):
     rays_d = rays_d * (1.0 + 0.2 * torch.rand(R, 1, generator=g))
     target_d = torch.rand(R, 1, generator=g) * 3 + 0.3
     if zero_depth_every:
-        target_d[::zero_depth_every] = 0
+        target_d[3::zero_depth_every] = 0
     target_s = torch.rand(R, 3, generator=g)
     noise = torch.rand(R, 43, generator=g)
     return rays_o, rays_d, target_s, target_d, noise

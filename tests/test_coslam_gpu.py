@@ -65,7 +65,7 @@ def test_step_parity(cuda_dev, R):
         assert max_abs(out[k], out_o[k]) < TOL_OUT, k
     assert max_abs(out['raw'], out_o['raw']) < 5e-5
     for k in ld_o:
-        a, b = float(ld[k]), float(ld_o[k])
+        a, b = float(ld[k].detach()), float(ld_o[k].detach())
         assert abs(a - b) <= TOL_LOSS * max(abs(b), 1e-6), (k, a, b)
     assert rel_err(model.embed_fn.params.grad, ora.embed_fn.params.grad) < TOL_GRAD
     pairs = [(model.decoder.sdf_net.model[0], ora.sdf0),
@@ -108,7 +108,7 @@ def test_mapping_step_with_smoothness(cuda_dev):
     functools.reduce(torch.add, ld.values()).backward()
     torch.cuda.synchronize()
     for k in ld_o:
-        a, b = float(ld[k]), float(ld_o[k])
+        a, b = float(ld[k].detach()), float(ld_o[k].detach())
         assert abs(a - b) <= TOL_LOSS * max(abs(b), 1e-9), (k, a, b)
     assert rel_err(model.embed_fn.params.grad, ora.embed_fn.params.grad) < TOL_GRAD
 
