@@ -1,0 +1,446 @@
+#!/usr/bin/env python
+"""Benchmark of the Co-SLAM render-and-optimise hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json configs[1]): co-slam hash grid + OneBlob, 640x480
+synthetic Replica-shaped RGB-D sequence.  One *step* = one mapping iteration of
+the reference loop body (slam/algorithms/base_algorithm.py:255-273): assemble a
+ray batch (2048 keyframe-bank rays + 2048 current-frame rays), fused
+forward + loss + backward on the GPU (incl. the smoothness term), optimizer step.
+
+  value   rays/s with the ray batches already resident in HBM (device timed,
+          CUDA events per step, L2 flushed between steps, max over ranks).
+  e2e     rays/s through the plugin call a user makes
+          (CoSLAM.get_loss -> backward -> Optimizers.optimizer_step_all) with the
+          keyframe ray bank in pinned HOST memory: per-step H2D copy of the
+          sampled batch and D2H read of the loss are inside the timed region.
+  N > 1   mapping rays are sharded: every rank owns a fixed 4096-ray batch
+          (weak scaling), one NCCL all-reduce over the flat gradient bucket
+          (hash table + MLP) per iteration, Adam replicated.
+
+--impl reference times the CPU oracle port (torch, all host threads) of the same
+step on rank 0 -- the reference's own code cannot travel to the GPU box (python
+3.12 import failure + tinycudann/faiss absent).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import random
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_RAY = 88064  # 43 samples x (1024 B gather + 1024 B scatter)
+SMOOTH_BYTES = 29791 * 2048  # smoothness lattice, per mapping iteration
+MAP_KF, MAP_CUR = 2048, 2048
+N_KEYFRAMES = 5
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ clocks ---
+class ClockSampler:
+    """SM clock + throttle reasons sampled in-process through NVML every 5 ms
+    while the timed region runs (the nvidia-smi recipe's fields)."""
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.ok = False
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(',')[self.index])
+                except ValueError:
+                    pass
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:  # noqa
+            self.err = repr(e)
+            return
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        nv = self.nv
+        bits = {
+            'hw_slowdown': nv.nvmlClocksThrottleReasonHwSlowdown,
+            'hw_thermal_slowdown': nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+            'sw_thermal_slowdown': nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+            'sw_power_cap': nv.nvmlClocksThrottleReasonSwPowerCap,
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, b in bits.items():
+                    if r & b:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def stop(self):
+        if not self.ok:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvml unavailable']}
+        self.stop_flag = True
+        self.t.join(timeout=1)
+        return {'sm_mhz': float(np.median(self.samples)) if self.samples else None,
+                'sm_max_mhz': self.sm_max, 'reasons': sorted(self.reasons),
+                'samples': len(self.samples)}
+
+
+# ------------------------------------------------------------------ set-up ---
+def build_algorithm(device, seed):
+    from xrdslam_b200.coslam import CoSLAMConfig
+    from xrdslam_b200.frame import Frame
+    from xrdslam_b200.synthetic import make_sequence
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    cam, poses, frames = make_sequence(N_KEYFRAMES + 1)
+    algo = CoSLAMConfig().setup(camera=cam, device=device)
+    kfs = []
+    for k in range(N_KEYFRAMES):
+        f = Frame(k, frames[k][0], frames[k][1], init_pose=poses[k],
+                  separate_LR=True, rot_rep='axis_angle')
+        algo.add_keyframe(f)
+        kfs.append(f)
+    cur = Frame(N_KEYFRAMES, frames[-1][0], frames[-1][1], init_pose=poses[-1],
+                separate_LR=True, rot_rep='axis_angle')
+    algo.set_initialized()
+    return algo, kfs, cur
+
+
+def flat_params(model):
+    return [model.embed_fn.params] + list(model.decoder.parameters())
+
+
+def allreduce_grads(params, world):
+    if world == 1:
+        return
+    import torch.distributed as dist
+    from torch._utils import _flatten_dense_tensors, _unflatten_dense_tensors
+    grads = [p.grad for p in params]
+    flat = _flatten_dense_tensors(grads)
+    dist.all_reduce(flat)
+    flat.div_(world)
+    for g, f in zip(grads, _unflatten_dense_tensors(flat, grads)):
+        g.copy_(f)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    from xrdslam_b200 import _cabi
+    lib = _cabi.lib()
+    _cabi.check('xrd_check_device', lib.xrd_check_device(local))
+
+    algo, kfs, cur = build_algorithm(dev, seed=1234 + rank)
+    model = algo.model
+    frames = kfs + [cur]
+    K, W = args.steps, args.warmup
+    R = MAP_KF + MAP_CUR
+    params = flat_params(model)
+    if world > 1:  # identical replicas
+        for p in params:
+            dist.broadcast(p.data, 0)
+    optim = algo.setup_optimizers(K, frames, is_mapping=True)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def make_batch():
+        """What CoSLAM.get_model_input builds, with the current-frame share raised
+        to 2048 rays (the reference's first-keyframe shape) so R is fixed."""
+        algo.config.min_sample_pixels = MAP_CUR
+        inp = algo.get_model_input(frames, True)
+        inp['smooth_rand'] = torch.rand(6)
+        return inp
+
+    def device_step(inp):
+        optim.zero_grad_all()
+        out = model(inp)
+        loss_dict = model.get_loss_dict(out, inp, True, 0)
+        loss = sum(loss_dict.values())
+        loss.backward()
+        allreduce_grads(params, world)
+        optim.optimizer_step_all(step=0)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- value: batches resident in HBM -----------------------
+    batches = []
+    for _ in range(K + W):
+        b = make_batch()
+        b = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in b.items()}
+        b['rays_o'].requires_grad_(True)  # bundle adjustment: pose gradients are
+        b['rays_d'].requires_grad_(True)  # part of the step (d loss / d rays)
+        batches.append(b)
+    for i in range(W):
+        device_step(batches[i])
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(K)]
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        flush.zero_()  # L2 flush (256 MB > 126 MB L2), outside the timed events
+        ev[i][0].record()
+        device_step(batches[W + i])
+        ev[i][1].record()
+    barrier()
+    wall = time.perf_counter() - t0
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    clk = clocks.stop() if rank == 0 else None
+    value = world * R * K / (ms_total * 1e-3)
+
+    # ---------------- roofline: the fused kernel alone ---------------------
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(K)]
+    for i in range(K):
+        flush.zero_()
+        optim.zero_grad_all()
+        kev[i][0].record()  # materialise the lazily-created handles
+        kev[i][1].record()  # (both are re-recorded by the library around k_fused)
+        lib.xrd_debug_kernel_events(kev[i][0].cuda_event, kev[i][1].cuda_event)
+        out = model(batches[W + i])
+        lib.xrd_debug_kernel_events(None, None)
+    torch.cuda.synchronize()
+    k_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    achieved = R * BYTES_PER_RAY / (k_ms * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': 'xrd::coslam::k_fused<true>',
+                'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak,
+                'peak_source': 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback 6650',
+                'traffic': None, 'kernel_ms': k_ms,
+                'algorithmic_bytes_per_launch': R * BYTES_PER_RAY,
+                'note': 'table (6.56 MB) is L2-resident: DRAM traffic is far below '
+                        'the algorithmic bytes, see profiles/'}
+
+    # ---------------- e2e: through the plugin, host ray bank ---------------
+    algo.config.min_sample_pixels = MAP_CUR
+    h2d = R * 7 * 4 + R * 8 + len(frames) * 16 * 4  # batch rows + ids + poses
+    d2h = 4
+    for i in range(W):
+        optim.zero_grad_all()
+        loss = algo.get_loss(frames, True, i, K)
+        loss.backward()
+        allreduce_grads(params, world)
+        optim.optimizer_step_all(step=i)
+        loss.item()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        optim.zero_grad_all()
+        loss = algo.get_loss(frames, True, i, K)
+        loss.backward()
+        allreduce_grads(params, world)
+        optim.optimizer_step_all(step=i)
+        lv = loss.item()  # D2H read of the step's result
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * R * K / float(t.item())
+
+    # ---------------- tracking iterations (reported beside) ----------------
+    trk = None
+    if rank == 0:
+        n_it = 20
+        topt = algo.setup_optimizers(n_it, [cur], is_mapping=False)
+        for i in range(3):
+            topt.zero_grad_all()
+            algo.get_loss([cur], False, i, n_it).backward()
+            topt.optimizer_step_all(step=i)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(n_it):
+            topt.zero_grad_all()
+            loss = algo.get_loss([cur], False, i, n_it)
+            loss.item()
+            loss.backward()
+            topt.optimizer_step_all(step=i)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        trk = {'tracking_iters_per_s': n_it / dt, 'tracking_rays': algo.config.tracking_sample,
+               'tracking_rays_per_s': n_it * algo.config.tracking_sample / dt}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(sample_rays=1024, iters=3)
+
+    if rank == 0:
+        line = {
+            'metric': 'rays/s (co-slam mapping iteration: sample+march+hash gather+decode+'
+                      'composite+loss+backward+Adam, 640x480 synthetic RGB-D)',
+            'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': ms_total / K, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'co-slam hash-grid(16 lvl x 2 feat, 2^16) + OneBlob16, '
+                                   '640x480 synthetic room, mapping iteration, '
+                                   f'{MAP_KF} keyframe-bank + {MAP_CUR} current-frame rays per GPU, '
+                                   '43 samples/ray, smoothness 31^3, '
+                                   f'{N_KEYFRAMES} keyframes',
+                       'rays_per_step_per_gpu': R, 'parallelism': f'dp{world}',
+                       'l2': 'flushed between timed steps (256 MB write); ray batches differ every step'},
+            'e2e': {'value': e2e_value, 'unit': 'rays/s', 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': d2h,
+                    'path': 'CoSLAM.get_loss (host pinned ray bank, random.sample, H2D) -> '
+                            'loss.backward -> Optimizers.optimizer_step_all -> loss.item()'},
+            'gpu_launches': K * 6,
+            'gpu_launches_note': 'per step: k_sample, k_fused<true>, k_finalize, k_smooth_fwd, '
+                                 'k_smooth_bwd, k_smooth_finalize (torch Adam/elementwise not counted)',
+            'clocks': clk, 'roofline': roofline, 'cpu_baseline': cpu,
+            'iters': {'mapping_iters_per_s': K / (ms_total * 1e-3),
+                      **(trk or {})},
+            'wall_s_value_leg': wall,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------ CPU baseline ---
+def cpu_step_factory(R):
+    """One Co-SLAM mapping iteration of the oracle port on CPU (fwd+bwd+Adam)."""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from oracle.coslam import CoslamOracle
+    from helpers import BOUND, make_rays
+    torch.manual_seed(0)
+    ora = CoslamOracle(BOUND)
+    opt = torch.optim.Adam([
+        {'params': [ora.embed_fn.params], 'lr': 1e-2, 'eps': 1e-15, 'betas': (0.9, 0.99)},
+        {'params': [ora.sdf0.weight, ora.sdf1.weight, ora.col0.weight, ora.col1.weight],
+         'lr': 1e-2, 'weight_decay': 1e-6, 'betas': (0.9, 0.99)}])
+    rays_o, rays_d, ts, td, _ = make_rays(R, seed=0)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        noise = torch.rand(R, 43)
+        _, _, tot = ora.step(rays_o, rays_d, ts, td, noise, True, False,
+                             smooth_rand=torch.rand(2, 3))
+        tot.backward()
+        opt.step()
+        return float(tot.detach())
+    return step
+
+
+def pick_threads(step):
+    """The oracle port is many small torch ops: past a few dozen threads the
+    intra-op pool only adds contention.  Calibrate once on one step each."""
+    cores = os.cpu_count() or 1
+    best, best_t = cores, None
+    for n in sorted({min(cores, c) for c in (8, 16, 32, cores)}):
+        torch.set_num_threads(n)
+        step()
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = n, dt
+    torch.set_num_threads(best)
+    return best
+
+
+def cpu_baseline(sample_rays=1024, iters=3):
+    step = cpu_step_factory(sample_rays)
+    cores = pick_threads(step)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        step()
+    dt = time.perf_counter() - t0
+    return {'value': sample_rays * iters / dt, 'unit': 'rays/s', 'cores': cores,
+            'kind': 'port',
+            'sample': f'{iters} mapping iterations x {sample_rays} rays x 43 samples '
+                      '(oracle/coslam.py torch-CPU port incl. smoothness + Adam)',
+            'ms_per_iter': dt / iters * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    R = 1024
+    step = cpu_step_factory(R)
+    cores = pick_threads(step)
+    K = min(args.steps, 8)
+    W = min(args.warmup, 2)
+    for _ in range(max(W, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step()
+    dt = time.perf_counter() - t0
+    v = R * K / dt
+    line = {
+        'impl': 'reference',
+        'metric': 'rays/s (co-slam mapping iteration: sample+march+hash gather+decode+'
+                  'composite+loss+backward+Adam, 640x480 synthetic RGB-D)',
+        'value': v, 'unit': 'rays/s', 'n_gpus': int(os.environ.get('WORLD_SIZE', '1')),
+        'steps': K, 'warmup': W, 'ms_per_step': dt / K * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'co-slam mapping iteration, CPU oracle port '
+                               '(reference python cannot run on the box), '
+                               f'bounded sample {R} rays x 43 samples per step'},
+        'cpu_baseline': {'value': v, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
+                         'sample': f'{K} steps x {R} rays'},
+        'e2e': {'value': v, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -57,6 +57,13 @@ int xrd_last_cuda_error(void);
 /* 0 if device `dev` is compute capability 10.x, XRD_E_ARCH otherwise. */
 int xrd_check_device(int dev);
 
+/* Measurement hook (bench.py roofline): when both events are non-NULL the NEXT
+ * dominant-kernel launch made from this thread (k_fused of xrd_coslam_step, the
+ * fused render kernels of the other representations) is bracketed by
+ * cudaEventRecord(start)/(stop) on the launching stream.  Pass NULL, NULL to
+ * clear.  The events are cudaEvent_t handles owned by the caller. */
+int xrd_debug_kernel_events(void* start_event, void* stop_event);
+
 /* ---- shared ------------------------------------------------------------ */
 
 /* A batch of rays.  All pointers are DEVICE pointers, fp32, contiguous. */

@@ -86,6 +86,7 @@ SYMBOLS = {
     'xrd_abi_version': (C.c_int, []),
     'xrd_last_cuda_error': (C.c_int, []),
     'xrd_check_device': (C.c_int, [C.c_int]),
+    'xrd_debug_kernel_events': (C.c_int, [vp, vp]),
     'xrd_linspace_f32': (C.c_int, [C.c_float, C.c_float, C.c_int, fp]),
     'xrd_hashgrid_layout':
     (C.c_int, [C.POINTER(XrdHashGrid), C.c_int, C.c_int, C.c_int, C.c_float]),

@@ -1,0 +1,233 @@
+"""Co-SLAM algorithm (host-side mirror of slam/algorithms/coslam.py): global
+keyframe ray bank, per-ray pose gather for bundle adjustment, persistent model
+optimizers -- driving the fused B200 step in joint_encoding.py."""
+from __future__ import annotations
+
+import functools
+import random
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Type
+
+import numpy as np
+import torch
+
+from .algorithm import Algorithm, AlgorithmConfig
+from .common import get_camera_rays, get_rays, get_samples
+from .joint_encoding import JointEncodingConfig
+from .optimizers import AdamOptimizerConfig, Optimizers
+
+
+def _coslam_optimizers():
+    """slam/configs/input_config.py:255-292."""
+    A = AdamOptimizerConfig
+    return {
+        'decoder': {'optimizer': A(lr=1e-2, weight_decay=1e-6, betas=(0.9, 0.99)),
+                    'scheduler': None},
+        'embed_fn': {'optimizer': A(lr=1e-2, eps=1e-15, betas=(0.9, 0.99)),
+                     'scheduler': None},
+        'embed_fn_color': {'optimizer': A(lr=1e-2, eps=1e-15, betas=(0.9, 0.99)),
+                           'scheduler': None},
+        'tracking_pose_r': {'optimizer': A(lr=1e-3), 'scheduler': None},
+        'tracking_pose_t': {'optimizer': A(lr=1e-3), 'scheduler': None},
+        'mapping_pose_r': {'optimizer': A(lr=1e-3, accum_step=5), 'scheduler': None},
+        'mapping_pose_t': {'optimizer': A(lr=1e-3, accum_step=5), 'scheduler': None},
+    }
+
+
+@dataclass
+class CoSLAMConfig(AlgorithmConfig):
+    """coslam.py:17-38 + the co-slam entry of input_config.py:203-296."""
+    _target: Type = field(default_factory=lambda: CoSLAM)
+    model: JointEncodingConfig = field(default_factory=lambda: JointEncodingConfig(
+        cam_depth_trunc=100.0, tcnn_encoding=True))
+    separate_LR: bool = True
+    retain_graph: bool = True
+    rot_rep: str = 'axis_angle'
+    tracking_n_iters: int = 10
+    mapping_n_iters: int = 10
+    mapping_first_n_iters: int = 200
+    keyframe_selection_method: str = 'all'
+    rays_to_save_ratio: float = 0.05
+    tracking_Wedge: int = 20
+    tracking_Hedge: int = 20
+    mapping_sample: int = 2048
+    min_sample_pixels: int = 100
+    tracking_sample: int = 1024
+    ray_batch_size: int = 30000
+    marching_cubes_bound: List[List[float]] = field(
+        default_factory=lambda: [[-2.2, 2.6], [-3.4, 2.1], [-1.4, 2.0]])
+    mapping_bound: List[List[float]] = field(
+        default_factory=lambda: [[-3, 3], [-4, 2.5], [-2, 2.5]])
+    optimizers: Dict[str, Any] = field(default_factory=_coslam_optimizers)
+
+
+class CoSLAM(Algorithm):
+    def __init__(self, config: CoSLAMConfig, camera, device: str) -> None:
+        super().__init__(config, camera, device)
+        self.bounding_box = torch.from_numpy(np.array(self.config.mapping_bound))
+        self.marching_cube_bound = torch.from_numpy(
+            np.array(self.config.marching_cubes_bound))
+        self.model = self.config.model.setup(camera=camera,
+                                             bounding_box=self.bounding_box)
+        self.model.to(device)
+        self.bundle_adjust = True
+        self.num_rays_to_save = int(self.camera.width * self.camera.height *
+                                    self.config.rays_to_save_ratio)
+        self.rays = None  # [n_kf * num_rays_to_save, 7] pinned host memory
+        self.model_optimizers = None
+        self._rng = np.random.default_rng(random.getrandbits(63))
+        self._cam_dirs = get_camera_rays(camera.height, camera.width, camera.fx,
+                                         camera.fy, camera.cx, camera.cy)
+
+    # coslam.py:66-112
+    def setup_optimizers(self, n_iters, optimize_frames, is_mapping=True,
+                         coarse=False) -> Optimizers:
+        cfg = dict(self.config.optimizers)
+        if not is_mapping:
+            return super().setup_optimizers(n_iters, optimize_frames, False)
+        if self.model_optimizers is None:
+            self.model_optimizers = Optimizers(cfg, {**self.model.get_param_groups()})
+        if not self.bundle_adjust or len(optimize_frames) == 1:
+            return self.model_optimizers
+        sep = self.config.separate_LR
+        pose_params = ({'mapping_pose_r': [], 'mapping_pose_t': []}
+                       if sep else {'mapping_pose': []})
+        for kf in optimize_frames[1:]:  # first frame's pose stays fixed
+            if sep:
+                pose_params['mapping_pose_r'].append(kf.get_params()[0])
+                pose_params['mapping_pose_t'].append(kf.get_params()[1])
+            else:
+                pose_params['mapping_pose'].extend(kf.get_params())
+        return Optimizers(cfg, {**pose_params}) + self.model_optimizers
+
+    # coslam.py:114-125
+    def _sample_ids(self, n, bs):
+        """bs distinct indices in [0,n) -- random.sample's distribution
+        (coslam.py:122,147) drawn with numpy's Floyd sampler (O(bs))."""
+        return torch.from_numpy(self._rng.choice(n, size=bs, replace=False,
+                                                 shuffle=False))
+
+    def _frame_rays(self, keyframe):
+        """[H*W,7] (dir_cam, rgb, depth) table of a frame, built once."""
+        t = keyframe.__dict__.get('_ray_table')
+        if t is None:
+            depth = torch.from_numpy(np.asarray(keyframe.depth, dtype=np.float32))
+            color = torch.from_numpy(np.asarray(keyframe.rgb, dtype=np.float32))
+            t = torch.cat([self._cam_dirs, color, depth[..., None]],
+                          dim=-1).reshape(-1, 7)
+            keyframe.__dict__['_ray_table'] = t
+        return t
+
+    def sample_single_keyframe_rays(self, keyframe, bs):
+        rays = self._frame_rays(keyframe)
+        return rays[self._sample_ids(rays.shape[0], bs)]
+
+    def add_keyframe(self, keyframe):
+        with self.lock:
+            rays = self.sample_single_keyframe_rays(keyframe, self.num_rays_to_save)
+            self.rays = rays if self.rays is None else torch.cat([self.rays, rays], 0)
+            if torch.cuda.is_available():
+                self.rays = self.rays.pin_memory()
+            keyframe.rgb = None
+            keyframe.depth = None
+            keyframe.__dict__.pop('_ray_table', None)
+            self.keyframe_graph.append(keyframe)
+
+    def sample_global_rays(self, bs):
+        n_kf = len(self.keyframe_graph)
+        idxs = self._sample_ids(n_kf * self.num_rays_to_save, bs)
+        return self.rays[idxs], idxs // self.num_rays_to_save
+
+    # coslam.py:152-230
+    def get_model_input(self, optimize_frames, is_mapping):
+        cur_frame = optimize_frames[-1]
+        dev = self.device
+        if is_mapping:
+            ids_all, rays_all, poses_all = [], [], []
+            n_cur = self.config.mapping_sample
+            if len(self.keyframe_graph) > 0:
+                sample_rays, frame_ids = self.sample_global_rays(
+                    self.config.mapping_sample)
+                ids_all, rays_all = [frame_ids], [sample_rays]
+                for frame in optimize_frames[:-1]:
+                    pose = frame.get_pose().unsqueeze(0).to(dev)
+                    if frame.fid == 0:
+                        pose = pose.detach()
+                    poses_all.append(pose)
+                n_cur = int(np.maximum(
+                    self.config.mapping_sample // len(self.keyframe_graph),
+                    self.config.min_sample_pixels))
+            rays = self.sample_single_keyframe_rays(cur_frame, n_cur)
+            poses_all.append(cur_frame.get_pose().unsqueeze(0).to(dev))
+            ids_all.append(-torch.ones(len(rays), dtype=torch.int64))
+            rays_all.append(rays)
+            poses_all = torch.cat(poses_all, dim=0)
+            ids_all = torch.cat(ids_all, dim=0).to(dev, non_blocking=True)
+            rays_all = torch.cat(rays_all, dim=0)
+            if dev.type == 'cuda':
+                rays_all = rays_all.pin_memory().to(dev, non_blocking=True)
+            d_cam = rays_all[..., :3]
+            target_s = rays_all[..., 3:6]
+            target_d = rays_all[..., 6:7]
+            R = poses_all[ids_all, :3, :3]  # [N,3,3] per-ray pose gather
+            rays_d = torch.sum(d_cam[:, None, :] * R, -1)
+            rays_o = poses_all[ids_all, :3, -1]
+            first_flag = len(self.keyframe_graph) == 0
+        else:
+            rays_o, rays_d, target_d, target_s = get_samples(
+                self.camera, self.config.tracking_sample, cur_frame.get_pose(),
+                self._frame_tensor(cur_frame, 'depth'),
+                self._frame_tensor(cur_frame, 'rgb'), device=dev,
+                Hedge=self.config.tracking_Hedge,
+                Wedge=self.config.tracking_Wedge)
+            first_flag = False
+        return {
+            'rays_o': rays_o.float(),
+            'rays_d': rays_d.float(),
+            'target_s': target_s.float(),
+            'target_d': target_d.float(),
+            'first': first_flag,
+        }
+
+    def _frame_tensor(self, frame, which):
+        """Upload a frame's image once and keep it resident (row f1)."""
+        key = '_dev_' + which
+        t = frame.__dict__.get(key)
+        if t is None:
+            t = torch.as_tensor(np.asarray(getattr(frame, which),
+                                           dtype=np.float32)).to(self.device)
+            frame.__dict__[key] = t
+        return t
+
+    def get_loss(self, optimize_frames, is_mapping, step=None, n_iters=None,
+                 coarse=False):
+        model_input = self.get_model_input(optimize_frames, is_mapping)
+        model_outputs = self.model(model_input)
+        loss_dict = self.model.get_loss_dict(model_outputs, model_input,
+                                             is_mapping, step)
+        return functools.reduce(torch.add, loss_dict.values())
+
+    # coslam.py:245-289
+    def render_img(self, c2w, gt_depth=None, idx=None):
+        with self.lock, torch.no_grad():
+            dev = self.device
+            rays_o, rays_d = get_rays(self.camera, c2w, device=dev)
+            rays_o, rays_d = rays_o.reshape(-1, 3), rays_d.reshape(-1, 3)
+            if gt_depth is not None:
+                gt_depth = torch.as_tensor(gt_depth, dtype=torch.float32
+                                           ).to(dev).reshape(-1, 1)
+            depths, colors = [], []
+            bs = self.config.ray_batch_size
+            for i in range(0, rays_d.shape[0], bs):
+                batch = {'rays_o': rays_o[i:i + bs], 'rays_d': rays_d[i:i + bs],
+                         'target_s': None, 'target_d': None}
+                if gt_depth is not None:
+                    batch['target_d'] = gt_depth[i:i + bs]
+                out = self.model(batch)
+                depths.append(out['depth'].double())
+                colors.append(out['rgb'])
+            depth = torch.cat(depths, 0).reshape(self.camera.height,
+                                                 self.camera.width)
+            color = torch.cat(colors, 0).reshape(self.camera.height,
+                                                 self.camera.width, 3)
+            return color.cpu().numpy(), depth.cpu().numpy()

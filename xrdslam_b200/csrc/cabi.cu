@@ -7,6 +7,7 @@
 
 namespace xrd {
 thread_local int g_last_cuda_error = 0;
+thread_local cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
 
 int num_sms() {
   static int cached[64] = {0};
@@ -25,6 +26,12 @@ int num_sms() {
 extern "C" int xrd_abi_version(void) { return XRD_ABI_VERSION; }
 
 extern "C" int xrd_last_cuda_error(void) { return xrd::g_last_cuda_error; }
+
+extern "C" int xrd_debug_kernel_events(void* start_event, void* stop_event) {
+  xrd::g_ev_start = (cudaEvent_t)start_event;
+  xrd::g_ev_stop = (cudaEvent_t)stop_event;
+  return XRD_OK;
+}
 
 extern "C" int xrd_check_device(int dev) {
   int major = 0;

@@ -8,6 +8,18 @@
 namespace xrd {
 
 extern thread_local int g_last_cuda_error;
+extern thread_local cudaEvent_t g_ev_start, g_ev_stop;
+
+// bracket the dominant kernel with the caller's events (xrd_debug_kernel_events)
+struct KernelTimer {
+  cudaStream_t s;
+  explicit KernelTimer(cudaStream_t stream) : s(stream) {
+    if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_start, s);
+  }
+  ~KernelTimer() {
+    if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_stop, s);
+  }
+};
 
 inline int cuda_fail(cudaError_t e) {
   g_last_cuda_error = (int)e;

@@ -1015,7 +1015,10 @@ extern "C" int xrd_coslam_step(const XrdRays* rays, const XrdHashGrid* grid,
     XRD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused<true>, threads, smem));
     if (occ < 1) return XRD_E_SHAPE;
     int gridx = P.n_tiles < sms * occ ? P.n_tiles : sms * occ;
-    k_fused<true><<<gridx, threads, smem, stream>>>(P);
+    {
+      KernelTimer kt(stream);
+      k_fused<true><<<gridx, threads, smem, stream>>>(P);
+    }
     XRD_LAUNCH_CHECK();
     FinalizeParams fp{loss_acc, counts, out->losses, R, S, cfg->w_rgb, cfg->w_depth, cfg->w_sdf, cfg->w_fs};
     k_finalize<<<1, 32, 0, stream>>>(fp);
