@@ -123,6 +123,18 @@ typedef struct {
   const float* lin_full;     /* [n_samples]   used when target_d == NULL      */
   uint64_t seed;             /* Philox seed when noise == NULL                */
   int rays_per_tile;         /* 0 = library default                           */
+  int precision;             /* decoder GEMMs on the tensor cores:
+                              * 0 = 3xTF32 everywhere (fp32-level accuracy),
+                              * 1 = 3xTF32 forward (outputs/losses fp32-level),
+                              *     plain TF32 backward (gradients ~1e-3 rel),
+                              * 2 = plain TF32 everywhere                       */
+  /* data-parallel mapping (loss normalisers are batch-global):       */
+  int phase;                 /* 0 = sample+render, 1 = sample only (z_vals and
+                              * counts_out), 2 = render only (z_vals given)     */
+  int n_rays_global;         /* rays of the all-rank batch; 0 = n_rays          */
+  const int* counts_global;  /* DEVICE [3] n_fs, n_sdf, n_valid of the all-rank
+                              * batch; NULL = this call's own counts            */
+  int* counts_out;           /* DEVICE [4], written in phase 1                  */
 } XrdCoslamCfg;
 
 /* Per-ray / per-sample outputs (DEVICE, any may be NULL except losses when
@@ -140,7 +152,9 @@ typedef struct {
 
 /* Gradients of (rgb+depth+sdf+fs) loss scaled by loss_scale[4] per term.
  * d_table and d_w_* are ACCUMULATED into (caller zeroes them: mapping-pose Adam
- * uses accum_step, Q11); d_rays_* are overwritten. */
+ * uses accum_step, Q11); d_rays_* are overwritten.  The five map gradients are
+ * all-or-nothing: all NULL selects the pose-only pass used by tracking (no
+ * scatter, no weight-gradient tiles). */
 typedef struct {
   float* d_table;  /* [n_entries*2] */
   float* d_w_sdf0; /* [32,80] */

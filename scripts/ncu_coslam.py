@@ -4,7 +4,8 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 import torch
 from helpers import coslam_pair, make_rays
 dev = torch.device('cuda:0')
-_, model = coslam_pair(dev, table_amp=1e-2)
+import os
+_, model = coslam_pair(dev, table_amp=1e-2, precision=int(os.environ.get("XRD_PREC", "0")))
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 rays_o, rays_d, ts, td, noise = make_rays(R, seed=1)
 w = model._weights(); tab = model.embed_fn.params

@@ -4,7 +4,8 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 import torch
 from helpers import coslam_pair, make_rays
 dev = torch.device('cuda:0')
-_, model = coslam_pair(dev, table_amp=1e-2)
+import os
+_, model = coslam_pair(dev, table_amp=1e-2, precision=int(os.environ.get("XRD_PREC", "0")))
 for R in [1024, 4096, 16384, 65536]:
     for nr in ([0] if len(sys.argv) < 2 else [int(a) for a in sys.argv[1:]]):
         model.config.rays_per_tile = nr

@@ -138,3 +138,79 @@ def test_strict_nonunit_loss_grad(cuda_dev):
     ld = model.get_loss_dict(model(inp), inp, False, 0)
     (2.0 * ld['rgb_loss'] + 0.5 * ld['sdf_loss'] + ld['fs_loss']).backward()
     assert rel_err(model.embed_fn.params.grad, ora.embed_fn.params.grad) < TOL_GRAD
+
+
+def test_step_parity_mixed_mode(cuda_dev):
+    """precision=1 (bench default): 3xTF32 forward -> outputs and losses at the
+    fp32 tolerance; plain-TF32 backward -> gradients within 5e-3 relative."""
+    ora, model = coslam_pair(cuda_dev, precision=1)
+    R = 512
+    rays_o, rays_d, ts, td, noise = make_rays(R, seed=22)
+    rays_o.requires_grad_(True)
+    rays_d.requires_grad_(True)
+    out_o, ld_o, tot_o = ora.step(rays_o, rays_d, ts, td, noise, False, True)
+    tot_o.backward()
+    ro = rays_o.detach().to(cuda_dev).requires_grad_(True)
+    rd = rays_d.detach().to(cuda_dev).requires_grad_(True)
+    inp = dict(rays_o=ro, rays_d=rd, target_s=ts.to(cuda_dev),
+               target_d=td.to(cuda_dev), first=True, noise=noise.to(cuda_dev))
+    out = model(inp)
+    ld = model.get_loss_dict(out, inp, False, 0)
+    sum(ld.values()).backward()
+    assert torch.equal(out['z_vals'].cpu(), out_o['z_vals'])
+    assert max_abs(out['rgb'], out_o['rgb']) < TOL_OUT
+    assert max_abs(out['depth'], out_o['depth']) < TOL_OUT
+    for k in ld_o:
+        a, b = float(ld[k].detach()), float(ld_o[k].detach())
+        assert abs(a - b) <= TOL_LOSS * max(abs(b), 1e-6), (k, a, b)
+    assert rel_err(model.embed_fn.params.grad, ora.embed_fn.params.grad) < 5e-3
+    assert rel_err(model.decoder.sdf_net.model[0].weight.grad, ora.sdf0.weight.grad) < 5e-3
+    assert rel_err(model.decoder.color_net.model[0].weight.grad, ora.col0.weight.grad) < 5e-3
+    assert rel_err(ro.grad, rays_o.grad) < 5e-3
+    assert rel_err(rd.grad, rays_d.grad) < 5e-3
+
+
+def test_step_parity_tf32_mode(cuda_dev):
+    """precision=2: plain TF32 decoder GEMMs everywhere (10-bit mantissa operands,
+    fp32 accumulate) -- the looser tolerance of SURVEY 8c.  The stress parameters
+    here (|table| <= 0.3, unit-variance weights) are far larger than a trained map."""
+    ora, model = coslam_pair(cuda_dev, precision=2)
+    R = 512
+    rays_o, rays_d, ts, td, noise = make_rays(R, seed=21)
+    out_o, ld_o, tot_o = ora.step(rays_o, rays_d, ts, td, noise, False, True)
+    tot_o.backward()
+    inp = dict(rays_o=rays_o.to(cuda_dev), rays_d=rays_d.to(cuda_dev),
+               target_s=ts.to(cuda_dev), target_d=td.to(cuda_dev), first=True,
+               noise=noise.to(cuda_dev))
+    out = model(inp)
+    ld = model.get_loss_dict(out, inp, False, 0)
+    sum(ld.values()).backward()
+    assert torch.equal(out['z_vals'].cpu(), out_o['z_vals'])
+    assert max_abs(out['rgb'], out_o['rgb']) < 5e-2
+    assert max_abs(out['depth'], out_o['depth']) < 5e-2
+    for k in ld_o:
+        a, b = float(ld[k].detach()), float(ld_o[k].detach())
+        assert abs(a - b) <= 3e-2 * max(abs(b), 1e-6), (k, a, b)
+    ga, gb = model.embed_fn.params.grad.cpu().double(), ora.embed_fn.params.grad.double()
+    cos = float((ga * gb).sum() / (ga.norm() * gb.norm()))
+    assert cos > 0.995
+
+
+def test_tracking_pose_only(cuda_dev):
+    """freeze_map_grads: only d loss / d rays is produced (tracking)."""
+    ora, model = coslam_pair(cuda_dev)
+    model.freeze_map_grads = True
+    rays_o, rays_d, ts, td, noise = make_rays(200, seed=4)
+    rays_o.requires_grad_(True)
+    rays_d.requires_grad_(True)
+    _, _, tot_o = ora.step(rays_o, rays_d, ts, td, noise, False, False)
+    tot_o.backward()
+    ro = rays_o.detach().to(cuda_dev).requires_grad_(True)
+    rd = rays_d.detach().to(cuda_dev).requires_grad_(True)
+    inp = dict(rays_o=ro, rays_d=rd, target_s=ts.to(cuda_dev),
+               target_d=td.to(cuda_dev), first=False, noise=noise.to(cuda_dev))
+    ld = model.get_loss_dict(model(inp), inp, False, 0)
+    sum(ld.values()).backward()
+    assert model.embed_fn.params.grad is None
+    assert rel_err(ro.grad, rays_o.grad) < TOL_GRAD
+    assert rel_err(rd.grad, rays_d.grad) < TOL_GRAD

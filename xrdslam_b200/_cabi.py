@@ -65,7 +65,9 @@ class XrdCoslamCfg(C.Structure):
                 ('w_sdf', C.c_float), ('w_fs', C.c_float),
                 ('lin_uniform', vp), ('lin_range', vp), ('lin_nodepth', vp),
                 ('lin_full', vp), ('seed', C.c_uint64),
-                ('rays_per_tile', C.c_int)]
+                ('rays_per_tile', C.c_int), ('precision', C.c_int),
+                ('phase', C.c_int), ('n_rays_global', C.c_int),
+                ('counts_global', vp), ('counts_out', vp)]
 
 
 class XrdCoslamOut(C.Structure):

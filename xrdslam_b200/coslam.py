@@ -201,6 +201,8 @@ class CoSLAM(Algorithm):
 
     def get_loss(self, optimize_frames, is_mapping, step=None, n_iters=None,
                  coarse=False):
+        # tracking optimises the pose only: no map gradients are needed
+        self.model.freeze_map_grads = not is_mapping
         model_input = self.get_model_input(optimize_frames, is_mapping)
         model_outputs = self.model(model_input)
         loss_dict = self.model.get_loss_dict(model_outputs, model_input,

@@ -11,12 +11,19 @@
 //   k_sample   one warp per ray: merge the 32 uniform + 11 depth-guided samples,
 //              stratified jitter, batch-global counts n_fs / n_sdf / n_valid.
 //   k_fused    persistent CTAs over tiles of NR rays (NR*S points, one thread per
-//              point).  Per-point record in shared memory:
-//                [feat32 | blob48 | geo15 | sdf | h1_32 | c1_32 | raw4]
+//              point for the gathers).  Per-point fp32 record in shared memory:
+//                [feat32 | blob48 | geo15 | sdf | h1_32 | c1_32 | raw4]   (stride 164)
+//              The decoder runs on the tensor cores: every warp pushes its own 32
+//              points through mma.sync m16n8k8 TF32 tiles whose A fragments are read
+//              straight from the records (stride 164 = 4 mod 32 -> conflict-free) and
+//              whose B fragments are the transposed weights staged in shared memory;
+//              3xTF32 error compensation keeps fp32-level parity (cfg.precision).
 //              forward -> per-ray composite + loss gradient (one warp per ray) ->
 //              layer-by-layer backward that overwrites activations with their
-//              gradients in place, a register-blocked tile GEMM per layer for the
-//              weight gradients, red.global.add.v2.f32 scatter for the table.
+//              gradients in place; weight gradients are 16x8 MMA tiles with the
+//              points on the K axis, accumulated in registers for the whole launch;
+//              the hash backward runs in the MMA fragment layout (lane (g,t) owns
+//              level 4*nt+t of rows g, g+8) and scatters with red.global.add.v2.f32.
 //   k_finalize loss accumulators -> the 4 weighted loss terms.
 #include <math.h>
 
@@ -30,13 +37,6 @@ constexpr int kBins = 16;
 // record layout (floats); stride == 4 (mod 32) keeps 128-bit LDS conflict-free
 constexpr int R_FEAT = 0, R_BLOB = 32, R_GEO = 80, R_SDF = 95, R_H1 = 96, R_C1 = 128,
               R_RAW = 160, REC = 164;
-// transposed weights in shared memory (floats)
-constexpr int W0T = 0;                 // [80][32]  w_sdf0^T
-constexpr int W1T = W0T + 80 * 32;     // [32][16]  w_sdf1^T, cols = (geo0..14, sdf)
-constexpr int WC0T = W1T + 32 * 16;    // [64][32]  w_col0^T, row 63 = 0
-constexpr int WC1T = WC0T + 64 * 32;   // [32][4]   w_col1^T, col 3 = 0
-constexpr int W_TOTAL = WC1T + 32 * 4; // 5248 floats
-
 struct GridDev {
   float scale[kL];
   uint32_t res[kL], size[kL], offset[kL], hashed[kL];
@@ -47,7 +47,7 @@ struct GridDev {
 
 struct Params {
   // rays
-  int R, S;
+  int R, S, Rg;  // Rg: rays of the global (all-rank) batch the loss means run over
   const float *rays_o, *rays_d, *target_s, *target_d;
   const float* z_vals;  // [R,S] (written by k_sample)
   // grid + mlp
@@ -152,17 +152,24 @@ __global__ void __launch_bounds__(128) k_sample(SampleParams p) {
 }
 
 // --------------------------------------------------------------- encoding ---
+// out-of-bound points on dense levels only (rare): keep the division sequence out of line
+__device__ __noinline__ uint32_t slow_mod(uint32_t a, uint32_t b) { return a % b; }
+
 __device__ __forceinline__ uint32_t grid_index(const GridDev& g, int l, uint32_t x,
                                                uint32_t y, uint32_t z) {
-  const uint32_t res = g.res[l], size = g.size[l];
+  const uint32_t size = g.size[l];
   uint32_t index;
   if (g.hashed[l]) {
     index = x ^ (y * 2654435761u) ^ (z * 805459861u);
   } else {
     // dense stride walk (stride <= size is true for all three dims on a dense level)
+    const uint32_t res = g.res[l];
     index = x + y * res + z * res * res;
   }
-  return index % size + g.offset[l];
+  // index % size: sizes of hashed levels are powers of two; in-range dense cells are < size
+  if ((size & (size - 1)) == 0) index &= size - 1;
+  else if (index >= size) index = slow_mod(index, size);
+  return index + g.offset[l];
 }
 
 __device__ __forceinline__ void pos_fract(float x, float scale, float& w, uint32_t& c) {
@@ -177,22 +184,62 @@ __device__ __forceinline__ float normalise(float p, double bmin, double bmax) {
   return (float)(((double)p - bmin) / (bmax - bmin));
 }
 
-__device__ __forceinline__ float quartic_cdf(float u_in, float s) {
-  float u = u_in * s, u2 = u * u, u4 = u2 * u2;
-  float v = 0.9375f * u * (1.f - (2.f / 3.f) * u2 + 0.2f * u4) + 0.5f;
+// quartic kernel cdf / pdf in bin units t (|t| <= 1 inside the kernel support)
+__device__ __forceinline__ float qcdf(float t) {
+  float t2 = t * t;
+  float v = 0.9375f * t * (1.f - (2.f / 3.f) * t2 + 0.2f * t2 * t2) + 0.5f;
   return fminf(fmaxf(v, 0.f), 1.f);
 }
-__device__ __forceinline__ float cdf3(float d, float s) {
-  return quartic_cdf(d, s) + quartic_cdf(d - 1.f, s) + quartic_cdf(d + 1.f, s);
+__device__ __forceinline__ float qpdf(float t) {
+  float q = 1.f - t * t;
+  return (fabsf(t) < 1.f) ? 0.9375f * q * q : 0.f;
 }
-// derivative of cdf3 w.r.t. its argument (quartic kernel, zero where clamped)
-__device__ __forceinline__ float quartic_pdf(float u_in, float s) {
-  float u = u_in * s;
-  float t = 1.f - u * u;
-  return (fabsf(u) < 1.f) ? 0.9375f * s * t * t : 0.f;
+
+// OneBlob, sparse form.  out[b] = sum_{s in -1,0,1} K(e_{b+1}-x+s) - K(e_b-x+s); for image s
+// only bins b0-1, b0, b0+1 (b0 = floor(16 (x-s))) are non-zero:
+//   cdf(-f), cdf(1-f)-cdf(-f), 1-cdf(1-f)   with f = 16 (x-s) - b0.
+__device__ __forceinline__ void blob_forward(const float xn[3], float* __restrict__ rec) {
+#pragma unroll
+  for (int q = 0; q < 12; ++q)
+    *reinterpret_cast<float4*>(rec + R_BLOB + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+#pragma unroll
+    for (int s = -1; s <= 1; ++s) {
+      const float u = (xn[d] - (float)s) * (float)kBins;
+      const float fl = floorf(u);
+      if (fl < -1.f || fl > (float)kBins) continue;
+      const int b0 = (int)fl;
+      const float f = u - fl;
+      const float c0 = qcdf(-f), c1 = qcdf(1.f - f);
+      float* o = rec + R_BLOB + d * kBins;
+      if (b0 - 1 >= 0 && b0 - 1 < kBins) o[b0 - 1] += c0;
+      if (b0 >= 0 && b0 < kBins) o[b0] += c1 - c0;
+      if (b0 + 1 >= 0 && b0 + 1 < kBins) o[b0 + 1] += 1.f - c1;
+    }
+  }
 }
-__device__ __forceinline__ float pdf3(float d, float s) {
-  return quartic_pdf(d, s) + quartic_pdf(d - 1.f, s) + quartic_pdf(d + 1.f, s);
+
+// dx[d] += sum_b dblob[d*16+b] * d out_b / dx  (dblob read through the functor)
+template <typename F>
+__device__ __forceinline__ void blob_backward(const float xn[3], F dblob, float dx[3]) {
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    float acc = 0.f;
+#pragma unroll
+    for (int s = -1; s <= 1; ++s) {
+      const float u = (xn[d] - (float)s) * (float)kBins;
+      const float fl = floorf(u);
+      if (fl < -1.f || fl > (float)kBins) continue;
+      const int b0 = (int)fl;
+      const float f = u - fl;
+      const float p0 = qpdf(-f), p1 = qpdf(1.f - f);  // d cdf(-f)/dx = -16 p0, d cdf(1-f)/dx = -16 p1
+      if (b0 - 1 >= 0 && b0 - 1 < kBins) acc -= dblob(d * kBins + b0 - 1) * p0;
+      if (b0 >= 0 && b0 < kBins) acc += dblob(d * kBins + b0) * (p0 - p1);
+      if (b0 + 1 >= 0 && b0 + 1 < kBins) acc += dblob(d * kBins + b0 + 1) * p1;
+    }
+    dx[d] = fmaf(acc, (float)kBins, dx[d]);
+  }
 }
 
 __device__ __forceinline__ void encode_point(const Params& P, const float xn[3],
@@ -200,7 +247,11 @@ __device__ __forceinline__ void encode_point(const Params& P, const float xn[3],
   const float2* __restrict__ tab = reinterpret_cast<const float2*>(P.table);
 #pragma unroll 4
   for (int l = 0; l < kL; ++l) {
-    if (l >= P.g.n_levels) break;
+    if (l >= P.g.n_levels) {
+      rec[R_FEAT + 2 * l] = 0.f;
+      rec[R_FEAT + 2 * l + 1] = 0.f;
+      continue;
+    }
     float w[3];
     uint32_t c[3];
     pos_fract(xn[0], P.g.scale[l], w[0], c[0]);
@@ -221,236 +272,235 @@ __device__ __forceinline__ void encode_point(const Params& P, const float xn[3],
       f0 = fmaf(wk, v[k].x, f0);
       f1 = fmaf(wk, v[k].y, f1);
     }
-    rec[R_FEAT + 2 * l] = f0;
-    rec[R_FEAT + 2 * l + 1] = f1;
+    *reinterpret_cast<float2*>(rec + R_FEAT + 2 * l) = make_float2(f0, f1);
   }
-  // OneBlob: out[d*16+b] = cdf3(e_{b+1}-x) - cdf3(e_b-x)
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    float prev = cdf3(0.f - xn[d], (float)kBins);
-#pragma unroll
-    for (int b = 0; b < kBins; ++b) {
-      float e = (float)(b + 1) * (1.f / kBins);
-      float cur = cdf3(e - xn[d], (float)kBins);
-      rec[R_BLOB + d * kBins + b] = cur - prev;
-      prev = cur;
-    }
-  }
+  blob_forward(xn, rec);
 }
 
-// d loss / d x (normalised coords) through the OneBlob, given dblob[48] via a functor
-template <typename F>
-__device__ __forceinline__ void blob_backward(const float xn[3], F dblob, float dx[3]) {
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    float prev = pdf3(0.f - xn[d], (float)kBins);
-    float acc = 0.f;
-#pragma unroll
-    for (int b = 0; b < kBins; ++b) {
-      float e = (float)(b + 1) * (1.f / kBins);
-      float cur = pdf3(e - xn[d], (float)kBins);
-      // d out_b / dx = -(pdf(e_{b+1}-x) - pdf(e_b - x))
-      acc = fmaf(dblob(d * kBins + b), prev - cur, acc);
-      prev = cur;
-    }
-    dx[d] += acc;
-  }
-}
-
-// scatter dfeat into the table gradient; optionally d loss / d x through the trilerp
-__device__ __forceinline__ void hash_backward(const Params& P, const float xn[3],
-                                              const float* dfeat, bool need_dx,
-                                              float dx[3]) {
+// one (point, level) item of the hash backward: scatter (g0,g1), optional d/dx.
+// Deliberately not inlined: 16 call sites per warp tile, and instruction-cache
+// footprint is what bounds this kernel (see profiles/).
+__device__ __noinline__ float3 hash_backward_item(const Params& P, int l, float x0, float x1,
+                                                  float x2, float g0, float g1, bool need_dx,
+                                                  bool scatter) {
   const float2* __restrict__ tab = reinterpret_cast<const float2*>(P.table);
-#pragma unroll 2
-  for (int l = 0; l < kL; ++l) {
-    if (l >= P.g.n_levels) break;
-    const float g0 = dfeat[2 * l], g1 = dfeat[2 * l + 1];
-    float w[3];
-    uint32_t c[3];
-    const float sc = P.g.scale[l];
-    pos_fract(xn[0], sc, w[0], c[0]);
-    pos_fract(xn[1], sc, w[1], c[1]);
-    pos_fract(xn[2], sc, w[2], c[2]);
-    uint32_t idx[8];
+  float w[3];
+  uint32_t c[3];
+  float dx[3] = {0.f, 0.f, 0.f};
+  const float sc = P.g.scale[l];
+  pos_fract(x0, sc, w[0], c[0]);
+  pos_fract(x1, sc, w[1], c[1]);
+  pos_fract(x2, sc, w[2], c[2]);
+  uint32_t idx[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      idx[k] = grid_index(P.g, l, c[0] + (k & 1), c[1] + ((k >> 1) & 1),
-                          c[2] + ((k >> 2) & 1));
-    if (need_dx) {
-      float t[8];  // <table entry, dfeat>
+  for (int k = 0; k < 8; ++k)
+    idx[k] = grid_index(P.g, l, c[0] + (k & 1), c[1] + ((k >> 1) & 1), c[2] + ((k >> 2) & 1));
+  if (need_dx) {
+    float t[8];  // <table entry, dfeat>
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float2 v = __ldg(&tab[idx[k]]);
-        t[k] = v.x * g0 + v.y * g1;
-      }
-      const float w0 = w[0], w1 = w[1], w2 = w[2];
-      // d/dw0: sum over (y,z) corners of weight_yz * (t[x=1] - t[x=0])
-      float d0 = (1 - w1) * (1 - w2) * (t[1] - t[0]) + w1 * (1 - w2) * (t[3] - t[2]) +
-                 (1 - w1) * w2 * (t[5] - t[4]) + w1 * w2 * (t[7] - t[6]);
-      float d1 = (1 - w0) * (1 - w2) * (t[2] - t[0]) + w0 * (1 - w2) * (t[3] - t[1]) +
-                 (1 - w0) * w2 * (t[6] - t[4]) + w0 * w2 * (t[7] - t[5]);
-      float d2 = (1 - w0) * (1 - w1) * (t[4] - t[0]) + w0 * (1 - w1) * (t[5] - t[1]) +
-                 (1 - w0) * w1 * (t[6] - t[2]) + w0 * w1 * (t[7] - t[3]);
-      dx[0] = fmaf(sc, d0, dx[0]);
-      dx[1] = fmaf(sc, d1, dx[1]);
-      dx[2] = fmaf(sc, d2, dx[2]);
+    for (int k = 0; k < 8; ++k) {
+      float2 v = __ldg(&tab[idx[k]]);
+      t[k] = v.x * g0 + v.y * g1;
     }
-    if (g0 != 0.f || g1 != 0.f) {
+    const float w0 = w[0], w1 = w[1], w2 = w[2];
+    float d0 = (1 - w1) * (1 - w2) * (t[1] - t[0]) + w1 * (1 - w2) * (t[3] - t[2]) +
+               (1 - w1) * w2 * (t[5] - t[4]) + w1 * w2 * (t[7] - t[6]);
+    float d1 = (1 - w0) * (1 - w2) * (t[2] - t[0]) + w0 * (1 - w2) * (t[3] - t[1]) +
+               (1 - w0) * w2 * (t[6] - t[4]) + w0 * w2 * (t[7] - t[5]);
+    float d2 = (1 - w0) * (1 - w1) * (t[4] - t[0]) + w0 * (1 - w1) * (t[5] - t[1]) +
+               (1 - w0) * w1 * (t[6] - t[2]) + w0 * w1 * (t[7] - t[3]);
+    dx[0] = fmaf(sc, d0, dx[0]);
+    dx[1] = fmaf(sc, d1, dx[1]);
+    dx[2] = fmaf(sc, d2, dx[2]);
+  }
+  if (scatter) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float wk = ((k & 1) ? w[0] : 1.f - w[0]) * ((k & 2) ? w[1] : 1.f - w[1]) *
-                   ((k & 4) ? w[2] : 1.f - w[2]);
-        red_add_v2(P.d_table + 2 * (size_t)idx[k], wk * g0, wk * g1);
+    for (int k = 0; k < 8; ++k) {
+      float wk = ((k & 1) ? w[0] : 1.f - w[0]) * ((k & 2) ? w[1] : 1.f - w[1]) *
+                 ((k & 4) ? w[2] : 1.f - w[2]);
+      red_add_v2(P.d_table + 2 * (size_t)idx[k], wk * g0, wk * g1);
+    }
+  }
+  return make_float3(dx[0], dx[1], dx[2]);
+}
+
+// ------------------------------------------------------- tensor-core GEMMs ---
+// mma.sync m16n8k8 tf32 (fp32 accumulate).  PREC3 = 3xTF32 error-compensated split:
+// x = big + small, d += a_s*b_b + a_b*b_s + a_b*b_b  -> fp32-level accuracy.
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4],
+                                         const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+      "{%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// Operand preparation.  The tensor core reads only the upper 19 bits of a .tf32 register, so
+// plain TF32 mode feeds the fp32 bits unchanged (truncation, |err| <= 2^-10 rel).  In 3xTF32
+// mode big = x with the low 13 mantissa bits cleared (exactly what the hardware would see) and
+// small = x - big (exact in fp32); small's own truncation error is second order (2^-20).
+template <bool PREC3>
+struct FragA {
+  uint32_t big[4], small[4];
+  __device__ __forceinline__ void set(const float (&v)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (PREC3) {
+        big[i] = __float_as_uint(v[i]) & 0xffffe000u;
+        small[i] = __float_as_uint(v[i] - __uint_as_float(big[i]));
+      } else {
+        big[i] = __float_as_uint(v[i]);
       }
+    }
+  }
+};
+template <bool PREC3>
+struct FragB {
+  uint32_t big[2], small[2];
+  __device__ __forceinline__ void set(float v0, float v1) {
+    if (PREC3) {
+      big[0] = __float_as_uint(v0) & 0xffffe000u;
+      big[1] = __float_as_uint(v1) & 0xffffe000u;
+      small[0] = __float_as_uint(v0 - __uint_as_float(big[0]));
+      small[1] = __float_as_uint(v1 - __uint_as_float(big[1]));
+    } else {
+      big[0] = __float_as_uint(v0);
+      big[1] = __float_as_uint(v1);
+    }
+  }
+};
+template <bool PREC3>
+__device__ __forceinline__ void mma(float (&d)[4], const FragA<PREC3>& a, const FragB<PREC3>& b) {
+  if (PREC3) {
+    mma_tf32(d, a.small, b.big);
+    mma_tf32(d, a.big, b.small);
+  }
+  mma_tf32(d, a.big, b.big);
+}
+
+// C[mt][nt] += A * B for the 32 points of this warp (2 m-tiles of 16 rows).
+//   A[row][k]   = wrec[row*REC + aoff + k]              (activations / gradients, records)
+//   B[k][n]     = TRANS ? w[(noff+n)*ld + koff + k] : w[(koff+k)*ld + noff + n]
+template <int KS, int NT, bool TRANS, bool PREC3>
+__device__ __forceinline__ void warp_gemm(const float* __restrict__ wrec, int aoff,
+                                          const float* __restrict__ w, int ld, int koff,
+                                          int noff, float (&c)[2][NT][4]) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll 1
+  for (int ks = 0; ks < KS; ++ks) {
+    FragA<PREC3> a[2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const float* r0 = wrec + (mt * 16 + g) * REC + aoff + ks * 8 + t;
+      const float v[4] = {r0[0], r0[8 * REC], r0[4], r0[8 * REC + 4]};
+      a[mt].set(v);
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      FragB<PREC3> b;
+      const int k0 = koff + ks * 8 + t, n0 = noff + nt * 8 + g;
+      if (TRANS) b.set(w[n0 * ld + k0], w[n0 * ld + k0 + 4]);
+      else b.set(w[k0 * ld + n0], w[(k0 + 4) * ld + n0]);
+      mma<PREC3>(c[0][nt], a[0], b);
+      mma<PREC3>(c[1][nt], a[1], b);
     }
   }
 }
 
-// ------------------------------------------------------------------- MLP ---
-// h1 = relu(W0 x), h = W1 h1, c1 = relu(WC0 [blob, geo]), rgb = WC1 c1
-__device__ __forceinline__ void mlp_forward(const float* __restrict__ sw,
-                                            float* __restrict__ rec) {
-  float acc[32];
+template <int NT>
+__device__ __forceinline__ void zero_c(float (&c)[2][NT][4]) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-#pragma unroll 2
-  for (int i4 = 0; i4 < 80; i4 += 4) {
-    const float4 xv = *reinterpret_cast<const float4*>(rec + R_FEAT + i4);
-    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int ii = 0; ii < 4; ++ii) {
-      const float4* wr = reinterpret_cast<const float4*>(sw + W0T + (i4 + ii) * 32);
+    for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        const float4 w = wr[j4];
-        acc[4 * j4 + 0] = fmaf(xs[ii], w.x, acc[4 * j4 + 0]);
-        acc[4 * j4 + 1] = fmaf(xs[ii], w.y, acc[4 * j4 + 1]);
-        acc[4 * j4 + 2] = fmaf(xs[ii], w.z, acc[4 * j4 + 2]);
-        acc[4 * j4 + 3] = fmaf(xs[ii], w.w, acc[4 * j4 + 3]);
-      }
-    }
-  }
-  float h[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) h[j] = 0.f;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const float a = fmaxf(acc[i], 0.f);
-    rec[R_H1 + i] = a;
-    const float4* wr = reinterpret_cast<const float4*>(sw + W1T + i * 16);
-#pragma unroll
-    for (int j4 = 0; j4 < 4; ++j4) {
-      const float4 w = wr[j4];
-      h[4 * j4 + 0] = fmaf(a, w.x, h[4 * j4 + 0]);
-      h[4 * j4 + 1] = fmaf(a, w.y, h[4 * j4 + 1]);
-      h[4 * j4 + 2] = fmaf(a, w.z, h[4 * j4 + 2]);
-      h[4 * j4 + 3] = fmaf(a, w.w, h[4 * j4 + 3]);
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < 16; ++j) rec[R_GEO + j] = h[j];  // geo0..14, sdf
-  // colour net: inputs rec[32..96) = blob48, geo15, (sdf slot: weight row 63 == 0)
-#pragma unroll
-  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-#pragma unroll 2
-  for (int i4 = 0; i4 < 64; i4 += 4) {
-    const float4 xv = *reinterpret_cast<const float4*>(rec + R_BLOB + i4);
-    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-    for (int ii = 0; ii < 4; ++ii) {
-      const float4* wr = reinterpret_cast<const float4*>(sw + WC0T + (i4 + ii) * 32);
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        const float4 w = wr[j4];
-        acc[4 * j4 + 0] = fmaf(xs[ii], w.x, acc[4 * j4 + 0]);
-        acc[4 * j4 + 1] = fmaf(xs[ii], w.y, acc[4 * j4 + 1]);
-        acc[4 * j4 + 2] = fmaf(xs[ii], w.z, acc[4 * j4 + 2]);
-        acc[4 * j4 + 3] = fmaf(xs[ii], w.w, acc[4 * j4 + 3]);
-      }
-    }
-  }
-  float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const float a = fmaxf(acc[i], 0.f);
-    rec[R_C1 + i] = a;
-    const float4 w = *reinterpret_cast<const float4*>(sw + WC1T + i * 4);
-    r0 = fmaf(a, w.x, r0);
-    r1 = fmaf(a, w.y, r1);
-    r2 = fmaf(a, w.z, r2);
-  }
-  rec[R_RAW + 0] = r0;
-  rec[R_RAW + 1] = r1;
-  rec[R_RAW + 2] = r2;
-  rec[R_RAW + 3] = h[15];
+      for (int i = 0; i < 4; ++i) c[mt][nt][i] = 0.f;
 }
 
-// dWT[(4*ib+ii)*ld + 4*jb+jj] += sum_p A[p][4*ib+ii] * B[p][4*jb+jj]
-__device__ __forceinline__ void tile_gemm(const float* __restrict__ recs, int n_pts,
-                                          int aoff, int nIb, int boff, int nJb,
-                                          float* __restrict__ dwt, int ld) {
-  for (int b = threadIdx.x; b < nIb * nJb; b += blockDim.x) {
-    const int jb = b % nJb, ib = b / nJb;
-    float acc[16];
+// store C (32 rows x 8*NT cols) into the records at column offset coff (float2 per row pair)
+template <int NT, bool RELU>
+__device__ __forceinline__ void store_c(float* __restrict__ wrec, int coff,
+                                        const float (&c)[2][NT][4]) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) acc[q] = 0.f;
-    const float* pa = recs + aoff + 4 * ib;
-    const float* pb = recs + boff + 4 * jb;
-#pragma unroll 4
-    for (int p = 0; p < n_pts; ++p) {
-      const float4 a = *reinterpret_cast<const float4*>(pa + p * REC);
-      const float4 bb = *reinterpret_cast<const float4*>(pb + p * REC);
-      const float av[4] = {a.x, a.y, a.z, a.w};
-      const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) acc[ii * 4 + jj] = fmaf(av[ii], bv[jj], acc[ii * 4 + jj]);
+    for (int nt = 0; nt < NT; ++nt) {
+      float v0 = c[mt][nt][0], v1 = c[mt][nt][1], v2 = c[mt][nt][2], v3 = c[mt][nt][3];
+      if (RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+      float* r0 = wrec + (mt * 16 + g) * REC + coff + nt * 8 + 2 * t;
+      *reinterpret_cast<float2*>(r0) = make_float2(v0, v1);
+      *reinterpret_cast<float2*>(r0 + 8 * REC) = make_float2(v2, v3);
     }
-    float* o = dwt + (4 * ib) * ld + 4 * jb;
-#pragma unroll
-    for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) o[ii * ld + jj] += acc[ii * 4 + jj];
+}
+
+// weights in shared memory: [in][out] with padded row strides (conflict-free B fragments)
+constexpr int LD0 = 40, LD1 = 24, LDC0 = 40, LDC1 = 8;
+constexpr int SW0 = 0;                     // [80][40]  w_sdf0^T
+constexpr int SW1 = SW0 + 80 * LD0;        // [32][24]  w_sdf1^T, cols = (geo0..14, sdf)
+constexpr int SWC0 = SW1 + 32 * LD1;       // [64][40]  w_col0^T, row 63 = 0
+constexpr int SWC1 = SWC0 + 64 * LDC0;     // [32][8]   w_col1^T, cols 3..7 = 0
+constexpr int SW_TOTAL = SWC1 + 32 * LDC1; // 6784 floats
+
+// weight-gradient tiles (16 in-features x 8 out-units each), global order
+//   [0,2) d w_col1   [2,18) d w_col0   [18,22) d w_sdf1   [22,42) d w_sdf0
+constexpr int DW_TILES = 42;
+
+template <bool PREC3>
+__device__ __forceinline__ void dw_tile(const float* __restrict__ recs, int npts, int aoff,
+                                        int boff, float (&acc)[4]) {
+  // acc[16 x 8] += sum_p A[p][aoff + m] * B[p][boff + n]; k-slot t <-> point 2t, t+4 <-> 2t+1
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll 2
+  for (int k0 = 0; k0 < npts; k0 += 8) {
+    const float* p0 = recs + (k0 + 2 * t) * REC;
+    const float* p1 = p0 + REC;
+    const float va[4] = {p0[aoff + g], p0[aoff + g + 8], p1[aoff + g], p1[aoff + g + 8]};
+    FragA<PREC3> a;
+    a.set(va);
+    FragB<PREC3> b;
+    b.set(p0[boff + g], p1[boff + g]);
+    mma<PREC3>(acc, a, b);
   }
 }
 
 // ----------------------------------------------------------------- fused ---
-template <bool BWD>
+template <bool BWD, bool PREC3, bool BPREC3, int SLOTS>
 __global__ void __launch_bounds__(256) k_fused(const Params P) {
   extern __shared__ __align__(16) float smem[];
-  float* sw = smem;                              // W_TOTAL
-  float* sdw = sw + W_TOTAL;                     // W_TOTAL (BWD only)
-  float* recs = sdw + (BWD ? W_TOTAL : 0);       // blockDim.x * REC
-  float* zbuf = recs + blockDim.x * REC;         // NR*S  z values
-  float* rayacc = zbuf + P.NR * P.S;             // NR*8  d_rays accumulators
+  float* sw = smem;                            // SW_TOTAL
+  float* recs = sw + SW_TOTAL;                 // (blockDim.x + 8) * REC
+  float* zbuf = recs + (blockDim.x + 8) * REC; // NR*S z values
+  float* sgb = zbuf + P.NR * P.S;              // NR*S sigma(sdf/trunc)
+  float* ub = sgb + P.NR * P.S;                // NR*S unnormalised weights
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
   const int nwarps = blockDim.x >> 5;
   const int S = P.S;
 
-  // stage transposed weights
+  // stage transposed weights (zero padding included)
+  for (int q = tid; q < SW_TOTAL; q += blockDim.x) sw[q] = 0.f;
+  __syncthreads();
   for (int q = tid; q < 80 * 32; q += blockDim.x) {
     int i = q / 32, j = q % 32;
-    sw[W0T + q] = P.w_sdf0[j * 80 + i];
+    sw[SW0 + i * LD0 + j] = P.w_sdf0[j * 80 + i];
   }
   for (int q = tid; q < 32 * 16; q += blockDim.x) {
-    int i = q / 16, jp = q % 16;           // jp: geo0..14 -> torch out 1..15, jp 15 -> out 0
+    int i = q / 16, jp = q % 16;  // jp: geo0..14 -> torch out 1..15, jp 15 -> out 0 (sdf)
     int jt = (jp + 1) & 15;
-    sw[W1T + q] = P.w_sdf1[jt * 32 + i];
+    sw[SW1 + i * LD1 + jp] = P.w_sdf1[jt * 32 + i];
   }
-  for (int q = tid; q < 64 * 32; q += blockDim.x) {
+  for (int q = tid; q < 63 * 32; q += blockDim.x) {
     int i = q / 32, j = q % 32;
-    sw[WC0T + q] = (i < 63) ? P.w_col0[j * 63 + i] : 0.f;
+    sw[SWC0 + i * LDC0 + j] = P.w_col0[j * 63 + i];
   }
-  for (int q = tid; q < 32 * 4; q += blockDim.x) {
-    int i = q / 4, k = q % 4;
-    sw[WC1T + q] = (k < 3) ? P.w_col1[k * 32 + i] : 0.f;
+  for (int q = tid; q < 32 * 3; q += blockDim.x) {
+    int i = q / 3, k = q % 3;
+    sw[SWC1 + i * LDC1 + k] = P.w_col1[k * 32 + i];
   }
-  if (BWD)
-    for (int q = tid; q < W_TOTAL; q += blockDim.x) sdw[q] = 0.f;
+  // the 8 pad records after the tile stay zero for the whole kernel (k-step overrun of dw_tile)
+  for (int q = tid; q < 8 * REC; q += blockDim.x) recs[blockDim.x * REC + q] = 0.f;
 
-  // batch-global normalisers (utils.py:126-130), float32 like torch's int/int division
   float fs_w = 0.f, sdf_w = 0.f, inv_nvalid = 0.f;
   if (BWD) {
     const float n_fs = (float)P.counts[0], n_sdf = (float)P.counts[1];
@@ -459,22 +509,31 @@ __global__ void __launch_bounds__(256) k_fused(const Params P) {
     sdf_w = 1.0f - n_sdf / n;
     inv_nvalid = 1.0f / (float)P.counts[2];
   }
-  double l_rgb = 0.0, l_depth = 0.0, l_sdf = 0.0, l_fs = 0.0;  // lane-0-of-warp partials
+  double l_rgb = 0.0, l_depth = 0.0, l_sdf = 0.0, l_fs = 0.0;
+  float dwacc[SLOTS][4];
+#pragma unroll
+  for (int j = 0; j < SLOTS; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dwacc[j][i] = 0.f;
   __syncthreads();
 
   float* rec = recs + tid * REC;
+  float* wrec = recs + (warp * 32) * REC;  // this warp's 32 records
+  const bool need_dx = BWD && ((P.d_rays_o != nullptr) || (P.d_rays_d != nullptr));
+  const bool map_grads = BWD && (P.d_table != nullptr);
+
   for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
     const int r0 = tile * P.NR;
     const int nr = min(P.NR, P.R - r0);
     const int npts = nr * S;
     const bool active = tid < npts;
+    const bool warp_active = warp * 32 < npts;
     const int rl = active ? tid / S : 0;
     const int k = active ? tid - rl * S : 0;
     const int r = r0 + rl;
     float xn[3] = {0.f, 0.f, 0.f};
     float zv = 0.f;
-    if (tid < nr * 8) rayacc[tid] = 0.f;
-    // ---------------- phase 1: per-point forward --------------------------
+    // ---------------- phase 1: forward -------------------------------------
     if (active) {
       zv = P.z_vals[(size_t)r * S + k];
       zbuf[tid] = zv;
@@ -484,7 +543,55 @@ __global__ void __launch_bounds__(256) k_fused(const Params P) {
         xn[d] = normalise(pt, P.g.bmin[d], P.g.bmax[d]);
       }
       encode_point(P, xn, rec);
-      mlp_forward(sw, rec);
+    } else {
+      // inactive rows must read as zero in every GEMM (k-dimension of the dW tiles)
+#pragma unroll 1
+      for (int q = 0; q < REC; q += 4)
+        *reinterpret_cast<float4*>(rec + q) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+    if (warp_active) {
+      {  // h1 = relu(x W0^T)
+        float c[2][4][4];
+        zero_c<4>(c);
+        warp_gemm<10, 4, false, PREC3>(wrec, R_FEAT, sw + SW0, LD0, 0, 0, c);
+        store_c<4, true>(wrec, R_H1, c);
+      }
+      __syncwarp();
+      {  // [geo, sdf] = h1 W1^T
+        float c[2][2][4];
+        zero_c<2>(c);
+        warp_gemm<4, 2, false, PREC3>(wrec, R_H1, sw + SW1, LD1, 0, 0, c);
+        store_c<2, false>(wrec, R_GEO, c);
+      }
+      __syncwarp();
+      {  // c1 = relu([blob, geo, (sdf: zero weight row)] Wc0^T)
+        float c[2][4][4];
+        zero_c<4>(c);
+        warp_gemm<8, 4, false, PREC3>(wrec, R_BLOB, sw + SWC0, LDC0, 0, 0, c);
+        store_c<4, true>(wrec, R_C1, c);
+      }
+      __syncwarp();
+      {  // rgb logits = c1 Wc1^T (cols 0..2 of an 8-wide tile)
+        float c[2][1][4];
+        zero_c<1>(c);
+        warp_gemm<4, 1, false, PREC3>(wrec, R_C1, sw + SWC1, LDC1, 0, 0, c);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          float* q0 = wrec + (mt * 16 + g) * REC + R_RAW;
+          if (t == 0) {
+            q0[0] = c[mt][0][0]; q0[1] = c[mt][0][1];
+            q0[8 * REC] = c[mt][0][2]; q0[8 * REC + 1] = c[mt][0][3];
+          } else if (t == 1) {
+            q0[2] = c[mt][0][0];
+            q0[8 * REC + 2] = c[mt][0][2];
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (active) {
+      rec[R_RAW + 3] = rec[R_SDF];
       if (P.raw) {
         float4 rw = *reinterpret_cast<const float4*>(rec + R_RAW);
         *reinterpret_cast<float4*>(P.raw + ((size_t)r * S + k) * 4) = rw;
@@ -492,26 +599,35 @@ __global__ void __launch_bounds__(256) k_fused(const Params P) {
     }
     __syncthreads();
     // ---------------- phase 2: per-ray composite, loss, d loss / d raw ----
+    // per sample the five sigmoids are evaluated once: colours overwrite the rgb logits in
+    // RAW[0..2]; sigma(s/tr) and the unnormalised weight u live in sgb / ub.
     for (int q = warp; q < nr; q += nwarps) {
       const int rr = r0 + q;
       const float* zr = zbuf + q * S;
+      float* sg_r = sgb + q * S;
+      float* u_r = ub + q * S;
       float* rq = recs + (size_t)(q * S) * REC;
       const float tr = P.trunc;
-      // first zero crossing (argmax of the 0/1 mask -> first true, else 0)
       int first = 0x7fffffff;
-      for (int kk = lane; kk < S - 1; kk += 32) {
-        float s0 = rq[kk * REC + R_RAW + 3], s1 = rq[(kk + 1) * REC + R_RAW + 3];
-        if (s1 * s0 < 0.f) first = min(first, kk);
+      for (int kk = lane; kk < S; kk += 32) {
+        float* rp = rq + kk * REC + R_RAW;
+        const float s = rp[3];
+        const float sg = sigmoidf_acc(s / tr);
+        sg_r[kk] = sg;
+        u_r[kk] = sg * sigmoidf_acc((-s) / tr);
+        rp[0] = sigmoidf_acc(rp[0]);
+        rp[1] = sigmoidf_acc(rp[1]);
+        rp[2] = sigmoidf_acc(rp[2]);
+        if (kk < S - 1 && rq[(kk + 1) * REC + R_RAW + 3] * s < 0.f) first = min(first, kk);
       }
       first = warp_min_i(first);
       if (first == 0x7fffffff) first = 0;
+      __syncwarp();
       const float zlim = zr[first] + P.trunc;
       float usum = 0.f;
       for (int kk = lane; kk < S; kk += 32) {
-        float s = rq[kk * REC + R_RAW + 3];
-        float sg = sigmoidf_acc(s / tr);
-        float a = sg * sigmoidf_acc((-s) / tr);
-        float u = (zr[kk] < zlim) ? a : 0.f;
+        const float u = (zr[kk] < zlim) ? u_r[kk] : 0.f;
+        u_r[kk] = u;
         usum += u;
       }
       usum = warp_sum(usum);
@@ -519,13 +635,10 @@ __global__ void __launch_bounds__(256) k_fused(const Params P) {
       float o_r = 0.f, o_g = 0.f, o_b = 0.f, o_d = 0.f, o_acc = 0.f;
       for (int kk = lane; kk < S; kk += 32) {
         const float* rp = rq + kk * REC + R_RAW;
-        float s = rp[3];
-        float sg = sigmoidf_acc(s / tr);
-        float a = sg * sigmoidf_acc((-s) / tr);
-        float w = ((zr[kk] < zlim) ? a : 0.f) / W;
-        o_r = fmaf(w, sigmoidf_acc(rp[0]), o_r);
-        o_g = fmaf(w, sigmoidf_acc(rp[1]), o_g);
-        o_b = fmaf(w, sigmoidf_acc(rp[2]), o_b);
+        const float w = u_r[kk] / W;
+        o_r = fmaf(w, rp[0], o_r);
+        o_g = fmaf(w, rp[1], o_g);
+        o_b = fmaf(w, rp[2], o_b);
         o_d = fmaf(w, zr[kk], o_d);
         o_acc += w;
       }
@@ -534,11 +647,8 @@ __global__ void __launch_bounds__(256) k_fused(const Params P) {
       if (P.depth_var) {
         float v = 0.f;
         for (int kk = lane; kk < S; kk += 32) {
-          float s = rq[kk * REC + R_RAW + 3];
-          float a = sigmoidf_acc(s / tr) * sigmoidf_acc((-s) / tr);
-          float w = ((zr[kk] < zlim) ? a : 0.f) / W;
-          float dz = zr[kk] - o_d;
-          v = fmaf(w, dz * dz, v);
+          const float dz = zr[kk] - o_d;
+          v = fmaf(u_r[kk] / W, dz * dz, v);
         }
         v = warp_sum(v);
         if (lane == 0) P.depth_var[rr] = v;
@@ -554,9 +664,8 @@ __global__ void __launch_bounds__(256) k_fused(const Params P) {
         const float tr_ = P.target_s[rr * 3], tg_ = P.target_s[rr * 3 + 1],
                     tb_ = P.target_s[rr * 3 + 2];
         const bool valid = (td > 0.f) && (td < P.depth_trunc);
-        const float RS = (float)P.R * (float)S;
-        // d total / d rgb, d depth  (mse means; Q1: rgb weight == 1 for every ray)
-        const float c_rgb = P.ls[0] * P.w_rgb * 2.0f / (3.0f * (float)P.R);
+        const float RS = (float)P.Rg * (float)S;
+        const float c_rgb = P.ls[0] * P.w_rgb * 2.0f / (3.0f * (float)P.Rg);
         const float g_r = c_rgb * (o_r - tr_), g_g = c_rgb * (o_g - tg_), g_b = c_rgb * (o_b - tb_);
         const float g_d = valid ? P.ls[1] * P.w_depth * 2.0f * (o_d - td) * inv_nvalid : 0.f;
         if (lane == 0) {
@@ -564,16 +673,11 @@ __global__ void __launch_bounds__(256) k_fused(const Params P) {
                             (o_b - tb_) * (o_b - tb_));
           if (valid) l_depth += (double)((o_d - td) * (o_d - td));
         }
-        // sum_j q_j w_j
         float qw = 0.f;
         for (int kk = lane; kk < S; kk += 32) {
           const float* rp = rq + kk * REC + R_RAW;
-          float s = rp[3];
-          float a = sigmoidf_acc(s / tr) * sigmoidf_acc((-s) / tr);
-          float w = ((zr[kk] < zlim) ? a : 0.f) / W;
-          float q_ = g_r * sigmoidf_acc(rp[0]) + g_g * sigmoidf_acc(rp[1]) +
-                     g_b * sigmoidf_acc(rp[2]) + g_d * zr[kk];
-          qw = fmaf(q_, w, qw);
+          const float q_ = g_r * rp[0] + g_g * rp[1] + g_b * rp[2] + g_d * zr[kk];
+          qw = fmaf(q_, u_r[kk] / W, qw);
         }
         qw = warp_sum(qw);
         float a_fs = 0.f, a_sdf = 0.f;
@@ -583,14 +687,12 @@ __global__ void __launch_bounds__(256) k_fused(const Params P) {
           float* rp = rq + kk * REC + R_RAW;
           const float z = zr[kk];
           const float s = rp[3];
-          const float sg = sigmoidf_acc(s / tr);
-          const float a = sg * sigmoidf_acc((-s) / tr);
-          const bool m = z < zlim;
-          const float w = (m ? a : 0.f) / W;
-          const float c0 = sigmoidf_acc(rp[0]), c1 = sigmoidf_acc(rp[1]), c2 = sigmoidf_acc(rp[2]);
+          const float sg = sg_r[kk];
+          const float u = u_r[kk];  // a * mask
+          const float w = u / W;
+          const float c0 = rp[0], c1 = rp[1], c2 = rp[2];
           const float q_ = g_r * c0 + g_g * c1 + g_b * c2 + g_d * z;
-          float ds = m ? (q_ - qw) / W * a * (1.f - 2.f * sg) / tr : 0.f;
-          // free-space / sdf terms (utils.py:154-186)
+          float ds = (q_ - qw) / W * u * (1.f - 2.f * sg) / tr;
           const bool front = z < __fsub_rn(td, P.trunc);
           const bool back = z > __fadd_rn(td, P.trunc);
           if (front) {
@@ -612,11 +714,23 @@ __global__ void __launch_bounds__(256) k_fused(const Params P) {
         if (lane == 0) { l_fs += (double)a_fs; l_sdf += (double)a_sdf; }
       }
     }
-    if (!BWD) { __syncthreads(); continue; }
     __syncthreads();
+    if (!BWD) continue;
     // ---------------- phase 3: backward ----------------------------------
-    // dW_col1 += c1^T draw
-    tile_gemm(recs, npts, R_C1, 8, R_RAW, 1, sdw + WC1T, 4);
+    // weight-gradient tiles owned by this warp: tile id = warp + j * nwarps
+    auto dw_phase = [&](int lo, int hi, int aoff, int boff, int n_tiles_n) {
+      if (!map_grads) return;
+#pragma unroll
+      for (int j = 0; j < SLOTS; ++j) {
+        const int id = warp + j * nwarps;
+        if (id >= lo && id < hi) {
+          const int loc = id - lo, mt = loc / n_tiles_n, nt = loc % n_tiles_n;
+          dw_tile<BPREC3>(recs, npts, aoff + 16 * mt, boff + 8 * nt, dwacc[j]);
+        }
+      }
+    };
+    // d w_col1 += c1^T draw        (8-wide n tile over raw[4] + 4 floats of the next record:
+    dw_phase(0, 2, R_C1, R_RAW, 1);  //  columns 3..7 are never written out)
     __syncthreads();
     float draw3 = 0.f;
     if (active) {
@@ -624,145 +738,189 @@ __global__ void __launch_bounds__(256) k_fused(const Params P) {
       draw3 = dr.w;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float4 w = *reinterpret_cast<const float4*>(sw + WC1T + j * 4);
+        const float* w = sw + SWC1 + j * LDC1;
         const float c1 = rec[R_C1 + j];
-        rec[R_C1 + j] = (c1 > 0.f) ? (dr.x * w.x + dr.y * w.y + dr.z * w.z) : 0.f;
+        rec[R_C1 + j] = (c1 > 0.f) ? (dr.x * w[0] + dr.y * w[1] + dr.z * w[2]) : 0.f;
       }
     }
     __syncthreads();
-    // dW_col0 += [blob,geo]^T dc1pre
-    tile_gemm(recs, npts, R_BLOB, 16, R_C1, 8, sdw + WC0T, 32);
+    // d w_col0 += [blob, geo, sdf]^T dc1pre   (row 63 is discarded at write-out)
+    dw_phase(2, 18, R_BLOB, R_C1, 4);
     __syncthreads();
-    float dxn[3] = {0.f, 0.f, 0.f};
-    if (active) {
-      float g[32];
+    if (warp_active) {
+      // dgeo = dc1pre Wc0[:, 48:64]  -> dH = [dgeo(15), dsdf]
+      float c[2][2][4];
+      zero_c<2>(c);
+      warp_gemm<4, 2, true, BPREC3>(wrec, R_C1, sw + SWC0, LDC0, 0, 48, c);
+      store_c<2, false>(wrec, R_GEO, c);
+    }
+    __syncwarp();
+    if (active) rec[R_SDF] = draw3;
+    __syncthreads();
+    // d w_sdf1 += h1^T dH
+    dw_phase(18, 22, R_H1, R_GEO, 2);
+    __syncthreads();
+    if (warp_active) {
+      // dh1pre = (h1 > 0) * (dH W1)
+      float c[2][4][4];
+      zero_c<4>(c);
+      warp_gemm<2, 4, true, BPREC3>(wrec, R_GEO, sw + SW1, LD1, 0, 0, c);
 #pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        const float4 v = *reinterpret_cast<const float4*>(rec + R_C1 + 4 * j4);
-        g[4 * j4] = v.x; g[4 * j4 + 1] = v.y; g[4 * j4 + 2] = v.z; g[4 * j4 + 3] = v.w;
-      }
-      auto dot32 = [&](const float* wrow) {
-        float a0 = 0.f, a1 = 0.f;
-        const float4* wr = reinterpret_cast<const float4*>(wrow);
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 w = wr[j4];
-          a0 = fmaf(g[4 * j4], w.x, a0);
-          a1 = fmaf(g[4 * j4 + 1], w.y, a1);
-          a0 = fmaf(g[4 * j4 + 2], w.z, a0);
-          a1 = fmaf(g[4 * j4 + 3], w.w, a1);
+        for (int nt = 0; nt < 4; ++nt) {
+          float* q0 = wrec + (mt * 16 + g) * REC + R_H1 + nt * 8 + 2 * t;
+          float2 h0 = *reinterpret_cast<float2*>(q0);
+          float2 h8 = *reinterpret_cast<float2*>(q0 + 8 * REC);
+          *reinterpret_cast<float2*>(q0) =
+              make_float2(h0.x > 0.f ? c[mt][nt][0] : 0.f, h0.y > 0.f ? c[mt][nt][1] : 0.f);
+          *reinterpret_cast<float2*>(q0 + 8 * REC) =
+              make_float2(h8.x > 0.f ? c[mt][nt][2] : 0.f, h8.y > 0.f ? c[mt][nt][3] : 0.f);
         }
-        return a0 + a1;
-      };
-      // colour-path OneBlob gradient -> dx immediately (the blob slots stay live for dW_sdf0)
-      blob_backward(xn, [&](int i) { return dot32(sw + WC0T + i * 32); }, dxn);
-      float dgeo[15];
-#pragma unroll
-      for (int i = 0; i < 15; ++i) dgeo[i] = dot32(sw + WC0T + (48 + i) * 32);
-      // (GEMM above already consumed geo) -> overwrite with dH = [dgeo, dsdf]
-#pragma unroll
-      for (int i = 0; i < 15; ++i) rec[R_GEO + i] = dgeo[i];
-      rec[R_SDF] = draw3;
     }
     __syncthreads();
-    // dW_sdf1 += h1^T dH
-    tile_gemm(recs, npts, R_H1, 8, R_GEO, 4, sdw + W1T, 16);
-    __syncthreads();
-    if (active) {
-      float dh[16];
+    // d w_sdf0 += x^T dh1pre
+    dw_phase(22, 42, R_FEAT, R_H1, 4);
+    // (readers of C1 / GEO slots are done: dW phases 2 and 3 finished before the last barrier)
+    float hdx[2][2][3];  // hash-path d loss / d x for rows (mt, g / g+8), fragment layout
 #pragma unroll
-      for (int j4 = 0; j4 < 4; ++j4) {
-        const float4 v = *reinterpret_cast<const float4*>(rec + R_GEO + 4 * j4);
-        dh[4 * j4] = v.x; dh[4 * j4 + 1] = v.y; dh[4 * j4 + 2] = v.z; dh[4 * j4 + 3] = v.w;
-      }
-#pragma unroll 4
-      for (int i = 0; i < 32; ++i) {
-        const float4* wr = reinterpret_cast<const float4*>(sw + W1T + i * 16);
-        float a = 0.f;
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 w = wr[j4];
-          a = fmaf(dh[4 * j4], w.x, a);
-          a = fmaf(dh[4 * j4 + 1], w.y, a);
-          a = fmaf(dh[4 * j4 + 2], w.z, a);
-          a = fmaf(dh[4 * j4 + 3], w.w, a);
-        }
-        const float h1 = rec[R_H1 + i];
-        rec[R_H1 + i] = (h1 > 0.f) ? a : 0.f;
-      }
-    }
-    __syncthreads();
-    // dW_sdf0 += x^T dh1pre
-    tile_gemm(recs, npts, R_FEAT, 20, R_H1, 8, sdw + W0T, 32);
-    if (active) {
-      float g[32];
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        const float4 v = *reinterpret_cast<const float4*>(rec + R_H1 + 4 * j4);
-        g[4 * j4] = v.x; g[4 * j4 + 1] = v.y; g[4 * j4 + 2] = v.z; g[4 * j4 + 3] = v.w;
-      }
-      auto dot32 = [&](const float* wrow) {
-        float a0 = 0.f, a1 = 0.f;
-        const float4* wr = reinterpret_cast<const float4*>(wrow);
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 w = wr[j4];
-          a0 = fmaf(g[4 * j4], w.x, a0);
-          a1 = fmaf(g[4 * j4 + 1], w.y, a1);
-          a0 = fmaf(g[4 * j4 + 2], w.z, a0);
-          a1 = fmaf(g[4 * j4 + 3], w.w, a1);
-        }
-        return a0 + a1;
-      };
-      blob_backward(xn, [&](int i) { return dot32(sw + W0T + (32 + i) * 32); }, dxn);
-      float dfeat[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) dfeat[i] = dot32(sw + W0T + i * 32);
-      const bool need_dx = (P.d_rays_o != nullptr) || (P.d_rays_d != nullptr);
-      hash_backward(P, xn, dfeat, need_dx, dxn);
+      for (int b = 0; b < 2; ++b) hdx[a][b][0] = hdx[a][b][1] = hdx[a][b][2] = 0.f;
+    if (warp_active) {
       if (need_dx) {
+        // dblob = dc1pre Wc0[:, 0:48] + dh1pre W0[:, 32:80]  -> scratch (C1 slots 0..31, GEO 32..47)
+        float c[2][6][4];
+        zero_c<6>(c);
+        warp_gemm<4, 6, true, BPREC3>(wrec, R_C1, sw + SWC0, LDC0, 0, 0, c);
+        warp_gemm<4, 6, true, BPREC3>(wrec, R_H1, sw + SW0, LD0, 0, 32, c);
+        __syncwarp();
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          float dp = (float)((double)dxn[d] / (P.g.bmax[d] - P.g.bmin[d]));
-          atomicAdd(&rayacc[rl * 8 + d], dp);
-          atomicAdd(&rayacc[rl * 8 + 3 + d], dp * zv);
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 6; ++nt) {
+            const int col = nt * 8 + 2 * t;
+            const int off = (col < 32) ? (R_C1 + col) : (R_GEO + col - 32);
+            float* q0 = wrec + (mt * 16 + g) * REC + off;
+            *reinterpret_cast<float2*>(q0) = make_float2(c[mt][nt][0], c[mt][nt][1]);
+            *reinterpret_cast<float2*>(q0 + 8 * REC) = make_float2(c[mt][nt][2], c[mt][nt][3]);
+          }
+      }
+      if (map_grads || need_dx) {
+        // dfeat = dh1pre W0[:, 0:32]; lane (g,t) holds (f0,f1) of level 4*nt+t for rows g, g+8
+        float c[2][4][4];
+        zero_c<4>(c);
+        warp_gemm<4, 4, true, BPREC3>(wrec, R_H1, sw + SW0, LD0, 0, 0, c);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int row = warp * 32 + mt * 16 + g + 8 * h;
+            if (row < npts) {
+              const int rr = r0 + row / S, kk = row % S;
+              const float z = zbuf[row];
+              float x3[3];
+#pragma unroll
+              for (int d = 0; d < 3; ++d) {
+                float pt = __fadd_rn(P.rays_o[rr * 3 + d], __fmul_rn(P.rays_d[rr * 3 + d], z));
+                x3[d] = normalise(pt, P.g.bmin[d], P.g.bmax[d]);
+              }
+              (void)kk;
+#pragma unroll
+              for (int nt = 0; nt < 4; ++nt) {
+                const int l = 4 * nt + t;
+                const float g0 = c[mt][nt][2 * h], g1 = c[mt][nt][2 * h + 1];
+                if (l < P.g.n_levels && (g0 != 0.f || g1 != 0.f)) {
+                  const float3 d3 = hash_backward_item(P, l, x3[0], x3[1], x3[2], g0, g1,
+                                                       need_dx, map_grads);
+                  hdx[mt][h][0] += d3.x; hdx[mt][h][1] += d3.y; hdx[mt][h][2] += d3.z;
+                }
+              }
+            }
+          }
+      }
+      if (need_dx) {
+        // reduce the hash-path dx over the 4 lanes (t) that share a row, park it in RAW[0..2]
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              float v = hdx[mt][h][d];
+              v += __shfl_xor_sync(0xffffffffu, v, 1);
+              v += __shfl_xor_sync(0xffffffffu, v, 2);
+              if (t == 0) wrec[(mt * 16 + g + 8 * h) * REC + R_RAW + d] = v;
+            }
+        __syncwarp();
+        if (active) {
+          float dxn[3] = {rec[R_RAW], rec[R_RAW + 1], rec[R_RAW + 2]};
+          blob_backward(xn, [&](int i) { return (i < 32) ? rec[R_C1 + i] : rec[R_GEO + i - 32]; }, dxn);
+          // park d loss / d pts and z * d loss / d pts in the (dead) C1 slots 0..5
+          float dp[3];
+#pragma unroll
+          for (int d = 0; d < 3; ++d)
+            dp[d] = (float)((double)dxn[d] / (P.g.bmax[d] - P.g.bmin[d]));
+          rec[R_C1 + 0] = dp[0]; rec[R_C1 + 1] = dp[1]; rec[R_C1 + 2] = dp[2];
+          rec[R_C1 + 3] = dp[0] * zv; rec[R_C1 + 4] = dp[1] * zv; rec[R_C1 + 5] = dp[2] * zv;
         }
       }
     }
     __syncthreads();
-    if (tid < nr * 6) {
-      const int q = tid / 6, c = tid % 6;
-      const float v = rayacc[q * 8 + c];
-      if (c < 3) { if (P.d_rays_o) P.d_rays_o[(r0 + q) * 3 + c] = v; }
-      else       { if (P.d_rays_d) P.d_rays_d[(r0 + q) * 3 + c - 3] = v; }
+    if (need_dx) {
+      for (int q = warp; q < nr; q += nwarps) {
+        float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int kk = lane; kk < S; kk += 32) {
+          const float* rp = recs + (size_t)(q * S + kk) * REC + R_C1;
+#pragma unroll
+          for (int d = 0; d < 6; ++d) a[d] += rp[d];
+        }
+#pragma unroll
+        for (int d = 0; d < 6; ++d) a[d] = warp_sum(a[d]);
+        if (lane == 0) {
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            if (P.d_rays_o) P.d_rays_o[(r0 + q) * 3 + d] = a[d];
+            if (P.d_rays_d) P.d_rays_d[(r0 + q) * 3 + d] = a[3 + d];
+          }
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
 
   if (BWD) {
-    // flush loss partials and weight gradients
     if (lane == 0) {
       if (l_rgb != 0.0) atomicAdd(&P.loss_acc[0], l_rgb);
       if (l_depth != 0.0) atomicAdd(&P.loss_acc[1], l_depth);
       if (l_sdf != 0.0) atomicAdd(&P.loss_acc[2], l_sdf);
       if (l_fs != 0.0) atomicAdd(&P.loss_acc[3], l_fs);
     }
-    __syncthreads();
-    for (int q = tid; q < 80 * 32; q += blockDim.x) {
-      int i = q / 32, j = q % 32;
-      red_add(P.d_w_sdf0 + j * 80 + i, sdw[W0T + q]);
-    }
-    for (int q = tid; q < 32 * 16; q += blockDim.x) {
-      int i = q / 16, jp = q % 16, jt = (jp + 1) & 15;
-      red_add(P.d_w_sdf1 + jt * 32 + i, sdw[W1T + q]);
-    }
-    for (int q = tid; q < 63 * 32; q += blockDim.x) {
-      int i = q / 32, j = q % 32;
-      red_add(P.d_w_col0 + j * 63 + i, sdw[WC0T + q]);
-    }
-    for (int q = tid; q < 32 * 3; q += blockDim.x) {
-      int i = q / 3, k = q % 3;
-      red_add(P.d_w_col1 + k * 32 + i, sdw[WC1T + i * 4 + k]);
+    if (map_grads) {
+      // write out the weight-gradient tiles: C(16 x 8): rows = in-feature, cols = out-unit
+#pragma unroll
+      for (int j = 0; j < SLOTS; ++j) {
+        const int id = warp + j * nwarps;
+        if (id >= DW_TILES) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float v = dwacc[j][i];
+          const int rloc = g + ((i & 2) ? 8 : 0), cloc = 2 * t + (i & 1);
+          if (id < 2) {  // d w_col1 [3][32]
+            const int in = 16 * id + rloc, out = cloc;
+            if (out < 3) red_add(P.d_w_col1 + out * 32 + in, v);
+          } else if (id < 18) {  // d w_col0 [32][63]
+            const int loc = id - 2, in = 16 * (loc / 4) + rloc, out = 8 * (loc % 4) + cloc;
+            if (in < 63) red_add(P.d_w_col0 + out * 63 + in, v);
+          } else if (id < 22) {  // d w_sdf1 [16][32], stored column jp -> torch row (jp+1)&15
+            const int loc = id - 18, in = 16 * (loc / 2) + rloc, jp = 8 * (loc % 2) + cloc;
+            red_add(P.d_w_sdf1 + ((jp + 1) & 15) * 32 + in, v);
+          } else {  // d w_sdf0 [32][80]
+            const int loc = id - 22, in = 16 * (loc / 4) + rloc, out = 8 * (loc % 4) + cloc;
+            red_add(P.d_w_sdf0 + out * 80 + in, v);
+          }
+        }
+      }
     }
   }
 }
@@ -960,17 +1118,29 @@ extern "C" int xrd_coslam_step(const XrdRays* rays, const XrdHashGrid* grid,
   if (has_depth && (!cfg->lin_uniform || !cfg->lin_range || !cfg->lin_nodepth)) return XRD_E_NULL;
   if (!has_depth && !cfg->lin_full) return XRD_E_NULL;
   if (grads && (!has_depth || !rays->target_s || !out->losses)) return XRD_E_NULL;
-  if (grads && (!grads->d_table || !grads->d_w_sdf0 || !grads->d_w_sdf1 || !grads->d_w_col0 ||
-                !grads->d_w_col1))
-    return XRD_E_NULL;
+  if (grads) {
+    // map gradients are all-or-nothing; d_table == NULL selects the pose-only (tracking) pass
+    const int n_map = (grads->d_table != nullptr) + (grads->d_w_sdf0 != nullptr) +
+                      (grads->d_w_sdf1 != nullptr) + (grads->d_w_col0 != nullptr) +
+                      (grads->d_w_col1 != nullptr);
+    if (n_map != 0 && n_map != 5) return XRD_E_NULL;
+    if (n_map == 0 && !grads->d_rays_o && !grads->d_rays_d) return XRD_E_NULL;
+  }
   if (workspace_bytes < xrd_coslam_workspace_bytes(R, S)) return XRD_E_WORKSPACE;
 
-  int* counts = reinterpret_cast<int*>(workspace);
+  int* counts = reinterpret_cast<int*>(workspace);  // n_fs, n_sdf, n_valid
   double* loss_acc = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 64);
   float* z_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
   float* z_vals = out->z_vals ? out->z_vals : z_ws;
+  const int phase = cfg->phase;  // 0: sample+render, 1: sample only, 2: render only
+  if (phase < 0 || phase > 2) return XRD_E_SHAPE;
+  if (phase != 0 && !out->z_vals) return XRD_E_NULL;
+  if (phase == 1 && !cfg->counts_out) return XRD_E_NULL;
   XRD_CUDA_TRY(cudaMemsetAsync(workspace, 0, 256, stream));
-
+  if (phase == 1) {
+    counts = cfg->counts_out;
+    XRD_CUDA_TRY(cudaMemsetAsync(counts, 0, 4 * sizeof(int), stream));
+  }
   SampleParams sp;
   sp.R = R; sp.S = S; sp.n_a = cfg->n_sample_d; sp.n_b = cfg->n_range_d;
   sp.perturb = cfg->perturb; sp.has_depth = has_depth;
@@ -978,13 +1148,17 @@ extern "C" int xrd_coslam_step(const XrdRays* rays, const XrdHashGrid* grid,
   sp.lin_nodepth = cfg->lin_nodepth; sp.lin_full = cfg->lin_full; sp.noise = noise;
   sp.trunc = cfg->trunc; sp.depth_trunc = cfg->depth_trunc; sp.seed = cfg->seed;
   sp.z_vals = z_vals; sp.counts = counts;
-  k_sample<<<(R + 3) / 4, 128, 0, stream>>>(sp);
-  XRD_LAUNCH_CHECK();
+  if (phase != 2) {
+    k_sample<<<(R + 3) / 4, 128, 0, stream>>>(sp);
+    XRD_LAUNCH_CHECK();
+  }
+  if (phase == 1) return XRD_OK;
 
   Params P;
   int st = fill_grid(P.g, grid);
   if (st != XRD_OK) return st;
   P.R = R; P.S = S;
+  P.Rg = cfg->n_rays_global > 0 ? cfg->n_rays_global : R;
   P.rays_o = rays->rays_o; P.rays_d = rays->rays_d; P.target_s = rays->target_s; P.target_d = rays->target_d;
   P.z_vals = z_vals; P.table = grid->table;
   P.w_sdf0 = mlp->w_sdf0; P.w_sdf1 = mlp->w_sdf1; P.w_col0 = mlp->w_col0; P.w_col1 = mlp->w_col1;
@@ -992,7 +1166,7 @@ extern "C" int xrd_coslam_step(const XrdRays* rays, const XrdHashGrid* grid,
   P.w_rgb = cfg->w_rgb; P.w_depth = cfg->w_depth; P.w_sdf = cfg->w_sdf; P.w_fs = cfg->w_fs;
   P.rgb = out->rgb; P.depth = out->depth; P.disp = out->disp; P.acc = out->acc;
   P.depth_var = out->depth_var; P.raw = out->raw;
-  P.counts = counts; P.loss_acc = loss_acc;
+  P.counts = cfg->counts_global ? cfg->counts_global : counts; P.loss_acc = loss_acc;
   for (int i = 0; i < 4; ++i) P.ls[i] = grads ? grads->loss_scale[i] : 0.f;
   if (grads) {
     P.d_table = grads->d_table; P.d_w_sdf0 = grads->d_w_sdf0; P.d_w_sdf1 = grads->d_w_sdf1;
@@ -1003,35 +1177,43 @@ extern "C" int xrd_coslam_step(const XrdRays* rays, const XrdHashGrid* grid,
   }
   int NR = pick_rays_per_tile(S, cfg->rays_per_tile);
   if (NR < 1 || NR * S > 256) return XRD_E_SHAPE;
+  int threads = (NR * S + 31) / 32 * 32;
+  if (grads && threads < 224) threads = 224;  // 7+ warps own the 42 weight-gradient tiles (6 each)
   P.NR = NR;
   P.n_tiles = (R + NR - 1) / NR;
-  const int threads = (NR * S + 31) / 32 * 32;
-  const size_t smem = sizeof(float) * ((size_t)W_TOTAL * (grads ? 2 : 1) + (size_t)threads * REC +
-                                       (size_t)NR * S + (size_t)NR * 8);
+  const size_t smem = sizeof(float) * ((size_t)SW_TOTAL + (size_t)(threads + 8) * REC + 3 * (size_t)NR * S);
   const int sms = num_sms();
+  const int nwarps = threads / 32;
+  const int slots = (DW_TILES + nwarps - 1) / nwarps;
+#define XRD_LAUNCH_FUSED(KERNEL)                                                                  \
+  do {                                                                                            \
+    XRD_CUDA_TRY(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                      (int)smem));                                                \
+    int occ = 1;                                                                                  \
+    XRD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, KERNEL, threads, smem));     \
+    if (occ < 1) return XRD_E_SHAPE;                                                              \
+    int gridx = P.n_tiles < sms * occ ? P.n_tiles : sms * occ;                                    \
+    KernelTimer kt(stream);                                                                       \
+    KERNEL<<<gridx, threads, smem, stream>>>(P);                                                  \
+  } while (0)
   if (grads) {
-    XRD_CUDA_TRY(cudaFuncSetAttribute(k_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 1;
-    XRD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused<true>, threads, smem));
-    if (occ < 1) return XRD_E_SHAPE;
-    int gridx = P.n_tiles < sms * occ ? P.n_tiles : sms * occ;
-    {
-      KernelTimer kt(stream);
-      k_fused<true><<<gridx, threads, smem, stream>>>(P);
+    if (slots != 6) return XRD_E_SHAPE;  // >= 7 warps own the 42 weight-gradient tiles
+    switch (cfg->precision) {
+      case 0: XRD_LAUNCH_FUSED((k_fused<true, true, true, 6>)); break;
+      case 1: XRD_LAUNCH_FUSED((k_fused<true, true, false, 6>)); break;
+      case 2: XRD_LAUNCH_FUSED((k_fused<true, false, false, 6>)); break;
+      default: return XRD_E_SHAPE;
     }
     XRD_LAUNCH_CHECK();
-    FinalizeParams fp{loss_acc, counts, out->losses, R, S, cfg->w_rgb, cfg->w_depth, cfg->w_sdf, cfg->w_fs};
+    FinalizeParams fp{loss_acc, P.counts, out->losses, P.Rg, S, cfg->w_rgb, cfg->w_depth, cfg->w_sdf, cfg->w_fs};
     k_finalize<<<1, 32, 0, stream>>>(fp);
     XRD_LAUNCH_CHECK();
   } else {
-    XRD_CUDA_TRY(cudaFuncSetAttribute(k_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 1;
-    XRD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused<false>, threads, smem));
-    if (occ < 1) return XRD_E_SHAPE;
-    int gridx = P.n_tiles < sms * occ ? P.n_tiles : sms * occ;
-    k_fused<false><<<gridx, threads, smem, stream>>>(P);
+    if (cfg->precision <= 1) XRD_LAUNCH_FUSED((k_fused<false, true, false, 1>));
+    else XRD_LAUNCH_FUSED((k_fused<false, false, false, 1>));
     XRD_LAUNCH_CHECK();
   }
+#undef XRD_LAUNCH_FUSED
   return XRD_OK;
 }
 

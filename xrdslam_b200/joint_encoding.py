@@ -77,6 +77,9 @@ class JointEncodingConfig(ModelConfig):
     seed: int = 0  # Philox seed for in-kernel jitter when no noise is passed
     strict_loss_grad: bool = False  # verify upstream d(total)/d(term) == 1
     rays_per_tile: int = 0
+    # decoder GEMMs on tensor cores: 0 = 3xTF32 everywhere (fp32-level parity),
+    # 1 = 3xTF32 forward + TF32 backward, 2 = TF32 everywhere
+    precision: int = 0
 
 
 class HashGridParams(nn.Module):
@@ -127,10 +130,14 @@ class _CoslamStep(torch.autograd.Function):
     def forward(ctx, rays_o, rays_d, table, w0, w1, wc0, wc1, model, target_s,
                 target_d, noise):
         need = any(ctx.needs_input_grad[:7])
+        need_rays = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        # tracking: only the pose is optimised -> skip scatter / weight-gradient tiles
+        map_grads = any(ctx.needs_input_grad[2:7]) and not (
+            model.freeze_map_grads and need_rays)
         outs, grads = model._launch(rays_o, rays_d, table, w0, w1, wc0, wc1,
                                     target_s, target_d, noise, with_grads=need,
-                                    need_ray_grads=ctx.needs_input_grad[0]
-                                    or ctx.needs_input_grad[1])
+                                    need_ray_grads=need_rays,
+                                    map_grads=map_grads)
         ctx.grads = grads
         ctx.model = model
         ctx.strict = model.config.strict_loss_grad
@@ -208,6 +215,9 @@ class JointEncoding(Model):
                              ls(cfg.cam_near, cfg.cam_far,
                                 cfg.training_n_samples), persistent=False)
         self._step_count = 0
+        # set by the Algorithm around tracking (only pose params have optimizers
+        # there, base_algorithm.py:168-181): the fused pass then produces d rays only
+        self.freeze_map_grads = False
 
     def get_resolution(self):
         """joint_encoding.py:199-210."""
@@ -253,7 +263,7 @@ class JointEncoding(Model):
 
     def _launch(self, rays_o, rays_d, table, w0, w1, wc0, wc1, target_s,
                 target_d, noise, with_grads, need_ray_grads=True,
-                loss_scale=None, seed=None):
+                loss_scale=None, seed=None, map_grads=True):
         cfg = self.config
         dev = table.device
         if dev.type != 'cuda':
@@ -297,7 +307,7 @@ class JointEncoding(Model):
             cfg.trainging_sdf_weight, cfg.trainging_fs_weight,
             ptr(self._lin_uniform), ptr(self._lin_range),
             ptr(self._lin_nodepth), ptr(self._lin_full),
-            seed, cfg.rays_per_tile)
+            seed, cfg.rays_per_tile, cfg.precision, 0, 0, None, None)
         out = XrdCoslamOut(ptr(o['rgb']), ptr(o['depth']), ptr(o['disp_map']),
                            ptr(o['acc_map']), ptr(o['depth_var']),
                            ptr(o['z_vals']), ptr(o['raw']), ptr(o['losses']))
@@ -306,10 +316,12 @@ class JointEncoding(Model):
         if with_grads:
             if not has_d or ts is None:
                 raise RuntimeError('gradients need target_s and target_d')
-            g = dict(d_table=torch.zeros_like(table, **f32),
-                     d_w_sdf0=torch.zeros_like(w0), d_w_sdf1=torch.zeros_like(w1),
-                     d_w_col0=torch.zeros_like(wc0),
-                     d_w_col1=torch.zeros_like(wc1),
+            z = torch.zeros_like
+            g = dict(d_table=z(table, **f32) if map_grads else None,
+                     d_w_sdf0=z(w0) if map_grads else None,
+                     d_w_sdf1=z(w1) if map_grads else None,
+                     d_w_col0=z(wc0) if map_grads else None,
+                     d_w_col1=z(wc1) if map_grads else None,
                      d_rays_o=torch.empty(R, 3, **f32) if need_ray_grads else None,
                      d_rays_d=torch.empty(R, 3, **f32) if need_ray_grads else None)
             sc = loss_scale or [1.0, 1.0, 1.0, 1.0]
