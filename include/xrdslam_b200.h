@@ -75,8 +75,11 @@ typedef struct {
   const float* target_d; /* [R]   depth target,  may be NULL                 */
 } XrdRays;
 
-/* torch.linspace(start, end, steps) for float32, bit-identical to ATen's CPU
- * kernel (host function, writes `steps` floats to host memory `out`). */
+/* torch.linspace(start, end, steps) for float32 by ATen's scalar formula (host
+ * function, writes `steps` floats to host memory `out`).  ATen's vectorised CPU
+ * path differs in the last bit for some elements depending on the host's SIMD
+ * width; callers that need the reference's exact z samples pass tables made by
+ * torch.linspace on the same host (the Python plugin does). */
 int xrd_linspace_f32(float start, float end, int steps, float* out);
 
 /* ---- Co-SLAM ------------------------------------------------------------ */

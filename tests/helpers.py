@@ -53,3 +53,33 @@ def rel_err(a, b):
 
 def max_abs(a, b):
     return float((a.detach().double().cpu() - b.detach().double().cpu()).abs().max())
+
+
+def load_golden_coslam():
+    """Golden vectors written by tests/golden/make_golden.py (reference classes)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden',
+                             'coslam_map_step.npz'))
+    g = {k: g[k] for k in g.files}
+    gen = torch.Generator().manual_seed(int(g['table_seed']))
+    from oracle.tcnn_restated import hashgrid_level_table
+    n = hashgrid_level_table(16, 2, 16, 16, np.exp2(np.log2(325 / 16) / 15))['n_params']
+    g['table'] = ((torch.rand(n, generator=gen) * 2 - 1) * 0.3)
+    assert abs(float(g['table'].double().sum()) - float(g['table_checksum'])) < 1e-9
+    return g
+
+
+def set_coslam_params(obj, g, kind):
+    """Load golden parameters into an oracle (kind='oracle') or B200 model."""
+    with torch.no_grad():
+        t = lambda k: torch.from_numpy(g[k])
+        if kind == 'oracle':
+            obj.embed_fn.params.copy_(g['table'])
+            obj.sdf0.weight.copy_(t('w_sdf0')); obj.sdf1.weight.copy_(t('w_sdf1'))
+            obj.col0.weight.copy_(t('w_col0')); obj.col1.weight.copy_(t('w_col1'))
+        else:
+            obj.embed_fn.params.copy_(g['table'])
+            obj.decoder.sdf_net.model[0].weight.copy_(t('w_sdf0'))
+            obj.decoder.sdf_net.model[2].weight.copy_(t('w_sdf1'))
+            obj.decoder.color_net.model[0].weight.copy_(t('w_col0'))
+            obj.decoder.color_net.model[2].weight.copy_(t('w_col1'))

@@ -214,3 +214,37 @@ def test_tracking_pose_only(cuda_dev):
     assert model.embed_fn.params.grad is None
     assert rel_err(ro.grad, rays_o.grad) < TOL_GRAD
     assert rel_err(rd.grad, rays_d.grad) < TOL_GRAD
+
+
+def test_cuda_matches_reference_golden(cuda_dev):
+    """CUDA path vs vectors produced by the reference's own JointEncoding class."""
+    from helpers import load_golden_coslam, set_coslam_params
+    from xrdslam_b200.camera import Camera
+    from xrdslam_b200.joint_encoding import JointEncodingConfig
+    g = load_golden_coslam()
+    model = JointEncodingConfig().setup(camera=Camera(320., 320., 319.5, 239.5, 640, 480),
+                                        bounding_box=BOUND)
+    set_coslam_params(model, g, 'model')
+    model.to(cuda_dev)
+    t = lambda k: torch.from_numpy(g[k]).to(cuda_dev)
+    ro = t('rays_o').requires_grad_(True)
+    rd = t('rays_d').requires_grad_(True)
+    inp = dict(rays_o=ro, rays_d=rd, target_s=t('target_s'), target_d=t('target_d'),
+               first=False, noise=t('noise'), smooth_rand=torch.from_numpy(g['smooth_rand']))
+    out = model(inp)
+    ld = model.get_loss_dict(out, inp, True, 0)
+    sum(ld.values()).backward()
+    assert np.array_equal(out['z_vals'].cpu().numpy(), g['z_vals'])
+    assert np.abs(out['rgb'].detach().cpu().numpy() - g['rgb']).max() < TOL_OUT
+    assert np.abs(out['depth'].detach().cpu().numpy() - g['depth']).max() < TOL_OUT
+    assert np.abs(out['raw'].detach().cpu().numpy() - g['raw']).max() < 5e-5
+    got = np.array([float(ld[k].detach()) for k in
+                    ('rgb_loss', 'depth_loss', 'sdf_loss', 'fs_loss', 'smooth_loss')])
+    assert np.allclose(got, g['losses'], rtol=TOL_LOSS, atol=0)
+    assert rel_err(ro.grad, torch.from_numpy(g['d_rays_o'])) < TOL_GRAD
+    assert rel_err(rd.grad, torch.from_numpy(g['d_rays_d'])) < TOL_GRAD
+    assert rel_err(model.decoder.sdf_net.model[0].weight.grad, torch.from_numpy(g['d_w_sdf0'])) < TOL_GRAD
+    assert rel_err(model.decoder.color_net.model[2].weight.grad, torch.from_numpy(g['d_w_col1'])) < TOL_GRAD
+    gt = model.embed_fn.params.grad
+    assert abs(float(gt.double().norm()) - float(g['d_table_norm'])) <= TOL_GRAD * float(g['d_table_norm'])
+    assert rel_err(gt[:4096], torch.from_numpy(g['d_table_head'])) < TOL_GRAD

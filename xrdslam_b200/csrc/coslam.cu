@@ -40,8 +40,9 @@ constexpr int R_FEAT = 0, R_BLOB = 32, R_GEO = 80, R_SDF = 95, R_H1 = 96, R_C1 =
 struct GridDev {
   float scale[kL];
   uint32_t res[kL], size[kL], offset[kL], hashed[kL];
+  uint32_t magic[kL];  // floor(2^32 / size): q = umulhi(index, magic) <= index/size, off by <= 1
   int n_levels;
-  double bmin[3], binv[3];  // 1/(max-min) is NOT used for the forward (division)
+  double bmin[3], binv[3];  // 1/(max-min): gradients only; the forward divides (index parity)
   double bmax[3];
 };
 
@@ -152,8 +153,6 @@ __global__ void __launch_bounds__(128) k_sample(SampleParams p) {
 }
 
 // --------------------------------------------------------------- encoding ---
-// out-of-bound points on dense levels only (rare): keep the division sequence out of line
-__device__ __noinline__ uint32_t slow_mod(uint32_t a, uint32_t b) { return a % b; }
 
 __device__ __forceinline__ uint32_t grid_index(const GridDev& g, int l, uint32_t x,
                                                uint32_t y, uint32_t z) {
@@ -167,8 +166,13 @@ __device__ __forceinline__ uint32_t grid_index(const GridDev& g, int l, uint32_t
     index = x + y * res + z * res * res;
   }
   // index % size: sizes of hashed levels are powers of two; in-range dense cells are < size
-  if ((size & (size - 1)) == 0) index &= size - 1;
-  else if (index >= size) index = slow_mod(index, size);
+  if ((size & (size - 1)) == 0) {
+    index &= size - 1;
+  } else if (index >= size) {  // points outside the bound wrap around (tcnn does not clamp)
+    index -= __umulhi(index, g.magic[l]) * size;  // exact remainder or remainder + size
+    if (index >= size) index -= size;
+    if (index >= size) index -= size;
+  }
   return index + g.offset[l];
 }
 
@@ -473,6 +477,7 @@ __global__ void __launch_bounds__(256) k_fused(const Params P) {
   float* zbuf = recs + (blockDim.x + 8) * REC; // NR*S z values
   float* sgb = zbuf + P.NR * P.S;              // NR*S sigma(sdf/trunc)
   float* ub = sgb + P.NR * P.S;                // NR*S unnormalised weights
+  float* xnb = ub + P.NR * P.S;                // NR*S*3 normalised coordinates
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int nwarps = blockDim.x >> 5;
@@ -541,6 +546,7 @@ __global__ void __launch_bounds__(256) k_fused(const Params P) {
       for (int d = 0; d < 3; ++d) {
         float pt = __fadd_rn(P.rays_o[r * 3 + d], __fmul_rn(P.rays_d[r * 3 + d], zv));
         xn[d] = normalise(pt, P.g.bmin[d], P.g.bmax[d]);
+        xnb[tid * 3 + d] = xn[d];
       }
       encode_point(P, xn, rec);
     } else {
@@ -817,15 +823,7 @@ __global__ void __launch_bounds__(256) k_fused(const Params P) {
           for (int h = 0; h < 2; ++h) {
             const int row = warp * 32 + mt * 16 + g + 8 * h;
             if (row < npts) {
-              const int rr = r0 + row / S, kk = row % S;
-              const float z = zbuf[row];
-              float x3[3];
-#pragma unroll
-              for (int d = 0; d < 3; ++d) {
-                float pt = __fadd_rn(P.rays_o[rr * 3 + d], __fmul_rn(P.rays_d[rr * 3 + d], z));
-                x3[d] = normalise(pt, P.g.bmin[d], P.g.bmax[d]);
-              }
-              (void)kk;
+              const float x3[3] = {xnb[row * 3], xnb[row * 3 + 1], xnb[row * 3 + 2]};
 #pragma unroll
               for (int nt = 0; nt < 4; ++nt) {
                 const int l = 4 * nt + t;
@@ -860,7 +858,7 @@ __global__ void __launch_bounds__(256) k_fused(const Params P) {
           float dp[3];
 #pragma unroll
           for (int d = 0; d < 3; ++d)
-            dp[d] = (float)((double)dxn[d] / (P.g.bmax[d] - P.g.bmin[d]));
+            dp[d] = (float)((double)dxn[d] * P.g.binv[d]);
           rec[R_C1 + 0] = dp[0]; rec[R_C1 + 1] = dp[1]; rec[R_C1 + 2] = dp[2];
           rec[R_C1 + 3] = dp[0] * zv; rec[R_C1 + 4] = dp[1] * zv; rec[R_C1 + 5] = dp[2] * zv;
         }
@@ -1075,6 +1073,7 @@ static int fill_grid(GridDev& g, const XrdHashGrid* h) {
   for (int l = 0; l < kL; ++l) {
     g.scale[l] = h->scale[l]; g.res[l] = h->resolution[l]; g.size[l] = h->size[l] ? h->size[l] : 1;
     g.offset[l] = h->offset[l]; g.hashed[l] = h->hashed[l];
+    g.magic[l] = (uint32_t)(0x100000000ull / g.size[l]);
   }
   for (int d = 0; d < 3; ++d) {
     g.bmin[d] = h->bbox_min[d]; g.bmax[d] = h->bbox_max[d];
@@ -1181,7 +1180,7 @@ extern "C" int xrd_coslam_step(const XrdRays* rays, const XrdHashGrid* grid,
   if (grads && threads < 224) threads = 224;  // 7+ warps own the 42 weight-gradient tiles (6 each)
   P.NR = NR;
   P.n_tiles = (R + NR - 1) / NR;
-  const size_t smem = sizeof(float) * ((size_t)SW_TOTAL + (size_t)(threads + 8) * REC + 3 * (size_t)NR * S);
+  const size_t smem = sizeof(float) * ((size_t)SW_TOTAL + (size_t)(threads + 8) * REC + 6 * (size_t)NR * S);
   const int sms = num_sms();
   const int nwarps = threads / 32;
   const int slots = (DW_TILES + nwarps - 1) / nwarps;
