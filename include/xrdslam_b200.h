@@ -198,6 +198,92 @@ int xrd_coslam_smoothness(const XrdHashGrid* grid, int sample_points,
 int xrd_hashgrid_encode(const XrdHashGrid* grid, const float* x, int n_points,
                         float* feat, uint32_t* idx, void* stream);
 
+/* ---- NICE-SLAM -------------------------------------------------------------
+ *
+ *   xrd_nice_step   slam/models/conv_onet.py:132-143 get_outputs -> render_batch_ray
+ *                   :377-524 (bbox far plane, 32 uniform + 16 surface samples in float64,
+ *                   sort), eval_points :339-375, NICE.forward
+ *                   slam/model_components/decoder_nice.py:386-414 with the three MLP
+ *                   decoders :207-234 (F.grid_sample trilerp :195-205, Gaussian Fourier
+ *                   embedding :11-38), raw2outputs_nerf_color
+ *                   slam/model_components/utils.py:189-244, get_loss_dict
+ *                   conv_onet.py:145-185 (incl. the batch-global median of the tracking
+ *                   mask) and autograd's backward.
+ *
+ * Feature grids are CHANNEL-LAST fp32 [Z][Y][X][32] (the reference holds [1,32,Z,Y,X];
+ * one voxel = one 128-byte line here).  Decoder weights keep torch's [out,in] layout. */
+
+typedef struct {
+  const float* B;        /* [3][93]   Gaussian Fourier matrix (embedder._B)      */
+  const float* pts_w[5]; /* [32][in]  in = 93, 32, 32, 125 (cat[embed, h]), 32     */
+  const float* pts_b[5]; /* [32]                                                   */
+  const float* fcc_w[5]; /* [32][c_dim]                                            */
+  const float* fcc_b[5]; /* [32]                                                   */
+  const float* out_w;    /* [n_out][32]                                            */
+  const float* out_b;    /* [n_out]                                                */
+  int c_dim;             /* 32 (middle, color) or 64 (fine: own grid ++ middle)    */
+  int n_out;             /* 1 (occupancy) or 4 (colour decoder)                    */
+} XrdNiceDecoder;
+
+typedef struct {          /* same shapes as XrdNiceDecoder, ACCUMULATED into       */
+  float* B;
+  float* pts_w[5];
+  float* pts_b[5];
+  float* fcc_w[5];
+  float* fcc_b[5];
+  float* out_w;
+  float* out_b;
+} XrdNiceDecoderGrads;
+
+typedef struct {
+  const float* data; /* DEVICE [Z][Y][X][32] */
+  int nx, ny, nz;
+} XrdNiceGrid;
+
+typedef enum { XRD_NICE_MIDDLE = 0, XRD_NICE_FINE = 1, XRD_NICE_COLOR = 2 } XrdNiceStage;
+
+typedef struct {
+  int stage;              /* XrdNiceStage                                          */
+  int is_mapping;         /* loss form (conv_onet.py:160-185)                      */
+  int n_samples;          /* 32 uniform                                            */
+  int n_surface;          /* 16 near the surface                                   */
+  double bound_min[3];    /* scene bound AFTER load_bound (float64)                */
+  double bound_max[3];
+  float w_color;          /* tracking 0.5 / mapping 0.2                            */
+  int handle_dynamic;     /* tracking: 10 x median mask                            */
+  int use_color_in_tracking;
+  const float* t_uniform; /* DEVICE [n_samples] torch.linspace(0,1,n_samples)       */
+  const float* t_surface; /* DEVICE [n_surface] torch.linspace(0,1,n_surface)       */
+  float max_depth_global; /* data-parallel mapping: max(target_d) over the all-rank
+                           * batch (far clamp and zero-depth sampling);
+                           * <= 0 -> computed from this call's rays                */
+} XrdNiceCfg;
+
+typedef struct {
+  float* rgb;         /* [R,3]                                                     */
+  double* depth;      /* [R]   float64 like the reference                          */
+  double* uncertainty;/* [R]                                                       */
+  double* z_vals;     /* [R,S] optional                                            */
+  float* raw;         /* [R,S,4] optional (rgb, occupancy logit)                   */
+  float* losses;      /* [2] depth_loss, rgb_loss (rgb 0 when the stage has none)  */
+} XrdNiceOut;
+
+typedef struct {
+  float* d_grid[3];            /* middle, fine, color: [Z][Y][X][32], ACCUMULATED;
+                                * NULL entries are skipped                         */
+  XrdNiceDecoderGrads* d_color;/* colour-decoder gradients or NULL (frozen)         */
+  float* d_rays_o;             /* [R,3] or NULL                                     */
+  float* d_rays_d;             /* [R,3] or NULL                                     */
+} XrdNiceGrads;
+
+size_t xrd_nice_workspace_bytes(int n_rays, int n_samples_total, int with_grads);
+
+/* decoders[3] = middle, fine, color; grids[3] = middle, fine, color. */
+int xrd_nice_step(const XrdRays* rays, const XrdNiceGrid grids[3],
+                  const XrdNiceDecoder decoders[3], const XrdNiceCfg* cfg,
+                  XrdNiceOut* out, XrdNiceGrads* grads, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

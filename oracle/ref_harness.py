@@ -83,3 +83,44 @@ def ref_joint_encoding(bounding_box, camera=None, **cfg_overrides):
     kw.update(cfg_overrides)
     cfg = JointEncodingConfig(**kw)
     return JointEncoding(cfg, camera=camera, bounding_box=bounding_box)
+
+
+def ref_conv_onet(bounding_box, camera=None, **cfg_overrides):
+    """Instantiate the reference's ConvOnet (NICE-SLAM model) on CPU.  The pretrained
+    decoder files are Git-LFS pointer stubs -> load_pretrain is bypassed and
+    the decoders keep their seeded xavier init."""
+    install()
+    import torch
+    from slam.common.camera import Camera
+    from slam.models.conv_onet import ConvOnet, ConvOnetConfig
+    if camera is None:
+        camera = Camera(320.0, 320.0, 319.5, 239.5, 640, 480)
+    kw = dict(coarse=False, mapping_frustum_feature_selection=False)
+    kw.update(cfg_overrides)
+    orig = ConvOnet.load_pretrain
+    ConvOnet.load_pretrain = lambda self: None
+    try:
+        model = ConvOnet(ConvOnetConfig(**kw), camera=camera,
+                         bounding_box=torch.as_tensor(bounding_box, dtype=torch.float64).clone())
+    finally:
+        ConvOnet.load_pretrain = orig
+    return model
+
+
+def copy_nice_ref_to_oracle(ref, ora):
+    """Copy decoders + grids of a reference ConvOnet into oracle.nice.NiceOracle."""
+    import torch
+    with torch.no_grad():
+        for name in ('middle', 'fine', 'color'):
+            r = getattr(ref.decoder, name + '_decoder')
+            o = getattr(ora, name)
+            o.B.copy_(r.embedder._B)
+            for i in range(5):
+                o.fc_c[i].weight.copy_(r.fc_c[i].weight)
+                o.fc_c[i].bias.copy_(r.fc_c[i].bias)
+                o.pts[i].weight.copy_(r.pts_linears[i].weight)
+                o.pts[i].bias.copy_(r.pts_linears[i].bias)
+            o.out.weight.copy_(r.output_linear.weight)
+            o.out.bias.copy_(r.output_linear.bias)
+        for k in ('grid_middle', 'grid_fine', 'grid_color'):
+            ora.grids[k].copy_(ref.grid_c[k])

@@ -1,0 +1,128 @@
+"""Parity of the NICE-SLAM CUDA path (C-ABI) against oracle/nice.py (itself pinned to the
+reference's ConvOnet).  Tolerances: the Gaussian Fourier embedding feeds sin() arguments of
+several hundred radians, so one ulp of the argument is ~3e-5 absolute in the embedding;
+fp32 oracle vs fp32 kernel agree to ~1e-4 on outputs (stated per assert)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import max_abs, rel_err
+
+BOUND = np.array([[-2.0, 2.0], [-2.0, 2.0], [-2.0, 2.0]])
+
+
+def nice_pair(device, seed=0, grid_amp=30.0):
+    from oracle.nice import NiceOracle
+    from xrdslam_b200.camera import Camera
+    from xrdslam_b200.conv_onet import ConvOnetConfig
+    ora = NiceOracle(BOUND, seed=seed)
+    g = torch.Generator().manual_seed(seed + 5)
+    with torch.no_grad():
+        for k in ora.grids:
+            ora.grids[k].mul_(grid_amp)
+        for dec in (ora.middle, ora.fine, ora.color):
+            dec.B.mul_(0.2)  # keep sin() arguments moderate for a tight comparison
+            for lin in list(dec.fc_c) + list(dec.pts) + [dec.out]:
+                lin.bias.copy_(torch.randn(lin.bias.shape, generator=g) * 0.1)
+    model = ConvOnetConfig(mapping_frustum_feature_selection=False).setup(
+        camera=Camera(320., 320., 319.5, 239.5, 640, 480), bounding_box=BOUND)
+    with torch.no_grad():
+        for name in ('middle', 'fine', 'color'):
+            o = getattr(ora, name)
+            m = getattr(model.decoder, name + '_decoder')
+            m.embedder._B.copy_(o.B)
+            for i in range(5):
+                m.fc_c[i].weight.copy_(o.fc_c[i].weight); m.fc_c[i].bias.copy_(o.fc_c[i].bias)
+                m.pts_linears[i].weight.copy_(o.pts[i].weight)
+                m.pts_linears[i].bias.copy_(o.pts[i].bias)
+            m.output_linear.weight.copy_(o.out.weight); m.output_linear.bias.copy_(o.out.bias)
+        for k in ora.grids:
+            model.set_grid(k, ora.grids[k])
+    assert torch.equal(model.bounding_box, ora.bound)
+    model.to(device)
+    return ora, model
+
+
+def rays(R, seed):
+    g = torch.Generator().manual_seed(seed)
+    rays_o = (torch.rand(R, 3, generator=g) - 0.5) * 0.6
+    rays_d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    td = torch.rand(R, 1, generator=g) * 1.5 + 0.3
+    td[3::7] = 0
+    ts = torch.rand(R, 3, generator=g)
+    return rays_o, rays_d, ts, td
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('stage', ['middle', 'fine', 'color'])
+@pytest.mark.parametrize('is_mapping', [True, False])
+def test_nice_step_parity(cuda_dev, stage, is_mapping):
+    ora, model = nice_pair(cuda_dev)
+    R = 200
+    rays_o, rays_d, ts, td = rays(R, 11)
+    rays_o.requires_grad_(True)
+    rays_d.requires_grad_(True)
+    out_o, ld_o, tot_o = ora.step(rays_o, rays_d, ts, td, is_mapping, stage)
+    tot_o.backward()
+    ro = rays_o.detach().to(cuda_dev).requires_grad_(True)
+    rd = rays_d.detach().to(cuda_dev).requires_grad_(True)
+    inp = dict(rays_o=ro, rays_d=rd, target_s=ts.to(cuda_dev), target_d=td.to(cuda_dev),
+               stage=stage, is_mapping=is_mapping)
+    out = model(inp)
+    ld = model.get_loss_dict(out, inp, is_mapping, stage)
+    assert set(ld) == set(ld_o)
+    sum(ld.values()).backward()
+    torch.cuda.synchronize()
+    assert max_abs(out['depth'], out_o['depth']) < 2e-4
+    assert max_abs(out['uncertainty'], out_o['uncertainty']) < 2e-4
+    assert max_abs(out['rgb'], out_o['rgb']) < 2e-4
+    for k in ld_o:
+        a, b = float(ld[k].detach()), float(ld_o[k].detach())
+        assert abs(a - b) <= 2e-4 * max(abs(b), 1.0), (k, a, b)
+    names = ['grid_middle'] + (['grid_fine'] if stage != 'middle' else []) + \
+        (['grid_color'] if stage == 'color' else [])
+    for k in names:
+        g_o = ora.grids[k].grad.squeeze(0).permute(1, 2, 3, 0)
+        assert rel_err(model.grids[k].grad, g_o) < 2e-3, k
+    assert rel_err(ro.grad, rays_o.grad) < 5e-3
+    assert rel_err(rd.grad, rays_d.grad) < 5e-3
+    if stage == 'color':
+        m, o = model.decoder.color_decoder, ora.color
+        assert rel_err(m.embedder._B.grad, o.B.grad) < 5e-3
+        for i in range(5):
+            assert rel_err(m.pts_linears[i].weight.grad, o.pts[i].weight.grad) < 2e-3, i
+            assert rel_err(m.pts_linears[i].bias.grad, o.pts[i].bias.grad) < 2e-3, i
+            assert rel_err(m.fc_c[i].weight.grad, o.fc_c[i].weight.grad) < 2e-3, i
+            assert rel_err(m.fc_c[i].bias.grad, o.fc_c[i].bias.grad) < 2e-3, i
+        assert rel_err(m.output_linear.weight.grad[:3], o.out.weight.grad[:3]) < 2e-3
+        assert rel_err(m.output_linear.bias.grad[:3], o.out.bias.grad[:3]) < 2e-3
+
+
+@pytest.mark.gpu
+def test_nice_z_vals_bit_exact(cuda_dev):
+    """float64 sample depths (far from the bound, surface band, sort) are bit-exact."""
+    import ctypes as C
+    from xrdslam_b200 import _cabi
+    ora, model = nice_pair(cuda_dev)
+    R = 333
+    rays_o, rays_d, ts, td = rays(R, 5)
+    z_o = ora.sample_z(rays_o, rays_d, td)
+    # run forward-only with z output requested through the raw C-ABI
+    dev = cuda_dev
+    o, _ = model._launch('middle', True, rays_o.to(dev), rays_d.to(dev), None, td.to(dev), False)
+    # z_vals are internal unless requested: call again capturing them
+    z = torch.empty(R, 48, dtype=torch.float64, device=dev)
+    model._z_capture = z
+    o2, _ = model._launch('middle', True, rays_o.to(dev), rays_d.to(dev), None, td.to(dev), False)
+    assert torch.equal(z.cpu(), z_o)
+
+
+def test_nice_shapes_match_survey_q2():
+    """Default office0 bound -> middle 31x37x35, fine/color 63x75x71 (Z,Y,X)."""
+    from xrdslam_b200.camera import Camera
+    from xrdslam_b200.conv_onet import ConvOnetConfig
+    m = ConvOnetConfig().setup(camera=Camera(320., 320., 319.5, 239.5, 640, 480),
+                               bounding_box=np.array([[-5.5, 5.9], [-6.7, 5.4], [-4.7, 5.3]]))
+    assert tuple(m.grids['grid_middle'].shape) == (31, 37, 35, 32)
+    assert tuple(m.grids['grid_fine'].shape) == (63, 75, 71, 32)
+    assert tuple(m.grid_c['grid_color'].shape) == (1, 32, 63, 75, 71)

@@ -81,6 +81,39 @@ class XrdCoslamGrads(C.Structure):
                 ('d_rays_d', vp), ('loss_scale', C.c_float * 4)]
 
 
+class XrdNiceDecoder(C.Structure):
+    _fields_ = [('B', vp), ('pts_w', vp * 5), ('pts_b', vp * 5), ('fcc_w', vp * 5),
+                ('fcc_b', vp * 5), ('out_w', vp), ('out_b', vp), ('c_dim', C.c_int),
+                ('n_out', C.c_int)]
+
+
+class XrdNiceDecoderGrads(C.Structure):
+    _fields_ = [('B', vp), ('pts_w', vp * 5), ('pts_b', vp * 5), ('fcc_w', vp * 5),
+                ('fcc_b', vp * 5), ('out_w', vp), ('out_b', vp)]
+
+
+class XrdNiceGrid(C.Structure):
+    _fields_ = [('data', vp), ('nx', C.c_int), ('ny', C.c_int), ('nz', C.c_int)]
+
+
+class XrdNiceCfg(C.Structure):
+    _fields_ = [('stage', C.c_int), ('is_mapping', C.c_int), ('n_samples', C.c_int),
+                ('n_surface', C.c_int), ('bound_min', C.c_double * 3),
+                ('bound_max', C.c_double * 3), ('w_color', C.c_float),
+                ('handle_dynamic', C.c_int), ('use_color_in_tracking', C.c_int),
+                ('t_uniform', vp), ('t_surface', vp), ('max_depth_global', C.c_float)]
+
+
+class XrdNiceOut(C.Structure):
+    _fields_ = [('rgb', vp), ('depth', vp), ('uncertainty', vp), ('z_vals', vp),
+                ('raw', vp), ('losses', vp)]
+
+
+class XrdNiceGrads(C.Structure):
+    _fields_ = [('d_grid', vp * 3), ('d_color', C.POINTER(XrdNiceDecoderGrads)),
+                ('d_rays_o', vp), ('d_rays_d', vp)]
+
+
 _lib = None
 
 # name -> (restype, argtypes); every symbol include/xrdslam_b200.h declares
@@ -108,6 +141,12 @@ SYMBOLS = {
     ]),
     'xrd_hashgrid_encode':
     (C.c_int, [C.POINTER(XrdHashGrid), vp, C.c_int, vp, vp, vp]),
+    'xrd_nice_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    'xrd_nice_step': (C.c_int, [
+        C.POINTER(XrdRays), C.POINTER(XrdNiceGrid), C.POINTER(XrdNiceDecoder),
+        C.POINTER(XrdNiceCfg), C.POINTER(XrdNiceOut), C.POINTER(XrdNiceGrads), vp,
+        C.c_size_t, vp
+    ]),
 }
 
 

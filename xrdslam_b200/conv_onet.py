@@ -1,0 +1,329 @@
+"""NICE-SLAM model behind the reference's ``Model`` plugin surface, B200-native.
+
+Host-side mirror of slam/models/conv_onet.py (reference @ f0366f20): same class / config
+field names, same ``forward / get_loss_dict / get_param_groups`` signatures, same
+parameter-group names (``decoder``, ``grid_middle``, ``grid_fine``, ``grid_color``) and the
+decoder state_dict keys of slam/model_components/decoder_nice.py (``embedder._B``,
+``fc_c.i``, ``pts_linears.i``, ``output_linear``).  The render / loss / backward run in
+``xrd_nice_step`` (csrc/nice.cu) through the C-ABI; no PyTorch fallback exists.
+
+Feature grids are stored CHANNEL-LAST ``[Z,Y,X,32]`` (one voxel = one 128-byte line);
+``grid_c[key]`` exposes the reference layout ``[1,32,Z,Y,X]`` as a permuted view.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import Dict, List, Optional, Type, Union
+
+import numpy as np
+import torch
+from torch import nn
+from torch.nn import Parameter
+
+from . import _cabi
+from ._cabi import (XrdNiceCfg, XrdNiceDecoder, XrdNiceDecoderGrads, XrdNiceGrads,
+                    XrdNiceGrid, XrdNiceOut, XrdRays, check, ptr)
+from .base_model import Model, ModelConfig
+
+STAGES = {'middle': 0, 'fine': 1, 'color': 2}
+
+
+@dataclass
+class ConvOnetConfig(ModelConfig):
+    """slam/models/conv_onet.py:18-63 (field names and defaults kept)."""
+    _target: Type = field(default_factory=lambda: ConvOnet)
+    coarse: bool = False
+    occupancy: bool = True
+    pretrained_decoders_coarse: Optional[Path] = None
+    pretrained_decoders_middle_fine: Optional[Path] = None
+    data_dim: int = 3
+    model_c_dim: int = 32
+    model_pos_embedding_method: str = 'fourier'
+    model_coarse_bound_enlarge: int = 2
+    grid_len_coarse: float = 2
+    grid_len_middle: float = 0.32
+    grid_len_fine: float = 0.16
+    grid_len_color: float = 0.16
+    grid_bound_divisible: float = 0.32
+    rendering_n_samples: int = 32
+    rendering_n_surface: int = 16
+    rendering_n_importance: int = 0
+    rendering_lindisp: bool = False
+    rendering_perturb: float = 0.0
+    points_batch_size: int = 500000
+    tracking_w_color_loss: float = 0.5
+    mapping_w_color_loss: float = 0.2
+    tracking_handle_dynamic: bool = True
+    tracking_use_color_in_tracking: bool = True
+    mapping_fix_fine: bool = True
+    mapping_fix_color: bool = False
+    mapping_frustum_feature_selection: bool = True
+
+
+class _Embedder(nn.Module):
+    def __init__(self, gen=None):
+        super().__init__()
+        self._B = nn.Parameter(torch.randn((3, 93), generator=gen) * 25)
+
+
+class _DenseLayer(nn.Linear):
+    """decoder_nice.py:76-91: xavier_uniform with the activation's gain, zero bias."""
+    def __init__(self, in_dim, out_dim, activation='relu'):
+        self.activation = activation
+        super().__init__(in_dim, out_dim)
+
+    def reset_parameters(self) -> None:
+        nn.init.xavier_uniform_(self.weight,
+                                gain=nn.init.calculate_gain(self.activation))
+        if self.bias is not None:
+            nn.init.zeros_(self.bias)
+
+
+class MLP(nn.Module):
+    """Parameter container of decoder_nice.py:101-234 (hidden 32, 5 blocks, skip at 2)."""
+    def __init__(self, name, c_dim, color, hidden_size=32):
+        super().__init__()
+        self.name, self.c_dim, self.color = name, c_dim, color
+        self.fc_c = nn.ModuleList([nn.Linear(c_dim, hidden_size) for _ in range(5)])
+        self.embedder = _Embedder()
+        dims = [93, hidden_size, hidden_size, hidden_size + 93, hidden_size]
+        self.pts_linears = nn.ModuleList([_DenseLayer(d, hidden_size) for d in dims])
+        self.output_linear = _DenseLayer(hidden_size, 4 if color else 1, 'linear')
+
+    def tensors(self):
+        t = [self.embedder._B]
+        for i in range(5):
+            t += [self.pts_linears[i].weight, self.pts_linears[i].bias]
+        for i in range(5):
+            t += [self.fc_c[i].weight, self.fc_c[i].bias]
+        return t + [self.output_linear.weight, self.output_linear.bias]
+
+
+class NICE(nn.Module):
+    """decoder_nice.py:323-384 (coarse level unsupported, as in the reference config)."""
+    def __init__(self, c_dim=32):
+        super().__init__()
+        self.middle_decoder = MLP('middle', c_dim, False)
+        self.fine_decoder = MLP('fine', 2 * c_dim, False)
+        self.color_decoder = MLP('color', c_dim, True)
+
+
+def _dec_struct(tensors, c_dim, n_out, cls=XrdNiceDecoder):
+    d = cls()
+    d.B = ptr(tensors[0])
+    for i in range(5):
+        d.pts_w[i] = ptr(tensors[1 + 2 * i])
+        d.pts_b[i] = ptr(tensors[2 + 2 * i])
+        d.fcc_w[i] = ptr(tensors[11 + 2 * i])
+        d.fcc_b[i] = ptr(tensors[12 + 2 * i])
+    d.out_w = ptr(tensors[21])
+    d.out_b = ptr(tensors[22])
+    if cls is XrdNiceDecoder:
+        d.c_dim, d.n_out = c_dim, n_out
+    return d
+
+
+class _NiceStep(torch.autograd.Function):
+    """(losses[2], rgb, depth, uncertainty) = fused(rays, 3 grids, colour decoder)."""
+    @staticmethod
+    def forward(ctx, model, stage, is_mapping, target_s, target_d, rays_o, rays_d, gm, gf,
+                gc, *color_params):
+        need_rays = ctx.needs_input_grad[5] or ctx.needs_input_grad[6]
+        need_grid = [ctx.needs_input_grad[7 + i] for i in range(3)]
+        need_col = any(ctx.needs_input_grad[10:])
+        with_grads = need_rays or any(need_grid) or need_col
+        outs, grads = model._launch(stage, is_mapping, rays_o, rays_d, target_s, target_d,
+                                    with_grads, need_rays, need_grid, need_col)
+        ctx.grads = grads
+        ret = (outs['losses'], outs['rgb'], outs['depth'], outs['uncertainty'])
+        ctx.mark_non_differentiable(*ret[1:])
+        return ret
+
+    @staticmethod
+    def backward(ctx, g_losses, *_):
+        g = ctx.grads
+        if g is None:
+            raise RuntimeError('backward through a forward-only NICE pass')
+        return (None, None, None, None, None, g['d_rays_o'], g['d_rays_d'], g['d_grid'][0],
+                g['d_grid'][1], g['d_grid'][2], *g['d_color'])
+
+
+class ConvOnet(Model):
+    """Model class (slam/models/conv_onet.py:66-524)."""
+
+    config: ConvOnetConfig
+
+    def __init__(self, config: ConvOnetConfig, camera, bounding_box, **kwargs) -> None:
+        super().__init__(config=config, camera=camera, bounding_box=bounding_box, **kwargs)
+
+    def populate_modules(self):
+        super().populate_modules()
+        cfg = self.config
+        if cfg.coarse or cfg.rendering_n_importance or cfg.rendering_perturb or \
+                cfg.rendering_lindisp or not cfg.occupancy:
+            raise NotImplementedError('B200 path covers the reference nice-slam config: '
+                                      'coarse=False, occupancy, no importance sampling')
+        self.bounding_box = torch.as_tensor(np.asarray(self.bounding_box),
+                                            dtype=torch.float64).clone()
+        self.decoder = NICE(cfg.model_c_dim)
+        self.load_bound()
+        self.grid_init()
+        self.grid_opti_mask = {}
+        self.register_buffer('_t_uniform', torch.linspace(0., 1., steps=cfg.rendering_n_samples),
+                             persistent=False)
+        self.register_buffer('_t_surface', torch.linspace(0., 1., steps=cfg.rendering_n_surface),
+                             persistent=False)
+
+    def load_bound(self):
+        """conv_onet.py:324-337 with its dtype chain (int32 * python float -> float32, Q2)."""
+        bd = self.config.grid_bound_divisible
+        self.bounding_box[:, 1] = (((self.bounding_box[:, 1] - self.bounding_box[:, 0]) /
+                                    bd).int() + 1) * bd + self.bounding_box[:, 0]
+
+    def grid_init(self):
+        """conv_onet.py:254-291 + feature_grid_nice.py (shapes), channel-last storage."""
+        cfg = self.config
+        xyz_len = self.bounding_box[:, 1] - self.bounding_box[:, 0]
+        self.grids = nn.ParameterDict()
+        for key, gl, std in (('grid_middle', cfg.grid_len_middle, 0.01),
+                             ('grid_fine', cfg.grid_len_fine, 0.0001),
+                             ('grid_color', cfg.grid_len_color, 0.01)):
+            s = list(map(int, (xyz_len / gl).tolist()))  # (X, Y, Z) counts
+            val = torch.zeros([s[2], s[1], s[0], cfg.model_c_dim]).normal_(mean=0, std=std)
+            self.grids[key] = nn.Parameter(val)
+
+    @property
+    def grid_c(self):
+        """Reference layout views [1, C, Z, Y, X]."""
+        return {k: v.permute(3, 0, 1, 2).unsqueeze(0) for k, v in self.grids.items()}
+
+    def set_grid(self, key, val_ref_layout):
+        with torch.no_grad():
+            self.grids[key].copy_(val_ref_layout.squeeze(0).permute(1, 2, 3, 0))
+
+    # ------------------------------------------------------------- C-ABI ---
+    def _launch(self, stage, is_mapping, rays_o, rays_d, target_s, target_d, with_grads,
+                need_rays=False, need_grid=(False, False, False), need_col=False):
+        cfg = self.config
+        dev = self.grids['grid_middle'].device
+        if dev.type != 'cuda':
+            raise RuntimeError('xrdslam_b200 has no CPU path: model must be on a CUDA device')
+        lib = _cabi.lib()
+        f32 = dict(dtype=torch.float32, device=dev)
+        f64 = dict(dtype=torch.float64, device=dev)
+        rays_o = rays_o.detach().to(**f32).contiguous()
+        rays_d = rays_d.detach().to(**f32).contiguous()
+        R = rays_o.shape[0]
+        S = cfg.rendering_n_samples + cfg.rendering_n_surface
+        td = target_d.detach().to(**f32).reshape(-1).contiguous()
+        ts = target_s.detach().to(**f32).contiguous() if target_s is not None else None
+        o = dict(rgb=torch.empty(R, 3, **f32), depth=torch.empty(R, **f64),
+                 uncertainty=torch.empty(R, **f64), losses=torch.zeros(2, **f32))
+        rays = XrdRays(R, ptr(rays_o), ptr(rays_d), ptr(ts), ptr(td))
+        keys = ('grid_middle', 'grid_fine', 'grid_color')
+        grids = (XrdNiceGrid * 3)()
+        for i, k in enumerate(keys):
+            g = self.grids[k].detach()
+            grids[i] = XrdNiceGrid(ptr(g), g.shape[2], g.shape[1], g.shape[0])
+        decs = (XrdNiceDecoder * 3)()
+        dmods = (self.decoder.middle_decoder, self.decoder.fine_decoder,
+                 self.decoder.color_decoder)
+        for i, m in enumerate(dmods):
+            decs[i] = _dec_struct([t.detach() for t in m.tensors()], m.c_dim, 4 if m.color else 1)
+        c = XrdNiceCfg()
+        c.stage = STAGES[stage]
+        c.is_mapping = int(is_mapping)
+        c.n_samples, c.n_surface = cfg.rendering_n_samples, cfg.rendering_n_surface
+        for d in range(3):
+            c.bound_min[d] = float(self.bounding_box[d, 0])
+            c.bound_max[d] = float(self.bounding_box[d, 1])
+        c.w_color = cfg.mapping_w_color_loss if is_mapping else cfg.tracking_w_color_loss
+        c.handle_dynamic = int(cfg.tracking_handle_dynamic)
+        c.use_color_in_tracking = int(cfg.tracking_use_color_in_tracking)
+        c.t_uniform, c.t_surface = ptr(self._t_uniform), ptr(self._t_surface)
+        c.max_depth_global = 0.0
+        zc = getattr(self, '_z_capture', None)  # tests: capture the f64 sample depths
+        out = XrdNiceOut(ptr(o['rgb']), ptr(o['depth']), ptr(o['uncertainty']), ptr(zc), None,
+                         ptr(o['losses']))
+        g = None
+        gs = None
+        keep = []
+        if with_grads:
+            if ts is None:
+                raise RuntimeError('gradients need target_s')
+            dgrid = [torch.zeros_like(self.grids[k]) if (need_grid[i] and i <= c.stage) else None
+                     for i, k in enumerate(keys)]
+            dcol = None
+            if need_col and c.stage == 2:
+                dcol = [torch.zeros_like(t) for t in self.decoder.color_decoder.tensors()]
+            g = dict(d_grid=dgrid, d_color=dcol if dcol is not None else [None] * 23,
+                     d_rays_o=torch.empty(R, 3, **f32) if need_rays else None,
+                     d_rays_d=torch.empty(R, 3, **f32) if need_rays else None)
+            gs = XrdNiceGrads()
+            for i in range(3):
+                gs.d_grid[i] = ptr(dgrid[i])
+            if dcol is not None:
+                dg = _dec_struct(dcol, 0, 0, XrdNiceDecoderGrads)
+                keep.append(dg)
+                gs.d_color = C.pointer(dg)
+            gs.d_rays_o, gs.d_rays_d = ptr(g['d_rays_o']), ptr(g['d_rays_d'])
+        nb = lib.xrd_nice_workspace_bytes(R, S, int(with_grads))
+        ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            st = lib.xrd_nice_step(C.byref(rays), grids, decs, C.byref(c), C.byref(out),
+                                   C.byref(gs) if gs is not None else None, ptr(ws), nb,
+                                   torch.cuda.current_stream(dev).cuda_stream)
+        check('xrd_nice_step', st)
+        return o, g
+
+    # --------------------------------------------------------- Model API ---
+    def get_outputs(self, input) -> Dict[str, Union[torch.Tensor, List]]:
+        """conv_onet.py:132-143."""
+        stage = input['stage']
+        if stage == 'coarse':
+            raise NotImplementedError('coarse level (reference: "TODO: support True")')
+        rays_o, rays_d = input['rays_o'], input['rays_d']
+        target_d, target_s = input['target_d'], input.get('target_s')
+        fused = torch.is_grad_enabled() and target_s is not None and 'is_mapping' in input
+        if fused:
+            cparams = self.decoder.color_decoder.tensors()
+            losses, rgb, depth, unc = _NiceStep.apply(
+                self, stage, input['is_mapping'], target_s, target_d, rays_o, rays_d,
+                self.grids['grid_middle'], self.grids['grid_fine'], self.grids['grid_color'],
+                *cparams)
+            return {'rgb': rgb, 'depth': depth, 'uncertainty': unc, '_losses': losses}
+        o, _ = self._launch(stage, True, rays_o, rays_d, target_s, target_d, False)
+        o.pop('losses')
+        return o
+
+    def get_loss_dict(self, outputs, inputs, is_mapping, stage=None) -> Dict[str, torch.Tensor]:
+        """conv_onet.py:145-185: terms come from the fused pass (forward needs
+        ``input['is_mapping']`` -- the Algorithm sets it -- to pick the loss form)."""
+        if '_losses' not in outputs:
+            raise RuntimeError('get_loss_dict needs a forward() run with grad enabled, '
+                               "target_s and input['is_mapping']")
+        if bool(inputs['is_mapping']) != bool(is_mapping):
+            raise RuntimeError("input['is_mapping'] disagrees with get_loss_dict(is_mapping)")
+        ls = outputs['_losses']
+        d = {'depth_loss': ls[0]}
+        cfg = self.config
+        if (not is_mapping and cfg.tracking_use_color_in_tracking) or \
+                (is_mapping and (stage or inputs['stage']) == 'color'):
+            d['rgb_loss'] = ls[1]
+        return d
+
+    def get_param_groups(self) -> Dict[str, List[Parameter]]:
+        """conv_onet.py:187-211 (frustum-masked sub-selection is SURVEY row f2)."""
+        groups = {}
+        dec = []
+        if not self.config.mapping_fix_fine:
+            raise NotImplementedError('mapping_fix_fine=False')
+        if not self.config.mapping_fix_color:
+            dec += list(self.decoder.color_decoder.parameters())
+        if dec:
+            groups['decoder'] = dec
+        for key in ('grid_middle', 'grid_fine', 'grid_color'):
+            groups[key] = [self.grids[key]]
+        return groups
