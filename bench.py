@@ -126,7 +126,9 @@ def build_algorithm(device, seed):
     np.random.seed(seed)
     torch.manual_seed(seed)
     cam, poses, frames = make_sequence(N_KEYFRAMES + 1)
-    algo = CoSLAMConfig().setup(camera=cam, device=device)
+    cfg = CoSLAMConfig()
+    cfg.model.precision = 1  # 3xTF32 forward (fp32-level outputs/losses), TF32 backward
+    algo = cfg.setup(camera=cam, device=device)
     kfs = []
     for k in range(N_KEYFRAMES):
         f = Frame(k, frames[k][0], frames[k][1], init_pose=poses[k],
@@ -143,17 +145,11 @@ def flat_params(model):
     return [model.embed_fn.params] + list(model.decoder.parameters())
 
 
-def allreduce_grads(params, world):
-    if world == 1:
-        return
-    import torch.distributed as dist
-    from torch._utils import _flatten_dense_tensors, _unflatten_dense_tensors
-    grads = [p.grad for p in params]
-    flat = _flatten_dense_tensors(grads)
-    dist.all_reduce(flat)
-    flat.div_(world)
-    for g, f in zip(grads, _unflatten_dense_tensors(flat, grads)):
-        g.copy_(f)
+def allreduce_grads(dp):
+    """ONE NCCL all-reduce over the flat gradient bucket (hash table + decoder).  The loss
+    normalisers inside the kernels are already batch-global (model.dp), so the sum of the
+    per-rank gradients IS the gradient of the all-rank batch: no division."""
+    dp.all_reduce_grads()
 
 
 def run_ours(args):
@@ -175,9 +171,10 @@ def run_ours(args):
     K, W = args.steps, args.warmup
     R = MAP_KF + MAP_CUR
     params = flat_params(model)
-    if world > 1:  # identical replicas
-        for p in params:
-            dist.broadcast(p.data, 0)
+    from xrdslam_b200.dp import MappingDataParallel
+    dp = MappingDataParallel(params)
+    dp.broadcast_params(0)  # identical replicas
+    model.dp = dp
     optim = algo.setup_optimizers(K, frames, is_mapping=True)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
@@ -195,7 +192,7 @@ def run_ours(args):
         loss_dict = model.get_loss_dict(out, inp, True, 0)
         loss = sum(loss_dict.values())
         loss.backward()
-        allreduce_grads(params, world)
+        allreduce_grads(dp)
         optim.optimizer_step_all(step=0)
         return loss
 
@@ -273,7 +270,7 @@ def run_ours(args):
         optim.zero_grad_all()
         loss = algo.get_loss(frames, True, i, K)
         loss.backward()
-        allreduce_grads(params, world)
+        allreduce_grads(dp)
         optim.optimizer_step_all(step=i)
         loss.item()
     barrier()
@@ -282,7 +279,7 @@ def run_ours(args):
         optim.zero_grad_all()
         loss = algo.get_loss(frames, True, i, K)
         loss.backward()
-        allreduce_grads(params, world)
+        allreduce_grads(dp)
         optim.optimizer_step_all(step=i)
         lv = loss.item()  # D2H read of the step's result
     barrier()
@@ -325,7 +322,8 @@ def run_ours(args):
             'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': ms_total / K, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'co-slam hash-grid(16 lvl x 2 feat, 2^16) + OneBlob16, '
+            'config': {'precision': 'fp32 gathers/compositing/loss; decoder GEMMs 3xTF32 forward, TF32 backward (fp32 accumulate)',
+                       'workload': 'co-slam hash-grid(16 lvl x 2 feat, 2^16) + OneBlob16, '
                                    '640x480 synthetic room, mapping iteration, '
                                    f'{MAP_KF} keyframe-bank + {MAP_CUR} current-frame rays per GPU, '
                                    '43 samples/ray, smoothness 31^3, '

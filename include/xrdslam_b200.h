@@ -254,9 +254,10 @@ typedef struct {
   int use_color_in_tracking;
   const float* t_uniform; /* DEVICE [n_samples] torch.linspace(0,1,n_samples)       */
   const float* t_surface; /* DEVICE [n_surface] torch.linspace(0,1,n_surface)       */
-  float max_depth_global; /* data-parallel mapping: max(target_d) over the all-rank
-                           * batch (far clamp and zero-depth sampling);
-                           * <= 0 -> computed from this call's rays                */
+  const float* max_depth_global; /* DEVICE scalar: max(target_d) over the all-rank batch
+                           * under data-parallel mapping (far clamp and zero-depth
+                           * sampling are batch-global); NULL -> computed
+                           * from this call's rays                                  */
 } XrdNiceCfg;
 
 typedef struct {

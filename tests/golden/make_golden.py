@@ -73,6 +73,66 @@ def coslam(R=96, seed=7):
     print('wrote coslam_map_step.npz')
 
 
+def nice(R=120, seed=3):
+    """Reference ConvOnet (slam/models/conv_onet.py), stage 'color' -- the one stage that
+    runs on CPU -- mapping and tracking losses, with gradients."""
+    bound = np.array([[-2.0, 2.0], [-2.0, 2.0], [-2.0, 2.0]])
+    torch.manual_seed(seed)
+    ref = ref_harness.ref_conv_onet(bound)
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for i, k in enumerate(sorted(ref.grid_c)):
+            # regenerated from the seed by the tests (keeps the fixture small)
+            gg = torch.Generator().manual_seed(1000 + i)
+            ref.grid_c[k] = (torch.randn(ref.grid_c[k].shape, generator=gg) * 0.3
+                             ).requires_grad_(True)
+        for dec in (ref.decoder.middle_decoder, ref.decoder.fine_decoder,
+                    ref.decoder.color_decoder):
+            dec.embedder._B.mul_(0.2)
+            for lin in list(dec.fc_c) + list(dec.pts_linears) + [dec.output_linear]:
+                lin.bias.copy_(torch.randn(lin.bias.shape, generator=g) * 0.1)
+    rays_o = ((torch.rand(R, 3, generator=g) - 0.5) * 0.6).requires_grad_(True)
+    rays_d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g),
+                                           dim=-1).requires_grad_(True)
+    td = torch.rand(R, 1, generator=g) * 1.5 + 0.3
+    td[3::7] = 0
+    ts = torch.rand(R, 3, generator=g)
+    blob = dict(bound=bound, rays_o=rays_o.detach().numpy(), rays_d=rays_d.detach().numpy(),
+                target_s=ts.numpy(), target_d=td.numpy())
+    sd = ref.decoder.state_dict()
+    for k, v in sd.items():
+        blob['dec.' + k] = v.numpy()
+    for k, v in ref.grid_c.items():
+        blob[k + '.shape'] = np.array(v.shape)
+        blob[k + '.checksum'] = np.float64(v.detach().double().sum().item())
+    for tag, is_mapping in (('map', True), ('trk', False)):
+        for t in [rays_o, rays_d] + list(ref.grid_c.values()) + list(ref.decoder.parameters()):
+            t.grad = None
+        inp = dict(rays_o=rays_o, rays_d=rays_d, target_s=ts, target_d=td, stage='color')
+        out = ref(inp)
+        ld = ref.get_loss_dict(out, inp, is_mapping, 'color')
+        sum(ld.values()).backward()
+        blob[tag + '.rgb'] = out['rgb'].detach().numpy()
+        blob[tag + '.depth'] = out['depth'].detach().numpy()
+        blob[tag + '.uncertainty'] = out['uncertainty'].detach().numpy()
+        blob[tag + '.losses'] = np.array([float(ld['depth_loss'].detach()),
+                                          float(ld['rgb_loss'].detach())])
+        blob[tag + '.d_rays_o'] = rays_o.grad.numpy().copy()
+        blob[tag + '.d_rays_d'] = rays_d.grad.numpy().copy()
+        gcg = ref.grid_c['grid_color'].grad
+        blob[tag + '.d_grid_color_norm'] = np.float64(gcg.double().norm().item())
+        blob[tag + '.d_grid_color_slice'] = gcg[0, :, 10:14, 10:14, 10:14].numpy().copy()
+        blob[tag + '.d_grid_middle_norm'] = np.float64(
+            ref.grid_c['grid_middle'].grad.double().norm().item())
+        cd = ref.decoder.color_decoder
+        blob[tag + '.d_B'] = cd.embedder._B.grad.numpy().copy()
+        blob[tag + '.d_pts3_w'] = cd.pts_linears[3].weight.grad.numpy().copy()
+        blob[tag + '.d_fcc0_w'] = cd.fc_c[0].weight.grad.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, 'nice_color_step.npz'), **blob)
+    print('wrote nice_color_step.npz')
+
+
 if __name__ == '__main__':
     assert ref_harness.available(), 'needs /root/reference'
     coslam()
+    nice()

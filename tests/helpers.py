@@ -83,3 +83,53 @@ def set_coslam_params(obj, g, kind):
             obj.decoder.sdf_net.model[2].weight.copy_(t('w_sdf1'))
             obj.decoder.color_net.model[0].weight.copy_(t('w_col0'))
             obj.decoder.color_net.model[2].weight.copy_(t('w_col1'))
+
+
+def load_golden_nice():
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden',
+                             'nice_color_step.npz'))
+    g = {k: g[k] for k in g.files}
+    for i, k in enumerate(sorted(['grid_middle', 'grid_fine', 'grid_color'])):
+        gg = torch.Generator().manual_seed(1000 + i)
+        g[k] = torch.randn(tuple(int(v) for v in g[k + '.shape']), generator=gg) * 0.3
+        assert abs(float(g[k].double().sum()) - float(g[k + '.checksum'])) < 1e-6
+    return g
+
+
+def nice_from_golden(g, kind, device=None):
+    """Build an oracle (kind='oracle') or B200 model from the golden parameters."""
+    t = lambda k: torch.from_numpy(g[k])
+    if kind == 'oracle':
+        from oracle.nice import NiceOracle
+        obj = NiceOracle(g['bound'])
+        decs = {'middle': obj.middle, 'fine': obj.fine, 'color': obj.color}
+    else:
+        from xrdslam_b200.camera import Camera
+        from xrdslam_b200.conv_onet import ConvOnetConfig
+        obj = ConvOnetConfig(mapping_frustum_feature_selection=False).setup(
+            camera=Camera(320., 320., 319.5, 239.5, 640, 480), bounding_box=g['bound'])
+        decs = {n: getattr(obj.decoder, n + '_decoder') for n in ('middle', 'fine', 'color')}
+    with torch.no_grad():
+        for n, d in decs.items():
+            pre = f'dec.{n}_decoder.'
+            if kind == 'oracle':
+                d.B.copy_(t(pre + 'embedder._B'))
+                for i in range(5):
+                    d.fc_c[i].weight.copy_(t(pre + f'fc_c.{i}.weight'))
+                    d.fc_c[i].bias.copy_(t(pre + f'fc_c.{i}.bias'))
+                    d.pts[i].weight.copy_(t(pre + f'pts_linears.{i}.weight'))
+                    d.pts[i].bias.copy_(t(pre + f'pts_linears.{i}.bias'))
+                d.out.weight.copy_(t(pre + 'output_linear.weight'))
+                d.out.bias.copy_(t(pre + 'output_linear.bias'))
+            else:
+                sd = {k[len(pre):]: t(k) for k in g if k.startswith(pre)}
+                d.load_state_dict(sd)  # same state_dict keys as the reference decoder
+        for k in ('grid_middle', 'grid_fine', 'grid_color'):
+            if kind == 'oracle':
+                obj.grids[k].copy_(g[k])
+            else:
+                obj.set_grid(k, g[k])
+    if device is not None:
+        obj.to(device)
+    return obj

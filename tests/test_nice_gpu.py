@@ -126,3 +126,36 @@ def test_nice_shapes_match_survey_q2():
     assert tuple(m.grids['grid_middle'].shape) == (31, 37, 35, 32)
     assert tuple(m.grids['grid_fine'].shape) == (63, 75, 71, 32)
     assert tuple(m.grid_c['grid_color'].shape) == (1, 32, 63, 75, 71)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('tag,is_mapping', [('map', True), ('trk', False)])
+def test_nice_cuda_matches_reference_golden(cuda_dev, tag, is_mapping):
+    """CUDA path vs vectors produced by the reference's own ConvOnet class."""
+    from helpers import load_golden_nice, nice_from_golden
+    g = load_golden_nice()
+    model = nice_from_golden(g, 'model', cuda_dev)
+    t = lambda k: torch.from_numpy(g[k]).to(cuda_dev)
+    ro = t('rays_o').requires_grad_(True)
+    rd = t('rays_d').requires_grad_(True)
+    inp = dict(rays_o=ro, rays_d=rd, target_s=t('target_s'), target_d=t('target_d'),
+               stage='color', is_mapping=is_mapping)
+    out = model(inp)
+    ld = model.get_loss_dict(out, inp, is_mapping, 'color')
+    sum(ld.values()).backward()
+    assert np.abs(out['rgb'].cpu().numpy() - g[tag + '.rgb']).max() < 2e-4
+    assert np.abs(out['depth'].cpu().numpy() - g[tag + '.depth']).max() < 2e-4
+    got = np.array([float(ld['depth_loss'].detach()), float(ld['rgb_loss'].detach())])
+    assert np.allclose(got, g[tag + '.losses'], rtol=2e-4)
+    assert rel_err(ro.grad, torch.from_numpy(g[tag + '.d_rays_o'])) < 5e-3
+    assert rel_err(rd.grad, torch.from_numpy(g[tag + '.d_rays_d'])) < 5e-3
+    cd = model.decoder.color_decoder
+    assert rel_err(cd.embedder._B.grad, torch.from_numpy(g[tag + '.d_B'])) < 5e-3
+    assert rel_err(cd.pts_linears[3].weight.grad, torch.from_numpy(g[tag + '.d_pts3_w'])) < 2e-3
+    assert rel_err(cd.fc_c[0].weight.grad, torch.from_numpy(g[tag + '.d_fcc0_w'])) < 2e-3
+    gc = model.grid_c['grid_color'].grad if False else model.grids['grid_color'].grad
+    gc_ref_layout = gc.permute(3, 0, 1, 2)
+    assert abs(float(gc.double().norm()) - float(g[tag + '.d_grid_color_norm'])) \
+        <= 2e-3 * float(g[tag + '.d_grid_color_norm'])
+    assert rel_err(gc_ref_layout[:, 10:14, 10:14, 10:14],
+                   torch.from_numpy(g[tag + '.d_grid_color_slice'])) < 2e-3

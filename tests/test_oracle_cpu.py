@@ -182,3 +182,66 @@ def test_synthetic_scene_and_host_sampling():
     assert np.allclose(d.reshape(-1).numpy(), depth[jj.numpy(), ii.numpy()])
     full_o, full_d = get_rays(cam, torch.from_numpy(poses[0]), 'cpu')
     assert torch.allclose(rd, full_d[jj, ii], atol=1e-6)
+
+
+def test_nice_oracle_matches_golden_reference_vectors():
+    """oracle/nice.py == vectors produced by the reference's ConvOnet (stage color)."""
+    from helpers import load_golden_nice, nice_from_golden
+    g = load_golden_nice()
+    ora = nice_from_golden(g, 'oracle')
+    t = lambda k: torch.from_numpy(g[k])
+    for tag, is_mapping in (('map', True), ('trk', False)):
+        ora.zero_grad()
+        rays_o = t('rays_o').requires_grad_(True)
+        rays_d = t('rays_d').requires_grad_(True)
+        out, ld, tot = ora.step(rays_o, rays_d, t('target_s'), t('target_d'), is_mapping, 'color')
+        tot.backward()
+        assert np.array_equal(out['rgb'].detach().numpy(), g[tag + '.rgb'])
+        assert np.array_equal(out['depth'].detach().numpy(), g[tag + '.depth'])
+        assert np.array_equal(out['uncertainty'].detach().numpy(), g[tag + '.uncertainty'])
+        got = [float(ld['depth_loss'].detach()), float(ld['rgb_loss'].detach())]
+        assert np.allclose(got, g[tag + '.losses'], rtol=1e-7, atol=0)
+        assert np.allclose(rays_o.grad.numpy(), g[tag + '.d_rays_o'], rtol=1e-5, atol=1e-7)
+        assert np.allclose(ora.color.B.grad.numpy(), g[tag + '.d_B'], rtol=1e-5, atol=1e-6)
+        assert np.allclose(ora.color.pts[3].weight.grad.numpy(), g[tag + '.d_pts3_w'],
+                           rtol=1e-5, atol=1e-6)
+        gc = ora.grids['grid_color'].grad
+        assert abs(float(gc.double().norm()) - float(g[tag + '.d_grid_color_norm'])) \
+            <= 1e-6 * float(g[tag + '.d_grid_color_norm'])
+
+
+@pytest.mark.needs_reference
+def test_nice_oracle_matches_reference_class_live():
+    from oracle import ref_harness
+    from oracle.nice import NiceOracle
+    bound = np.array([[-2.0, 2.0], [-2.0, 2.0], [-2.0, 2.0]])
+    torch.manual_seed(1)
+    ref = ref_harness.ref_conv_onet(bound)
+    ora = NiceOracle(bound)
+    ref_harness.copy_nice_ref_to_oracle(ref, ora)
+    with torch.no_grad():
+        for k in ora.grids:
+            ora.grids[k].mul_(30)
+            ref.grid_c[k] = ref.grid_c[k] * 30
+    assert torch.equal(ref.bounding_box, ora.bound)
+    g = torch.Generator().manual_seed(2)
+    R = 64
+    rays_o = (torch.rand(R, 3, generator=g) - 0.5) * 0.5
+    rays_d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    td = torch.rand(R, 1, generator=g) * 1.5 + 0.3
+    td[3::7] = 0
+    ts = torch.rand(R, 3, generator=g)
+    inp = dict(rays_o=rays_o, rays_d=rays_d, target_s=ts, target_d=td, stage='color')
+    out_r = ref(inp)
+    out_o = ora.render(rays_o, rays_d, td, 'color')
+    for k in ('rgb', 'depth', 'uncertainty'):
+        assert torch.equal(out_r[k], out_o[k]), k
+    for m in (True, False):
+        ld_r = ref.get_loss_dict(out_r, inp, m, 'color')
+        ld_o = ora.loss_dict(out_o, ts, td, m, 'color')
+        for k in ld_r:
+            assert float(ld_r[k].detach()) == float(ld_o[k].detach()), (m, k)
+    # the reference's grid-shape hazard (SURVEY Q2) at the default office0 bound
+    ref2 = ref_harness.ref_conv_onet(np.array([[-5.5, 5.9], [-6.7, 5.4], [-4.7, 5.3]]))
+    assert tuple(ref2.grid_c['grid_middle'].shape) == (1, 32, 31, 37, 35)
+    assert tuple(ref2.grid_c['grid_fine'].shape) == (1, 32, 63, 75, 71)

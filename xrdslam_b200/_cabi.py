@@ -101,7 +101,7 @@ class XrdNiceCfg(C.Structure):
                 ('n_surface', C.c_int), ('bound_min', C.c_double * 3),
                 ('bound_max', C.c_double * 3), ('w_color', C.c_float),
                 ('handle_dynamic', C.c_int), ('use_color_in_tracking', C.c_int),
-                ('t_uniform', vp), ('t_surface', vp), ('max_depth_global', C.c_float)]
+                ('t_uniform', vp), ('t_surface', vp), ('max_depth_global', vp)]
 
 
 class XrdNiceOut(C.Structure):

@@ -171,6 +171,7 @@ class ConvOnet(Model):
         self.load_bound()
         self.grid_init()
         self.grid_opti_mask = {}
+        self.dp = None  # xrdslam_b200.dp.MappingDataParallel when mapping rays are sharded
         self.register_buffer('_t_uniform', torch.linspace(0., 1., steps=cfg.rendering_n_samples),
                              persistent=False)
         self.register_buffer('_t_surface', torch.linspace(0., 1., steps=cfg.rendering_n_surface),
@@ -243,7 +244,10 @@ class ConvOnet(Model):
         c.handle_dynamic = int(cfg.tracking_handle_dynamic)
         c.use_color_in_tracking = int(cfg.tracking_use_color_in_tracking)
         c.t_uniform, c.t_surface = ptr(self._t_uniform), ptr(self._t_surface)
-        c.max_depth_global = 0.0
+        maxd = None
+        if self.dp is not None and self.dp.world > 1 and is_mapping and with_grads:
+            maxd = self.dp.all_reduce_max(td.max().reshape(1))  # batch-global (Q9), no host sync
+        c.max_depth_global = ptr(maxd)
         zc = getattr(self, '_z_capture', None)  # tests: capture the f64 sample depths
         out = XrdNiceOut(ptr(o['rgb']), ptr(o['depth']), ptr(o['uncertainty']), ptr(zc), None,
                          ptr(o['losses']))

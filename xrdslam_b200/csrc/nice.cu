@@ -115,7 +115,6 @@ struct SampleParams {
   double bmin[3], bmax[3];
   const float *t_uniform, *t_surface;  // torch.linspace(0,1,n) tables
   const float* maxd;   // device scalar
-  float maxd_override; // > 0: use instead
   double* z;           // [R][ns+nsurf]
 };
 
@@ -126,7 +125,7 @@ __global__ void __launch_bounds__(128) k_sample(SampleParams p) {
   if (r >= p.R) return;
   const int S = p.ns + p.nsurf;
   double* z = zs[warp];
-  const float maxd = p.maxd_override > 0.f ? p.maxd_override : p.maxd[0];
+  const float maxd = p.maxd[0];
   const float gt = p.target_d[r];
   // far_bb = min_d max_side (bound - o) / d  (+0.01), all in f64 (conv_onet.py:407-414)
   double far_bb = INFINITY;
@@ -926,7 +925,7 @@ extern "C" int xrd_nice_step(const XrdRays* rays, const XrdNiceGrid grids[3],
   float* rgb = reinterpret_cast<float*>(ws + L.rgb);
   const int stage = cfg->stage;
 
-  if (!(cfg->max_depth_global > 0.f)) {
+  if (!cfg->max_depth_global) {
     k_maxdepth<<<1, 1024, 0, stream>>>(rays->target_d, R, maxd);
     XRD_LAUNCH_CHECK();
   }
@@ -934,7 +933,7 @@ extern "C" int xrd_nice_step(const XrdRays* rays, const XrdNiceGrid grids[3],
   sp.R = R; sp.ns = cfg->n_samples; sp.nsurf = cfg->n_surface;
   sp.rays_o = rays->rays_o; sp.rays_d = rays->rays_d; sp.target_d = rays->target_d;
   for (int d = 0; d < 3; ++d) { sp.bmin[d] = cfg->bound_min[d]; sp.bmax[d] = cfg->bound_max[d]; }
-  sp.maxd = maxd; sp.maxd_override = cfg->max_depth_global; sp.z = z;
+  sp.maxd = cfg->max_depth_global ? cfg->max_depth_global : maxd; sp.z = z;
   sp.t_uniform = cfg->t_uniform; sp.t_surface = cfg->t_surface;
   k_sample<<<(R + 3) / 4, 128, 0, stream>>>(sp);
   XRD_LAUNCH_CHECK();

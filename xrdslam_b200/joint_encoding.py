@@ -218,6 +218,7 @@ class JointEncoding(Model):
         # set by the Algorithm around tracking (only pose params have optimizers
         # there, base_algorithm.py:168-181): the fused pass then produces d rays only
         self.freeze_map_grads = False
+        self.dp = None  # xrdslam_b200.dp.MappingDataParallel when mapping rays are sharded
 
     def get_resolution(self):
         """joint_encoding.py:199-210."""
@@ -299,6 +300,9 @@ class JointEncoding(Model):
         if seed is None:
             self._step_count += 1
             seed = (cfg.seed << 32) + self._step_count
+        # sharding applies to mapping only (tracking is per-frame sequential, single GPU)
+        dp = self.dp if (self.dp is not None and self.dp.world > 1 and with_grads
+                         and map_grads) else None
         c = XrdCoslamCfg(
             S, cfg.training_n_sample_d, cfg.training_n_range_d,
             int(cfg.training_perturb > 0),
@@ -333,6 +337,18 @@ class JointEncoding(Model):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
+            if dp is not None:
+                # sharded mapping: the loss normalisers are batch-global:
+                # sample -> all-reduce the three counters -> render with the global counts
+                counts = torch.zeros(4, dtype=torch.int32, device=dev)
+                c.phase, c.counts_out = 1, ptr(counts)
+                st = lib.xrd_coslam_step(C.byref(rays), C.byref(grid), C.byref(mlp),
+                                         C.byref(c), ptr(noise), C.byref(out), None,
+                                         ptr(ws), ws_bytes, stream)
+                check('xrd_coslam_step[sample]', st)
+                dp.all_reduce_sum(counts)
+                c.phase, c.counts_global = 2, ptr(counts)
+                c.n_rays_global = R * dp.world  # equal shards
             st = lib.xrd_coslam_step(C.byref(rays), C.byref(grid), C.byref(mlp),
                                      C.byref(c), ptr(noise), C.byref(out),
                                      C.byref(gs) if gs is not None else None,
