@@ -285,6 +285,133 @@ int xrd_nice_step(const XrdRays* rays, const XrdNiceGrid grids[3],
                   XrdNiceOut* out, XrdNiceGrads* grads, void* workspace,
                   size_t workspace_bytes, void* stream);
 
+/* ---- Vox-Fusion -------------------------------------------------------------
+ *
+ * Map structure (host side, once per mapping call -- SURVEY row f2):
+ *   xrd_octree_*   third_party/sparse_octree: Octree::init/insert
+ *                  (src/octree.cpp:35-115), get_centres_and_children (:297-346); node ids
+ *                  (= embedding rows) follow the reference's creation order.
+ * The octree handle is a host object that owns its memory (like svo.Octree). */
+typedef struct XrdOctree XrdOctree;
+XrdOctree* xrd_octree_create(int grid_dim); /* 256; NULL on failure                 */
+void xrd_octree_destroy(XrdOctree* t);
+int xrd_octree_num_nodes(const XrdOctree* t);
+/* voxels: HOST int32 [n][3] voxel coordinates (floor(p / voxel_size)); returns the node
+ * count after the insertion (negative XrdStatus on error). */
+int xrd_octree_insert(XrdOctree* t, const int32_t* voxels, int n);
+/* HOST outputs sized by xrd_octree_num_nodes: voxels f32 [N][4], children f32 [N][8],
+ * features i32 [N][8].  Returns N. */
+int xrd_octree_export(const XrdOctree* t, float* voxels, float* children, int32_t* features);
+
+/* Per-iteration path:
+ *   xrd_voxfusion_march   slam/model_components/voxel_helpers_voxfusion.py:647-687 ray_intersect
+ *                         (third_party/sparse_voxels/src/intersect_gpu.cu:191-270
+ *                         svo_intersect_point_kernel + the host-side fill/sort/trim) and
+ *                         :690-714 ray_sample (src/sample_gpu.cu:133-239
+ *                         inverse_cdf_sampling_kernel incl. its batching quirks).
+ *   xrd_voxfusion_render  slam/models/sparse_voxel.py:152-274 render_rays after sampling:
+ *                         get_features (voxel_helpers_voxfusion.py:106-123,147-153), Decoder
+ *                         (slam/model_components/decoder_voxfusion.py:122-149), sdf2weights
+ *                         (:276-304), get_loss_dict (:103-143, utils.py:154-186) + backward.
+ * The two calls are separated by ONE host read of `XrdVoxMarch.stats` (the reference syncs at
+ * the same place: `hits.sum() == 0` -> None, sparse_voxel.py:179-181): the render workspace is
+ * sized by the number of valid sample points. */
+typedef struct {
+  int n_nodes;
+  const float* centres;      /* DEVICE [N][3]  (xyz + side/2) * voxel_size               */
+  const int32_t* children;   /* DEVICE [N][9]  8 child ids (-1: none) ++ side            */
+  const int32_t* vertex_idx; /* DEVICE [N][8]  corner-leaf ids = embedding rows          */
+  const float* embeddings;   /* DEVICE [n_embeddings][16]                                */
+  int n_embeddings;
+} XrdVoxMap;
+
+typedef struct {
+  float voxel_size;   /* 0.2                                                              */
+  float step_size;    /* voxel_size * 0.05 = 0.01 m                                       */
+  int max_hits;       /* 50 (ray_intersect's max_hits_temp)                               */
+  float max_distance; /* 10                                                               */
+  int max_samples;    /* capacity per ray of the sample arrays (>= batch max + hits)      */
+  int rays_per_block; /* inverse_cdf batching: K = ceil(R' / 200) of the reference
+                         wrapper (voxel_helpers_voxfusion.py:411-424); 0 = derive       */
+  uint64_t seed;      /* Philox when noise == NULL                                        */
+} XrdVoxMarchCfg;
+
+typedef struct {
+  /* sorted, trimmed intersections (DEVICE) */
+  int32_t* hit_idx;   /* [R][max_hits]                                                    */
+  float* hit_tmin;    /* [R][max_hits]                                                    */
+  float* hit_tmax;    /* [R][max_hits]                                                    */
+  /* samples (DEVICE) */
+  int32_t* smp_idx;   /* [R][max_samples]  voxel id or -1                                 */
+  float* smp_depth;   /* [R][max_samples]                                                 */
+  float* smp_dist;    /* [R][max_samples]                                                 */
+  int32_t* smp_count; /* [R]  valid samples of the ray                                    */
+  int32_t* smp_base;  /* [R]  first slot of the ray in the compact point list            */
+  uint8_t* ray_mask;  /* [R]  ray hit at least one voxel                                  */
+  int32_t* stats;     /* DEVICE [8 + 2R]: 0 n_hit_rays, 1 n_points, 2 S_max (batch max
+                         samples), 3 P_max (batch max hits), 4 overflow (samples dropped by
+                         the cap); [8, 8+R) rank of each ray among the hit rays, [8+R, 8+2R)
+                         rank -> ray                                                       */
+} XrdVoxMarch;
+
+/* noise: DEVICE [R][max_samples] uniform(0,1) (clamped to [0.001,0.999] inside) or NULL. */
+int xrd_voxfusion_march(const XrdRays* rays, const XrdVoxMap* map, const XrdVoxMarchCfg* cfg,
+                        const float* noise, XrdVoxMarch* out, void* stream);
+
+/* Parity hooks: the raw kernels with the reference kernels' exact signatures of data.
+ * intersect: unsorted DFS-order hits (idx -1 padded), as svo_intersect returns them.
+ * sample: explicit probs / steps / noise, compact layout [R][H] -> [R][max_steps]. */
+int xrd_voxfusion_intersect_raw(const XrdRays* rays, const XrdVoxMap* map, float voxel_size,
+                                int n_max, int32_t* idx, float* tmin, float* tmax, void* stream);
+int xrd_voxfusion_sample_raw(int n_rays, int max_hits, int max_steps, int rays_per_block,
+                             const int32_t* pts_idx, const float* min_depth,
+                             const float* max_depth, const float* noise, const float* probs,
+                             const float* steps, int32_t* smp_idx, float* smp_depth,
+                             float* smp_dist, void* stream);
+
+typedef struct {            /* torch nn.Linear layouts [out][in] + bias, DEVICE            */
+  const float *w0, *b0;     /* pts_linears.0   [128][16]                                   */
+  const float *w1, *b1;     /* pts_linears.1   [128][128]                                  */
+  const float *ws, *bs;     /* sdf_out         [129][128]  (sdf, feat128)                  */
+  const float *wc0, *bc0;   /* color_out.0     [128][144]  in = feat128 ++ emb16           */
+  const float *wc1, *bc1;   /* color_out.2     [3][128]                                    */
+} XrdVoxDecoder;
+
+typedef struct {            /* same shapes, ACCUMULATED into                               */
+  float *w0, *b0, *w1, *b1, *ws, *bs, *wc0, *bc0, *wc1, *bc1;
+} XrdVoxDecoderGrads;
+
+typedef struct {
+  float voxel_size;
+  float trunc;        /* training_trunc * sc_factor (0.05)                                */
+  float max_depth;    /* loss: valid depth in (0.01, max_dpeth)                           */
+  float pad_depth;    /* MAX_DEPTH = 10 that pads z_vals (voxel_helpers_voxfusion.py:11)   */
+  float w_rgb, w_depth, w_sdf, w_fs; /* .5, 1, 5000, 10                                   */
+  int n_points;       /* host copy of stats[1]                                            */
+  int s_max;          /* host copy of stats[2]                                            */
+  int n_hit_rays;     /* host copy of stats[0]                                            */
+} XrdVoxRenderCfg;
+
+typedef struct {
+  float* rgb;     /* [R,3]  0 for rays without a hit                                      */
+  float* depth;   /* [R]                                                                   */
+  float* losses;  /* [4] rgb, depth, sdf, fs (weighted)                                    */
+} XrdVoxOut;
+
+typedef struct {
+  float* d_embeddings;          /* [n_embeddings][16], ACCUMULATED                        */
+  XrdVoxDecoderGrads* d_decoder;/* or NULL                                                */
+  float* d_rays_o;              /* [R,3] or NULL                                          */
+  float* d_rays_d;              /* [R,3] or NULL                                          */
+} XrdVoxGrads;
+
+size_t xrd_voxfusion_render_workspace_bytes(int n_rays, int n_points, int with_grads);
+
+int xrd_voxfusion_render(const XrdRays* rays, const XrdVoxMap* map, const XrdVoxMarch* march,
+                         const XrdVoxMarchCfg* mcfg, const XrdVoxDecoder* dec,
+                         const XrdVoxRenderCfg* cfg, XrdVoxOut* out, XrdVoxGrads* grads,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,6 +114,47 @@ class XrdNiceGrads(C.Structure):
                 ('d_rays_o', vp), ('d_rays_d', vp)]
 
 
+class XrdVoxMap(C.Structure):
+    _fields_ = [('n_nodes', C.c_int), ('centres', vp), ('children', vp), ('vertex_idx', vp),
+                ('embeddings', vp), ('n_embeddings', C.c_int)]
+
+
+class XrdVoxMarchCfg(C.Structure):
+    _fields_ = [('voxel_size', C.c_float), ('step_size', C.c_float), ('max_hits', C.c_int),
+                ('max_distance', C.c_float), ('max_samples', C.c_int),
+                ('rays_per_block', C.c_int), ('seed', C.c_uint64)]
+
+
+class XrdVoxMarch(C.Structure):
+    _fields_ = [('hit_idx', vp), ('hit_tmin', vp), ('hit_tmax', vp), ('smp_idx', vp),
+                ('smp_depth', vp), ('smp_dist', vp), ('smp_count', vp), ('smp_base', vp),
+                ('ray_mask', vp), ('stats', vp)]
+
+
+class XrdVoxDecoder(C.Structure):
+    _fields_ = [(n, vp) for n in ('w0', 'b0', 'w1', 'b1', 'ws', 'bs', 'wc0', 'bc0', 'wc1', 'bc1')]
+
+
+class XrdVoxDecoderGrads(C.Structure):
+    _fields_ = [(n, vp) for n in ('w0', 'b0', 'w1', 'b1', 'ws', 'bs', 'wc0', 'bc0', 'wc1', 'bc1')]
+
+
+class XrdVoxRenderCfg(C.Structure):
+    _fields_ = [('voxel_size', C.c_float), ('trunc', C.c_float), ('max_depth', C.c_float),
+                ('pad_depth', C.c_float), ('w_rgb', C.c_float), ('w_depth', C.c_float),
+                ('w_sdf', C.c_float), ('w_fs', C.c_float), ('n_points', C.c_int),
+                ('s_max', C.c_int), ('n_hit_rays', C.c_int)]
+
+
+class XrdVoxOut(C.Structure):
+    _fields_ = [('rgb', vp), ('depth', vp), ('losses', vp)]
+
+
+class XrdVoxGrads(C.Structure):
+    _fields_ = [('d_embeddings', vp), ('d_decoder', C.POINTER(XrdVoxDecoderGrads)),
+                ('d_rays_o', vp), ('d_rays_d', vp)]
+
+
 _lib = None
 
 # name -> (restype, argtypes); every symbol include/xrdslam_b200.h declares
@@ -141,6 +182,22 @@ SYMBOLS = {
     ]),
     'xrd_hashgrid_encode':
     (C.c_int, [C.POINTER(XrdHashGrid), vp, C.c_int, vp, vp, vp]),
+    'xrd_octree_create': (vp, [C.c_int]),
+    'xrd_octree_destroy': (None, [vp]),
+    'xrd_octree_num_nodes': (C.c_int, [vp]),
+    'xrd_octree_insert': (C.c_int, [vp, vp, C.c_int]),
+    'xrd_octree_export': (C.c_int, [vp, vp, vp, vp]),
+    'xrd_voxfusion_march': (C.c_int, [C.POINTER(XrdRays), C.POINTER(XrdVoxMap),
+                                      C.POINTER(XrdVoxMarchCfg), vp, C.POINTER(XrdVoxMarch), vp]),
+    'xrd_voxfusion_intersect_raw': (C.c_int, [C.POINTER(XrdRays), C.POINTER(XrdVoxMap),
+                                              C.c_float, C.c_int, vp, vp, vp, vp]),
+    'xrd_voxfusion_sample_raw': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp,
+                                           vp, vp, vp, vp, vp, vp]),
+    'xrd_voxfusion_render_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    'xrd_voxfusion_render': (C.c_int, [
+        C.POINTER(XrdRays), C.POINTER(XrdVoxMap), C.POINTER(XrdVoxMarch),
+        C.POINTER(XrdVoxMarchCfg), C.POINTER(XrdVoxDecoder), C.POINTER(XrdVoxRenderCfg),
+        C.POINTER(XrdVoxOut), C.POINTER(XrdVoxGrads), vp, C.c_size_t, vp]),
     'xrd_nice_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     'xrd_nice_step': (C.c_int, [
         C.POINTER(XrdRays), C.POINTER(XrdNiceGrid), C.POINTER(XrdNiceDecoder),
