@@ -412,6 +412,83 @@ int xrd_voxfusion_render(const XrdRays* rays, const XrdVoxMap* map, const XrdVox
                          const XrdVoxRenderCfg* cfg, XrdVoxOut* out, XrdVoxGrads* grads,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Point-SLAM -------------------------------------------------------------
+ *
+ *   xrd_pointslam_knn_query  slam/model_components/neural_point_cloud.py:223-282
+ *                            find_neighbors_faiss.  The reference's index is faiss-gpu
+ *                            IndexIVFFlat(nlist 400, nprobe 4) -- approximate, un-vendored;
+ *                            this is an EXACT radius-limited 8-NN (ties by lower id) over a
+ *                            uniform hash grid, with faiss's sentinels (id -1, D = FLT_MAX).
+ *   xrd_pointslam_step       slam/models/conv_onet_pointslam.py:311-461 render_batch_ray
+ *                            (5 surface samples), :248-309 eval_points, POINT.forward
+ *                            slam/model_components/decoder_pointslam.py:595-655 stage
+ *                            'geometry' (MLP_geometry :162-273: inverse-distance kNN feature
+ *                            interpolation + 5x32 Fourier MLP), raw2outputs_nerf_color2
+ *                            slam/model_components/utils.py:247-295, get_loss_dict
+ *                            conv_onet_pointslam.py:144-195 and autograd's backward.
+ */
+typedef struct {
+  const float* pos;           /* DEVICE [N][3] neural point positions                      */
+  int n_points;
+  float cell;                 /* grid cell edge (>= the largest query radius / 2)          */
+  int table_size;             /* power of two                                              */
+  const int32_t* cell_start;  /* DEVICE [table_size] first slot of the bucket              */
+  const int32_t* cell_end;    /* DEVICE [table_size] one past the last slot                */
+  const int32_t* sorted_ids;  /* DEVICE [N] point ids ordered by bucket                    */
+} XrdPointIndex;
+
+/* bucket of cell (ix,iy,iz): ((ix*73856093) ^ (iy*19349663) ^ (iz*83492791)) & (table-1),
+ * uint32 arithmetic, ix = floor(x / cell). */
+int xrd_pointslam_knn_query(const XrdPointIndex* index, const float* queries, const float* radius,
+                            int radius_stride, int n_queries, float* D, int32_t* I,
+                            int32_t* neighbor_num, void* stream);
+
+typedef struct {
+  int stage;               /* 0 = 'geometry' (stage 'color' -> XRD_E_SHAPE in this round)   */
+  int is_mapping;
+  int n_surface;           /* 5                                                             */
+  float near_end_surface;  /* 0.98                                                          */
+  float far_end_surface;   /* 1.02                                                          */
+  float near_end;          /* 0.3                                                           */
+  float sigmoid_coef;      /* 0.1                                                           */
+  int min_nn_num;          /* 2                                                             */
+  float w_color;
+  int handle_dynamic;
+  int use_color_in_tracking;
+  const float* t_surface;  /* DEVICE [n_surface] torch.linspace(0,1,n)                      */
+  const float* far;        /* DEVICE scalar min(5*mean(d), max(1.2*d)) (batch-global, Q9)   */
+  const float* radius_query; /* DEVICE [R] per-ray dynamic query radius                     */
+  const float* rand_feat;  /* DEVICE [32] feature of samples with < min_nn neighbours (Q6)
+                              or NULL = zeros                                               */
+} XrdPointCfg;
+
+typedef struct {
+  const float* geo_feats;      /* DEVICE [N][32]                                            */
+  const uint8_t* frustum_mask; /* DEVICE [N] or NULL                                        */
+} XrdPointFeats;
+
+typedef struct {
+  float* rgb;              /* [R,3] (zeros in stage geometry)                               */
+  float* depth;            /* [R]                                                           */
+  float* uncertainty;      /* [R]                                                           */
+  uint8_t* valid_ray_mask; /* [R]                                                           */
+  float* z_vals;           /* [R,n_surface] optional                                        */
+  float* losses;           /* [2] geo_loss, rgb_loss                                        */
+} XrdPointOut;
+
+typedef struct {
+  float* d_geo_feats;      /* [N][32] ACCUMULATED                                           */
+  float* d_rays_o;         /* [R,3] or NULL                                                 */
+  float* d_rays_d;
+} XrdPointGrads;
+
+size_t xrd_pointslam_workspace_bytes(int n_rays, int n_surface, int with_grads);
+
+int xrd_pointslam_step(const XrdRays* rays, const XrdPointIndex* index,
+                       const XrdPointFeats* feats, const XrdNiceDecoder* geo_decoder,
+                       const XrdPointCfg* cfg, XrdPointOut* out, XrdPointGrads* grads,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

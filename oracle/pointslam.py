@@ -1,0 +1,138 @@
+"""Torch-CPU restatement of the Point-SLAM render-and-optimise step (stage 'geometry').
+
+ORACLE / TEST INFRASTRUCTURE -- never imported by xrdslam_b200/.
+
+Follows (reference @ f0366f20):
+  slam/model_components/neural_point_cloud.py:223-282  find_neighbors_faiss -- faiss-gpu
+      IndexIVFFlat(nlist 400, nprobe 4) is un-vendored and approximate: parity is DEFINED
+      against the exact radius-independent 8-NN below (ties by lower id, faiss sentinels
+      id -1 / D FLT_MAX) -> "parity unpinned vs real faiss" 
+  slam/model_components/decoder_pointslam.py:162-273    MLP_geometry
+  slam/models/conv_onet_pointslam.py:311-461, :144-195  render_batch_ray, get_loss_dict
+  slam/model_components/utils.py:247-295                raw2outputs_nerf_color2
+Pinned against the reference's own ConvOnet2 / POINT classes (run on CPU with the exact-kNN
+faiss stand-in of oracle/ref_harness.py) by tests/test_oracle_cpu.py and tests/golden.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+FLT_MAX = float(np.finfo(np.float32).max)
+
+
+def exact_knn(cloud, q, k=8):
+    """Exact k-NN (squared L2, float32, ((dx^2 + dy^2) + dz^2)), ties by lower id."""
+    d = (cloud[None, :, :] - q[:, None, :])
+    D = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+    N = cloud.shape[0]
+    if N < k:
+        pad = torch.full((q.shape[0], k - N), FLT_MAX)
+        D = torch.cat([D, pad], 1)
+    vals, idx = torch.sort(D, dim=1, stable=True)
+    vals, idx = vals[:, :k], idx[:, :k]
+    idx = torch.where(idx < N, idx, torch.full_like(idx, -1))
+    return vals, idx
+
+
+class GeoDecoder(nn.Module):
+    """MLP_geometry (decoder_pointslam.py:77-273): sin(2 pi p B), 5 x 32 + fc_c, skip at 2."""
+    def __init__(self, gen=None):
+        super().__init__()
+        self.B = nn.Parameter(torch.randn(3, 93, generator=gen) * 25)
+        self.fc_c = nn.ModuleList([nn.Linear(32, 32) for _ in range(5)])
+        self.pts = nn.ModuleList([nn.Linear(d, 32) for d in (93, 32, 32, 125, 32)])
+        self.out = nn.Linear(32, 1)
+
+    def forward(self, p, c):
+        e = torch.sin((2 * math.pi * p.float()) @ self.B)
+        h = e
+        for i in range(5):
+            h = F.relu(self.pts[i](h)) + self.fc_c[i](c)
+            if i == 2:
+                h = torch.cat([e, h], -1)
+        return self.out(h).squeeze(-1)
+
+
+class PointOracle(nn.Module):
+    def __init__(self, n_surface=5, seed=0):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.geo = GeoDecoder(g)
+        self.n_surface = n_surface
+        self.near_s, self.far_s, self.near_end, self.coef, self.min_nn = 0.98, 1.02, 0.3, 0.1, 2
+        self.cloud = None
+        self.geo_feats = None
+        self.frustum_mask = None
+
+    def set_cloud(self, pos, geo_feats, mask=None):
+        self.cloud = pos.clone()
+        self.geo_feats = nn.Parameter(geo_feats.clone())
+        self.frustum_mask = mask if mask is not None else torch.ones(pos.shape[0], 1, dtype=torch.bool)
+
+    def feature_at(self, p, radius, rand_feat):
+        D, I = exact_knn(self.cloud, p.detach(), 8)
+        bound = radius.reshape(-1, 1)**2
+        nn_num = (D < bound).sum(-1)
+        Dg = torch.sum(torch.square(self.cloud[I] - p.reshape(-1, 1, 3)), dim=-1)  # is_tracker
+        has = nn_num > self.min_nn - 1
+        w = 1.0 / (Dg + 1e-10)
+        w = torch.where(Dg > bound, torch.zeros_like(w), w)
+        w = torch.where(I < 0, torch.zeros_like(w), w)
+        w = F.normalize(w, p=1, dim=1).unsqueeze(-1)
+        feats = self.geo_feats * self.frustum_mask
+        c = (w * feats[I]).sum(1)
+        c = torch.where(has[:, None], c, rand_feat[None, :].expand_as(c))
+        return c, has
+
+    def sample_z(self, target_d):
+        S = self.n_surface
+        gt = target_d.reshape(-1, 1)
+        far = torch.minimum(5 * gt.mean(), torch.max(gt * 1.2))
+        nz = (gt > 0).squeeze(-1)
+        t = torch.linspace(0.0, 1.0, steps=S)
+        z = torch.zeros(gt.shape[0], S)
+        gs = gt[nz].repeat(1, S)
+        z[nz] = self.near_s * gs * (1. - t) + self.far_s * gs * t
+        if nz.sum() < gt.shape[0]:
+            z[~nz] = torch.linspace(self.near_end, float(far), steps=S).repeat(int((~nz).sum()), 1)
+        return z, nz
+
+    def render(self, rays_o, rays_d, target_d, radius, rand_feat):
+        S = self.n_surface
+        z, nz = self.sample_z(target_d)
+        pts = (rays_o[..., None, :] + rays_d[..., None, :] * z[..., :, None]).reshape(-1, 3)
+        r = radius.reshape(-1, 1).repeat_interleave(S, dim=0)
+        c, has = self.feature_at(pts, r, rand_feat)
+        valid_ray = ~(torch.sum(has.view(-1, S), 1) < int(S / 2 + 1))
+        occ = self.geo(pts, c)
+        occ = torch.where(has, occ, torch.full_like(occ, -100.0))
+        occ = occ.reshape(-1, S)
+        alpha = torch.sigmoid(self.coef * occ)
+        w = alpha * torch.cumprod(torch.cat([torch.ones(alpha.shape[0], 1),
+                                             1. - alpha + 1e-10], -1), -1)[:, :-1]
+        wsum = w.sum(-1, keepdim=True) + 1e-10
+        depth = (w * z).sum(-1) / wsum.squeeze(-1)
+        tmp = z - depth.unsqueeze(-1)
+        var = (w * tmp * tmp).sum(1)
+        depth = torch.where(nz, depth, torch.zeros_like(depth))
+        return dict(depth=depth, uncertainty=var, valid_ray_mask=valid_ray, z_vals=z,
+                    rgb=torch.zeros(rays_o.shape[0], 3))
+
+    def loss(self, out, target_d, is_mapping, handle_dynamic=True):
+        td = target_d.squeeze()
+        depth, unc = out['depth'], out['uncertainty']
+        if not is_mapping:
+            unc = unc.detach()
+            nan_mask = (~torch.isnan(depth)) & (~torch.isnan(unc))
+            tmp = torch.abs(td - depth) / torch.sqrt(unc + 1e-10) if handle_dynamic \
+                else torch.abs(td - depth)
+            mask = (tmp < 10 * tmp.median()) & (td > 0) & nan_mask
+            return torch.clamp(torch.abs(td - depth) / torch.sqrt(unc + 1e-10),
+                               min=0.0, max=1e3)[mask].sum()
+        m = (td > 0) & out['valid_ray_mask'] & (~torch.isnan(depth))
+        return torch.abs(td[m] - depth[m]).sum()

@@ -124,3 +124,64 @@ def copy_nice_ref_to_oracle(ref, ora):
             o.out.bias.copy_(r.output_linear.bias)
         for k in ('grid_middle', 'grid_fine', 'grid_color'):
             ora.grids[k].copy_(ref.grid_c[k])
+
+
+# ---- Point-SLAM: the reference's ConvOnet2 with an exact-kNN stand-in for faiss -----------
+class _ExactIndex:
+    """Minimal faiss.Index stand-in: exact L2 search (the real IndexIVFFlat(nlist 400,
+    nprobe 4) is approximate and un-vendored: parity is defined against exact kNN)."""
+    def __init__(self):
+        import numpy as np
+        self.xb = np.zeros((0, 3), np.float32)
+        self.is_trained = False
+        self.nprobe = 1
+
+    @property
+    def ntotal(self):
+        return self.xb.shape[0]
+
+    def train(self, x):
+        self.is_trained = True
+
+    def add(self, x):
+        import numpy as np
+        self.xb = np.concatenate([self.xb, np.asarray(x, np.float32)], 0)
+
+    def search(self, q, k):
+        import numpy as np
+        import torch
+        from oracle.pointslam import exact_knn
+        D, I = exact_knn(torch.from_numpy(self.xb), torch.from_numpy(np.asarray(q, np.float32)), k)
+        return D.numpy(), I.numpy().astype(np.int64)
+
+
+def install_faiss_stub():
+    import types
+    f = types.ModuleType('faiss')
+    f.METRIC_L2 = 1
+    f.StandardGpuResources = lambda: None
+    f.IndexFlatL2 = lambda d: None
+    f.IndexIVFFlat = lambda quant, d, nlist, metric: _ExactIndex()
+    f.index_cpu_to_gpu = lambda res, dev, index: index
+    sys.modules['faiss'] = f
+
+
+def ref_conv_onet2(**cfg_overrides):
+    """The reference's Point-SLAM model (ConvOnet2) on CPU: pretrained-decoder loading
+    bypassed (Git-LFS stubs), faiss replaced by the exact stand-in above."""
+    install_faiss_stub()
+    install()
+    import importlib
+    import slam.model_components.neural_point_cloud as npc_mod
+    importlib.reload(npc_mod)  # bind the stub
+    from slam.common.camera import Camera
+    import slam.models.conv_onet_pointslam as m
+    importlib.reload(m)
+    orig = m.ConvOnet2.load_pretrain
+    m.ConvOnet2.load_pretrain = lambda self: None
+    try:
+        model = m.ConvOnet2(m.ConvOnet2Config(**cfg_overrides),
+                            camera=Camera(320.0, 320.0, 319.5, 239.5, 640, 480))
+    finally:
+        m.ConvOnet2.load_pretrain = orig
+    return model

@@ -132,7 +132,65 @@ def nice(R=120, seed=3):
     print('wrote nice_color_step.npz')
 
 
+def pointslam(R0=300, R=80, seed=11):
+    """Reference ConvOnet2 (slam/models/conv_onet_pointslam.py) + NeuralPointCloud, stage
+    'geometry', on CPU with the exact-kNN stand-in for faiss (oracle/ref_harness.py):
+    point-adding, mapping and tracking losses with gradients."""
+    torch.manual_seed(seed)
+    ref = ref_harness.ref_conv_onet2()
+    g = torch.Generator().manual_seed(seed)
+    ro0 = torch.zeros(R0, 3)
+    rd0 = torch.nn.functional.normalize(
+        torch.randn(R0, 3, generator=g) * torch.tensor([0.3, 0.3, 0.05]) +
+        torch.tensor([0, 0, -1.0]), dim=-1)
+    d0 = torch.rand(R0, generator=g) * 0.5 + 1.5
+    e = torch.zeros(0)
+    ref.model_update(dict(batch_rays_o=ro0, batch_rays_d=rd0, batch_gt_depth=d0,
+                          batch_gt_color=torch.rand(R0, 3, generator=g),
+                          batch_dynamic_r=torch.full((R0,), 0.04),
+                          batch_rays_o_grad=ro0[:0], batch_rays_d_grad=rd0[:0],
+                          batch_gt_depth_grad=e, batch_gt_color_grad=torch.rand(0, 3),
+                          batch_dynamic_r_grad=e))
+    npc = ref.neural_point_cloud
+    gd = ref.decoder.geo_decoder
+    with torch.no_grad():
+        gd.embedder._B.mul_(0.05)
+        for lin in list(gd.fc_c) + list(gd.pts_linears) + [gd.output_linear]:
+            lin.bias.copy_(torch.randn(lin.bias.shape, generator=g) * 0.1)
+        npc.geo_feats.mul_(5.0)
+    rays_o = (torch.randn(R, 3, generator=g) * 0.01).requires_grad_(True)
+    rays_d = rd0[:R].clone().requires_grad_(True)
+    td = (d0[:R] + torch.randn(R, generator=g) * 0.01).reshape(-1, 1)
+    td[5::9] = 0
+    radius = torch.rand(R, generator=g) * 0.08 + 0.04
+    blob = dict(add_rays_d=rd0.numpy(), add_depth=d0.numpy(),
+                cloud_pos=np.asarray(npc._cloud_pos, np.float32),
+                geo_feats=npc.geo_feats.detach().numpy().copy(),
+                rays_o=rays_o.detach().numpy(), rays_d=rays_d.detach().numpy(),
+                target_d=td.numpy(), radius=radius.numpy())
+    for k, v in gd.state_dict().items():
+        blob['dec.' + k] = v.numpy().copy()
+    for tag, is_mapping in (('map', True), ('trk', False)):
+        for t in [rays_o, rays_d, npc.geo_feats] + list(gd.parameters()):
+            t.grad = None
+        inp = dict(rays_o=rays_o, rays_d=rays_d, target_d=td, target_s=torch.zeros(R, 3),
+                   stage='geometry', batch_dynamic_r=radius)
+        out = ref(inp)
+        ld = ref.get_loss_dict(out, inp, is_mapping)
+        ld['geo_loss'].backward()
+        blob[tag + '.depth'] = out['depth'].detach().numpy()
+        blob[tag + '.uncertainty'] = out['uncertainty'].detach().numpy()
+        blob[tag + '.valid'] = out['valid_ray_mask'].numpy()
+        blob[tag + '.loss'] = np.float32(ld['geo_loss'].item())
+        blob[tag + '.d_geo_feats'] = npc.geo_feats.grad.numpy().copy()
+        blob[tag + '.d_rays_o'] = rays_o.grad.numpy().copy()
+        blob[tag + '.d_rays_d'] = rays_d.grad.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, 'pointslam_geo_step.npz'), **blob)
+    print('wrote pointslam_geo_step.npz', npc.pts_num(), 'points')
+
+
 if __name__ == '__main__':
     assert ref_harness.available(), 'needs /root/reference'
-    coslam()
-    nice()
+    which = sys.argv[1:] or ['coslam', 'nice', 'pointslam']
+    for w in which:
+        globals()[w]()

@@ -45,13 +45,19 @@ def coslam_pair(device, table_amp=0.3, seed=1, **cfg):
     return ora, model
 
 
+def _t(x):
+    return torch.from_numpy(np.asarray(x)) if not torch.is_tensor(x) else x
+
+
 def rel_err(a, b):
+    a, b = _t(a), _t(b)
     a = a.detach().double().cpu().reshape(-1)
     b = b.detach().double().cpu().reshape(-1)
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
 def max_abs(a, b):
+    a, b = _t(a), _t(b)
     return float((a.detach().double().cpu() - b.detach().double().cpu()).abs().max())
 
 
@@ -132,4 +138,44 @@ def nice_from_golden(g, kind, device=None):
                 obj.set_grid(k, g[k])
     if device is not None:
         obj.to(device)
+    return obj
+
+
+def load_golden_pointslam():
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden',
+                             'pointslam_geo_step.npz'))
+    return {k: g[k] for k in g.files}
+
+
+def pointslam_from_golden(g, kind, device=None):
+    """Oracle (kind='oracle') or B200 ConvOnet2 with the golden decoder + point cloud."""
+    t = lambda k: torch.from_numpy(g[k])
+    pre = 'dec.'
+    if kind == 'oracle':
+        from oracle.pointslam import PointOracle
+        obj = PointOracle()
+        d = obj.geo
+        with torch.no_grad():
+            d.B.copy_(t(pre + 'embedder._B'))
+            for i in range(5):
+                d.fc_c[i].weight.copy_(t(pre + f'fc_c.{i}.weight'))
+                d.fc_c[i].bias.copy_(t(pre + f'fc_c.{i}.bias'))
+                d.pts[i].weight.copy_(t(pre + f'pts_linears.{i}.weight'))
+                d.pts[i].bias.copy_(t(pre + f'pts_linears.{i}.bias'))
+            d.out.weight.copy_(t(pre + 'output_linear.weight'))
+            d.out.bias.copy_(t(pre + 'output_linear.bias'))
+        obj.set_cloud(t('cloud_pos'), t('geo_feats'))
+        return obj
+    from xrdslam_b200.camera import Camera
+    from xrdslam_b200.conv_onet_pointslam import ConvOnet2Config
+    obj = ConvOnet2Config().setup(camera=Camera(320., 320., 319.5, 239.5, 640, 480))
+    # same keys as the reference decoder (whose geometry MLP also carries unused colour-only
+    # members embedder_rel_pos / mlp_col_neighbor: dropped)
+    own = obj.decoder.geo_decoder.state_dict().keys()
+    sd = {k[len(pre):]: t(k) for k in g if k.startswith(pre) and k[len(pre):] in own}
+    obj.decoder.geo_decoder.load_state_dict(sd)
+    obj.to(device)
+    npc = obj.model_update(device)
+    npc.set_cloud(t('cloud_pos'), t('geo_feats'), torch.zeros(g['cloud_pos'].shape[0], 32))
     return obj

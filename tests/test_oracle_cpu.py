@@ -245,3 +245,34 @@ def test_nice_oracle_matches_reference_class_live():
     ref2 = ref_harness.ref_conv_onet(np.array([[-5.5, 5.9], [-6.7, 5.4], [-4.7, 5.3]]))
     assert tuple(ref2.grid_c['grid_middle'].shape) == (1, 32, 31, 37, 35)
     assert tuple(ref2.grid_c['grid_fine'].shape) == (1, 32, 63, 75, 71)
+
+
+@pytest.mark.parametrize('tag,is_mapping', [('map', True), ('trk', False)])
+def test_pointslam_oracle_matches_golden_reference_vectors(tag, is_mapping):
+    """oracle/pointslam.py vs the reference's ConvOnet2 + NeuralPointCloud outputs and
+    gradients (tests/golden/make_golden.py:pointslam; faiss -> exact kNN)."""
+    from helpers import load_golden_pointslam, max_abs, pointslam_from_golden, rel_err
+    g = load_golden_pointslam()
+    ora = pointslam_from_golden(g, 'oracle')
+    ro = torch.from_numpy(g['rays_o']).requires_grad_(True)
+    rd = torch.from_numpy(g['rays_d']).requires_grad_(True)
+    td = torch.from_numpy(g['target_d'])
+    out = ora.render(ro, rd, td, torch.from_numpy(g['radius']), torch.zeros(32))
+    loss = ora.loss(out, td, is_mapping)
+    loss.backward()
+    assert torch.equal(out['valid_ray_mask'], torch.from_numpy(g[tag + '.valid']))
+    assert max_abs(out['depth'], g[tag + '.depth']) < 1e-6
+    assert max_abs(out['uncertainty'], g[tag + '.uncertainty']) < 1e-7
+    assert abs(float(loss.detach()) - float(g[tag + '.loss'])) < 1e-5 * max(1, abs(float(loss.detach())))
+    assert rel_err(ora.geo_feats.grad, g[tag + '.d_geo_feats']) < 1e-5
+    # ray grads go through 1 / (D + 1e-10) weights: fp32 op-order noise ~1e-5 relative
+    assert rel_err(ro.grad, g[tag + '.d_rays_o']) < 1e-4
+    assert rel_err(rd.grad, g[tag + '.d_rays_d']) < 1e-4
+
+
+def test_exact_knn_sentinels_and_ties():
+    from oracle.pointslam import FLT_MAX, exact_knn
+    cloud = torch.tensor([[0., 0, 0], [1, 0, 0], [-1, 0, 0]])
+    D, I = exact_knn(cloud, torch.zeros(1, 3), 8)
+    assert I[0].tolist() == [0, 1, 2, -1, -1, -1, -1, -1]  # tie 1 vs 2 -> lower id first
+    assert D[0, 3:].eq(FLT_MAX).all() and D[0, :3].tolist() == [0.0, 1.0, 1.0]

@@ -155,6 +155,34 @@ class XrdVoxGrads(C.Structure):
                 ('d_rays_o', vp), ('d_rays_d', vp)]
 
 
+class XrdPointIndex(C.Structure):
+    _fields_ = [('pos', vp), ('n_points', C.c_int), ('cell', C.c_float),
+                ('table_size', C.c_int), ('cell_start', vp), ('cell_end', vp),
+                ('sorted_ids', vp)]
+
+
+class XrdPointCfg(C.Structure):
+    _fields_ = [('stage', C.c_int), ('is_mapping', C.c_int), ('n_surface', C.c_int),
+                ('near_end_surface', C.c_float), ('far_end_surface', C.c_float),
+                ('near_end', C.c_float), ('sigmoid_coef', C.c_float), ('min_nn_num', C.c_int),
+                ('w_color', C.c_float), ('handle_dynamic', C.c_int),
+                ('use_color_in_tracking', C.c_int), ('t_surface', vp), ('far', vp),
+                ('radius_query', vp), ('rand_feat', vp)]
+
+
+class XrdPointFeats(C.Structure):
+    _fields_ = [('geo_feats', vp), ('frustum_mask', vp)]
+
+
+class XrdPointOut(C.Structure):
+    _fields_ = [('rgb', vp), ('depth', vp), ('uncertainty', vp), ('valid_ray_mask', vp),
+                ('z_vals', vp), ('losses', vp)]
+
+
+class XrdPointGrads(C.Structure):
+    _fields_ = [('d_geo_feats', vp), ('d_rays_o', vp), ('d_rays_d', vp)]
+
+
 _lib = None
 
 # name -> (restype, argtypes); every symbol include/xrdslam_b200.h declares
@@ -198,6 +226,13 @@ SYMBOLS = {
         C.POINTER(XrdRays), C.POINTER(XrdVoxMap), C.POINTER(XrdVoxMarch),
         C.POINTER(XrdVoxMarchCfg), C.POINTER(XrdVoxDecoder), C.POINTER(XrdVoxRenderCfg),
         C.POINTER(XrdVoxOut), C.POINTER(XrdVoxGrads), vp, C.c_size_t, vp]),
+    'xrd_pointslam_knn_query': (C.c_int, [C.POINTER(XrdPointIndex), vp, vp, C.c_int, C.c_int,
+                                          vp, vp, vp, vp]),
+    'xrd_pointslam_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    'xrd_pointslam_step': (C.c_int, [
+        C.POINTER(XrdRays), C.POINTER(XrdPointIndex), C.POINTER(XrdPointFeats),
+        C.POINTER(XrdNiceDecoder), C.POINTER(XrdPointCfg), C.POINTER(XrdPointOut),
+        C.POINTER(XrdPointGrads), vp, C.c_size_t, vp]),
     'xrd_nice_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     'xrd_nice_step': (C.c_int, [
         C.POINTER(XrdRays), C.POINTER(XrdNiceGrid), C.POINTER(XrdNiceDecoder),

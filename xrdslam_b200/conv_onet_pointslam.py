@@ -1,0 +1,215 @@
+"""Point-SLAM model behind the reference's ``Model`` plugin surface, B200-native.
+
+Host-side mirror of slam/models/conv_onet_pointslam.py (class ConvOnet2, same config fields,
+``forward / get_loss_dict / get_param_groups`` signatures, groups ``decoder``, ``geometry``,
+``color``).  Stage 'geometry' (kNN feature interpolation + 5x32 Fourier MLP + normalised
+occupancy compositing + losses + backward) runs in csrc/pointslam.cu through the C-ABI.
+Stage 'color' (per-neighbour MLP + width-128 softplus decoder) is not built in this round:
+it raises NotImplementedError (no PyTorch fallback exists on the product path)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import Dict, List, Optional, Type, Union
+
+import torch
+from torch import nn
+from torch.nn import Parameter
+
+from . import _cabi
+from ._cabi import (XrdNiceDecoder, XrdPointCfg, XrdPointFeats, XrdPointGrads, XrdPointOut,
+                    XrdRays, check, ptr)
+from .base_model import Model, ModelConfig
+from .conv_onet import MLP as _GeoMLP
+from .conv_onet import _dec_struct
+from .neural_point_cloud import NeuralPointCloud
+
+
+@dataclass
+class ConvOnet2Config(ModelConfig):
+    """slam/models/conv_onet_pointslam.py:18-72 (field names and defaults kept)."""
+    _target: Type = field(default_factory=lambda: ConvOnet2)
+    use_dynamic_radius: bool = True
+    points_batch_size: int = 50000
+    cuda_id: int = 0
+    pretrained_decoders_middle_fine: Optional[Path] = None
+    model_c_dim: int = 32
+    model_pos_embedding_method: str = 'fourier'
+    model_use_view_direction: bool = False
+    model_encode_rel_pos_in_col: bool = True
+    model_encode_exposure: bool = False
+    model_encode_viewd: bool = True
+    model_exposure_dim: int = 8
+    pointcloud_nn_weighting: str = 'distance'
+    pointcloud_nn_num: int = 8
+    pointcloud_min_nn_num: int = 2
+    pointcloud_radius_add: float = 0.04
+    pointcloud_radius_min: float = 0.02
+    pointcloud_radius_query: float = 0.08
+    pointcloud_fix_interval_when_add_along_ray: bool = False
+    pointcloud_n_add: int = 3
+    rendering_n_surface: int = 5
+    rendering_sample_near_pcl: bool = False
+    rendering_near_end_surface: float = 0.98
+    rendering_near_end: float = 0.3
+    rendering_far_end_surface: float = 1.02
+    rendering_sigmoid_coef_mapper: float = 0.1
+    tracking_w_color_loss: float = 0.5
+    mapping_w_color_loss: float = 0.1
+    tracking_handle_dynamic: bool = True
+    tracking_use_color_in_tracking: bool = True
+    mapping_fix_color_decoder: bool = False
+    mapping_fix_geo_decoder: bool = True
+    mapping_pixels_based_on_color_grad: int = 1000
+
+
+class POINT(nn.Module):
+    """Parameter container of decoder_pointslam.py:545-594 (geometry decoder: the 5x32 Fourier
+    MLP with fc_c; same tensor layout as the NICE decoders)."""
+    def __init__(self, c_dim=32):
+        super().__init__()
+        self.geo_decoder = _GeoMLP('geometry', c_dim, False)
+
+
+class _PointStep(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, stage, is_mapping, target_s, target_d, radius, rand_feat, rays_o,
+                rays_d, geo_feats):
+        need_rays = ctx.needs_input_grad[7] or ctx.needs_input_grad[8]
+        need_feats = ctx.needs_input_grad[9]
+        outs, grads = model._launch(stage, is_mapping, rays_o, rays_d, target_s, target_d, radius,
+                                    rand_feat, need_rays or need_feats, need_rays, need_feats)
+        ctx.grads = grads
+        ret = (outs['losses'], outs['rgb'], outs['depth'], outs['uncertainty'],
+               outs['valid_ray_mask'])
+        ctx.mark_non_differentiable(*ret[1:])
+        return ret
+
+    @staticmethod
+    def backward(ctx, g_losses, *_):
+        g = ctx.grads
+        return (None, None, None, None, None, None, None, g['d_rays_o'], g['d_rays_d'],
+                g['d_geo_feats'])
+
+
+class ConvOnet2(Model):
+    config: ConvOnet2Config
+
+    def __init__(self, config: ConvOnet2Config, camera, **kwargs) -> None:
+        super().__init__(config=config, camera=camera, bounding_box=None, **kwargs)
+
+    def populate_modules(self):
+        super().populate_modules()
+        cfg = self.config
+        if not cfg.use_dynamic_radius or cfg.pointcloud_nn_weighting != 'distance' or \
+                cfg.rendering_sample_near_pcl or cfg.model_encode_exposure:
+            raise NotImplementedError('B200 path covers the reference point-slam config')
+        self.decoder = POINT(cfg.model_c_dim)
+        self.neural_point_cloud = None
+        self.register_buffer('_t_surface', torch.linspace(0.0, 1.0, steps=cfg.rendering_n_surface),
+                             persistent=False)
+
+    def model_update(self, device=None):
+        """conv_onet_pointslam.py:98-128: create the point cloud lazily."""
+        if self.neural_point_cloud is None:
+            cfg = self.config
+            self.neural_point_cloud = NeuralPointCloud(
+                c_dim=cfg.model_c_dim, nn_num=cfg.pointcloud_nn_num,
+                radius_add=cfg.pointcloud_radius_add, radius_min=cfg.pointcloud_radius_min,
+                radius_query=cfg.pointcloud_radius_query, n_add=cfg.pointcloud_n_add,
+                near_end_surface=cfg.rendering_near_end_surface,
+                far_end_surface=cfg.rendering_far_end_surface,
+                device=device or self._t_surface.device)
+        return self.neural_point_cloud
+
+    def _launch(self, stage, is_mapping, rays_o, rays_d, target_s, target_d, radius, rand_feat,
+                with_grads, need_rays=False, need_feats=False):
+        if stage != 'geometry':
+            raise NotImplementedError("Point-SLAM stage 'color' is not built yet")
+        cfg = self.config
+        npc = self.neural_point_cloud
+        dev = npc.device
+        if dev.type != 'cuda':
+            raise RuntimeError('xrdslam_b200 has no CPU path')
+        lib = _cabi.lib()
+        f32 = dict(dtype=torch.float32, device=dev)
+        rays_o = rays_o.detach().to(**f32).contiguous()
+        rays_d = rays_d.detach().to(**f32).contiguous()
+        R, S = rays_o.shape[0], cfg.rendering_n_surface
+        td = target_d.detach().to(**f32).reshape(-1).contiguous()
+        ts = target_s.detach().to(**f32).contiguous() if target_s is not None else None
+        radius = radius.detach().to(**f32).reshape(-1).contiguous()
+        # far = min(5 * mean(d), max(1.2 * d)) (conv_onet_pointslam.py:340-342), batch-global
+        far = torch.minimum(5 * td.mean(), torch.max(td * 1.2)).reshape(1).float().contiguous()
+        o = dict(rgb=torch.empty(R, 3, **f32), depth=torch.empty(R, **f32),
+                 uncertainty=torch.empty(R, **f32),
+                 valid_ray_mask=torch.empty(R, dtype=torch.uint8, device=dev),
+                 losses=torch.zeros(2, **f32))
+        rays = XrdRays(R, ptr(rays_o), ptr(rays_d), ptr(ts), ptr(td))
+        ix = npc.index_struct()
+        feats = XrdPointFeats(ptr(npc.geo_feats.detach()), ptr(npc.frustum_mask))
+        dec = _dec_struct([t.detach() for t in self.decoder.geo_decoder.tensors()], 32, 1)
+        rf = rand_feat.detach().to(**f32).contiguous() if rand_feat is not None else None
+        c = XrdPointCfg(0, int(is_mapping), S, cfg.rendering_near_end_surface,
+                        cfg.rendering_far_end_surface, cfg.rendering_near_end,
+                        cfg.rendering_sigmoid_coef_mapper, cfg.pointcloud_min_nn_num,
+                        cfg.mapping_w_color_loss if is_mapping else cfg.tracking_w_color_loss,
+                        int(cfg.tracking_handle_dynamic), int(cfg.tracking_use_color_in_tracking),
+                        ptr(self._t_surface), ptr(far), ptr(radius), ptr(rf))
+        zc = getattr(self, '_z_capture', None)
+        out = XrdPointOut(ptr(o['rgb']), ptr(o['depth']), ptr(o['uncertainty']),
+                          ptr(o['valid_ray_mask']), ptr(zc), ptr(o['losses']))
+        g, gs = None, None
+        if with_grads:
+            g = dict(d_geo_feats=torch.zeros_like(npc.geo_feats) if need_feats else None,
+                     d_rays_o=torch.empty(R, 3, **f32) if need_rays else None,
+                     d_rays_d=torch.empty(R, 3, **f32) if need_rays else None)
+            gs = XrdPointGrads(ptr(g['d_geo_feats']), ptr(g['d_rays_o']), ptr(g['d_rays_d']))
+        nb = lib.xrd_pointslam_workspace_bytes(R, S, int(with_grads))
+        ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            st = lib.xrd_pointslam_step(C.byref(rays), C.byref(ix), C.byref(feats), C.byref(dec),
+                                        C.byref(c), C.byref(out),
+                                        C.byref(gs) if gs is not None else None, ptr(ws), nb,
+                                        torch.cuda.current_stream(dev).cuda_stream)
+        check('xrd_pointslam_step', st)
+        o['valid_ray_mask'] = o['valid_ray_mask'].bool()
+        return o, g
+
+    def get_outputs(self, input) -> Dict[str, Union[torch.Tensor, List]]:
+        """conv_onet_pointslam.py:130-142.  Optional ``rand_feat`` [32] replaces the random
+        feature of samples with too few neighbours (Q6)."""
+        stage = input['stage']
+        rays_o, rays_d = input['rays_o'], input['rays_d']
+        td, ts = input['target_d'], input.get('target_s')
+        radius = input['batch_dynamic_r']
+        fused = torch.is_grad_enabled() and 'is_mapping' in input
+        if fused:
+            losses, rgb, depth, unc, valid = _PointStep.apply(
+                self, stage, input['is_mapping'], ts, td, radius, input.get('rand_feat'), rays_o,
+                rays_d, self.neural_point_cloud.geo_feats)
+            return {'rgb': rgb, 'depth': depth, 'uncertainty': unc, 'valid_ray_mask': valid,
+                    'stage': stage, '_losses': losses}
+        o, _ = self._launch(stage, True, rays_o, rays_d, ts, td, radius, input.get('rand_feat'), False)
+        o.pop('losses')
+        o['stage'] = stage
+        return o
+
+    def get_loss_dict(self, outputs, inputs, is_mapping, stage=None) -> Dict[str, torch.Tensor]:
+        """conv_onet_pointslam.py:144-195."""
+        ls = outputs['_losses']
+        d = {'geo_loss': ls[0]}
+        if outputs['stage'] == 'color' or (not is_mapping and
+                                           self.config.tracking_use_color_in_tracking
+                                           and outputs['stage'] == 'color'):
+            d['rgb_loss'] = ls[1]
+        return d
+
+    def get_param_groups(self) -> Dict[str, List[Parameter]]:
+        """conv_onet_pointslam.py:197-210."""
+        groups = {}
+        npc = self.neural_point_cloud
+        groups['geometry'] = [npc.geo_feats]
+        groups['color'] = [npc.col_feats]
+        return groups

@@ -83,6 +83,11 @@ struct DecParams {
   int Pp;
   float* dp;            // [3][P] d loss / d point, accumulated across the decoder passes
   int need_dp;
+  // Point-SLAM reuses this decoder with a kNN-interpolated feature instead of a grid:
+  const float* zf;      // float32 sample depths (z == NULL)
+  const float* ext_c;   // [c_dim][P] feature rows (ga.data == NULL)
+  float* ext_dc;        // [c_dim][P] gradient w.r.t. the feature rows
+  float embed_scale;    // 1 (NICE: sin(p B)) or 2*pi (Point-SLAM: sin(2 pi p B))
 };
 
 // rows of the activation workspace (trainable decoder)
@@ -96,7 +101,7 @@ __host__ __device__ inline int row_do(int c_dim) { return row_pf(c_dim) + 3; }
 __host__ __device__ inline int n_rows(int c_dim) { return row_do(c_dim) + 4; }
 
 // ------------------------------------------------------------- sampling ---
-__global__ void k_maxdepth(const float* d, int R, float* out) {
+static __global__ void k_maxdepth(const float* d, int R, float* out) {
   __shared__ float sm[32];
   float m = -INFINITY;
   for (int i = threadIdx.x; i < R; i += blockDim.x) m = fmaxf(m, d[i]);
@@ -119,7 +124,7 @@ struct SampleParams {
   double* z;           // [R][ns+nsurf]
 };
 
-__global__ void __launch_bounds__(128) k_sample(SampleParams p) {
+static __global__ void __launch_bounds__(128) k_sample(SampleParams p) {
   __shared__ double zs[4][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 4 + warp;
@@ -191,6 +196,13 @@ __device__ __forceinline__ void src_index(float x, int size, int& i0, float& f, 
 
 __device__ __forceinline__ void point_f64(const DecParams& P, int p, double pt[3]) {
   const int r = p / P.S;
+  if (!P.z) {  // Point-SLAM: pts = rays_o + rays_d * z, all float32
+    const float z = P.zf[p];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      pt[d] = (double)__fadd_rn(P.rays_o[r * 3 + d], __fmul_rn(P.rays_d[r * 3 + d], z));
+    return;
+  }
   const double z = P.z[p];
 #pragma unroll
   for (int d = 0; d < 3; ++d)
@@ -329,31 +341,31 @@ __device__ __forceinline__ float dot32(const float (&g)[H], const float* __restr
   return a0 + a1;
 }
 // acc += W^T[0..n) x, x in a shared-memory column (stride T)
-__device__ __noinline__ void dense_col(float (&acc)[H], const float* __restrict__ wT,
+static __device__ __noinline__ void dense_col(float (&acc)[H], const float* __restrict__ wT,
                                        const float* __restrict__ col, int n) {
 #pragma unroll 2
   for (int i = 0; i < n; ++i) fma32(acc, col[i * T], wT + i * H);
 }
 // acc += W^T h, h in registers
-__device__ __noinline__ void dense_reg(float (&acc)[H], const float* __restrict__ wT,
+static __device__ __noinline__ void dense_reg(float (&acc)[H], const float* __restrict__ wT,
                                        const float (&h)[H]) {
 #pragma unroll
   for (int i = 0; i < H; ++i) fma32(acc, h[i], wT + i * H);
 }
 // col[i] += <W^T[i], g>  for i in [0,n)
-__device__ __noinline__ void denseT_col(float* __restrict__ col, const float* __restrict__ wT,
+static __device__ __noinline__ void denseT_col(float* __restrict__ col, const float* __restrict__ wT,
                                         const float (&g)[H], int n) {
 #pragma unroll 2
   for (int i = 0; i < n; ++i) col[i * T] += dot32(g, wT + i * H);
 }
 // out[i] = <W^T[i], g>
-__device__ __noinline__ void denseT_reg(float (&out)[H], const float* __restrict__ wT,
+static __device__ __noinline__ void denseT_reg(float (&out)[H], const float* __restrict__ wT,
                                         const float (&g)[H]) {
 #pragma unroll
   for (int i = 0; i < H; ++i) out[i] = dot32(g, wT + i * H);
 }
 
-__device__ void stage_weights(const XrdNiceDecoder& d, float* sw) {
+static __device__ void stage_weights(const XrdNiceDecoder& d, float* sw) {
   const WOff o = woff(d.c_dim);
   const int in[5] = {E, H, H, E + H, H};
   for (int l = 0; l < 5; ++l) {
@@ -379,7 +391,7 @@ __device__ void stage_weights(const XrdNiceDecoder& d, float* sw) {
 }
 
 // -------------------------------------------------------------- forward ---
-__global__ void __launch_bounds__(T) k_decoder_fwd(const DecParams P) {
+static __global__ void __launch_bounds__(T) k_decoder_fwd(const DecParams P) {
   extern __shared__ __align__(16) float smem[];
   const WOff o = woff(P.dec.c_dim);
   float* sw = smem;
@@ -394,15 +406,20 @@ __global__ void __launch_bounds__(T) k_decoder_fwd(const DecParams P) {
     const bool active = p < P.P;
     double pt[3] = {0.0, 0.0, 0.0};
     if (active) point_f64(P, p, pt);
-    Cell ca = make_cell(P, P.ga, pt);
-    trilerp_coop(P.ga, ca, active, ccol, tbase);
-    if (P.gb.data) {
-      Cell cb = make_cell(P, P.gb, pt);
-      trilerp_coop(P.gb, cb, active, ccol + 32 * T, tbase);
+    if (P.ga.data) {
+      Cell ca = make_cell(P, P.ga, pt);
+      trilerp_coop(P.ga, ca, active, ccol, tbase);
+      if (P.gb.data) {
+        Cell cb = make_cell(P, P.gb, pt);
+        trilerp_coop(P.gb, cb, active, ccol + 32 * T, tbase);
+      }
+    } else if (active) {
+      for (int m = 0; m < P.dec.c_dim; ++m) ccol[m * T + tid] = P.ext_c[(size_t)m * P.P + p];
     }
     __syncwarp();
     if (active) {
-    const float pf[3] = {(float)pt[0], (float)pt[1], (float)pt[2]};
+    const float sc = P.embed_scale;
+    const float pf[3] = {sc * (float)pt[0], sc * (float)pt[1], sc * (float)pt[2]};
     float* e = ecol + tid;
     float* c = ccol + tid;
     const float* Bm = sw + o.B;
@@ -449,7 +466,7 @@ __global__ void __launch_bounds__(T) k_decoder_fwd(const DecParams P) {
 }
 
 // ------------------------------------------------------------- backward ---
-__global__ void __launch_bounds__(T) k_decoder_bwd(const DecParams P) {
+static __global__ void __launch_bounds__(T) k_decoder_bwd(const DecParams P) {
   extern __shared__ __align__(16) float smem[];
   const WOff o = woff(P.dec.c_dim);
   float* sw = smem;
@@ -494,8 +511,9 @@ __global__ void __launch_bounds__(T) k_decoder_bwd(const DecParams P) {
         if (l == 0 || l == 3) denseT_col(de, sw + o.pts[l], g, E);
         if (l != 0) denseT_reg(dh, sw + o.pts[l] + (l == 3 ? E * H : 0), g);
       }
-      // embedding backward: e = sin(pf B)
-      const float pf[3] = {(float)pt[0], (float)pt[1], (float)pt[2]};
+      // embedding backward: e = sin(scale * p B)
+      const float sc = P.embed_scale;
+      const float pf[3] = {sc * (float)pt[0], sc * (float)pt[1], sc * (float)pt[2]};
       const float* Bm = sw + o.B;
       for (int m = 0; m < E; ++m) {
         const float gm = de[m * T] * cosf(pf[0] * Bm[m] + pf[1] * Bm[E + m] + pf[2] * Bm[2 * E + m]);
@@ -504,10 +522,22 @@ __global__ void __launch_bounds__(T) k_decoder_bwd(const DecParams P) {
         dpf[2] = fmaf(gm, Bm[2 * E + m], dpf[2]);
         if (P.acts) P.acts[(size_t)(row_gm(cd) + m) * P.Pp + p] = gm;
       }
+#pragma unroll
+      for (int d = 0; d < 3; ++d) dpf[d] *= sc;
       if (P.acts)
         for (int d = 0; d < 3; ++d) P.acts[(size_t)(row_pf(cd) + d) * P.Pp + p] = pf[d];
     }
     __syncwarp();
+    if (!P.ga.data) {  // Point-SLAM: hand d loss / d feature to the kNN interpolation backward
+      if (active) {
+        for (int m = 0; m < cd; ++m) P.ext_dc[(size_t)m * P.P + p] = dc[m * T];
+        if (P.need_dp)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) P.dp[(size_t)d * P.P + p] += dpf[d];
+      }
+      __syncwarp();
+      continue;
+    }
     Cell ca = make_cell(P, P.ga, pt);
     float gi[3];
     trilerp_coop_bwd(P.ga, ca, active, ccol, tbase, P.need_dp != 0, gi);
@@ -553,7 +583,7 @@ __device__ __forceinline__ bool in_bound(const CompParams& P, int r, double z) {
 
 // warp per ray, S <= 64: lane handles samples lane and lane + 32
 template <bool BWD>
-__global__ void __launch_bounds__(128) k_composite(const CompParams P) {
+static __global__ void __launch_bounds__(128) k_composite(const CompParams P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 4 + warp;
   if (r >= P.R) return;
@@ -676,7 +706,7 @@ struct LossParams {
   float* losses;          // [2]
 };
 
-__global__ void __launch_bounds__(1024) k_loss(const LossParams P) {
+static __global__ void __launch_bounds__(1024) k_loss(const LossParams P) {
   __shared__ double red[2][32];
   __shared__ double s_med;
   const int tid = threadIdx.x;
@@ -756,7 +786,7 @@ __global__ void __launch_bounds__(1024) k_loss(const LossParams P) {
 }
 
 // --------------------------------------------------------- ray reduction ---
-__global__ void __launch_bounds__(128) k_rayreduce(int R, int S, int P, const double* z,
+static __global__ void __launch_bounds__(128) k_rayreduce(int R, int S, int P, const double* z,
                                                    const float* dp, float* d_o, float* d_d) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 4 + warp;
@@ -785,6 +815,7 @@ __global__ void __launch_bounds__(128) k_rayreduce(int R, int S, int P, const do
 }  // namespace nice
 }  // namespace xrd
 
+#ifndef XRD_NICE_KERNELS_ONLY
 using namespace xrd;
 using namespace xrd::nice;
 
@@ -874,6 +905,7 @@ extern "C" int xrd_nice_step(const XrdRays* rays, const XrdNiceGrid grids[3],
     D.acts = nullptr; D.Pp = Pp;
     D.dp = grads ? reinterpret_cast<float*>(ws + L.dp) : nullptr;
     D.need_dp = grads && (grads->d_rays_o || grads->d_rays_d);
+    D.zf = nullptr; D.ext_c = nullptr; D.ext_dc = nullptr; D.embed_scale = 1.0f;
     return D;
   };
   auto dec_smem = [&](int c_dim) { return sizeof(float) * ((size_t)woff(c_dim).total + (size_t)(E + CMAX) * T); };
@@ -975,3 +1007,5 @@ extern "C" int xrd_nice_step(const XrdRays* rays, const XrdNiceGrid grids[3],
   }
   return XRD_OK;
 }
+
+#endif  // XRD_NICE_KERNELS_ONLY

@@ -1,0 +1,541 @@
+// Point-SLAM render-and-optimise step, stage 'geometry' (sm_100a): exact hash-grid kNN, inverse-
+// distance feature interpolation over the neural point cloud, Fourier MLP, normalised occupancy
+// compositing, losses and backward.
+//
+// Replaces (reference @ f0366f20):
+//   slam/model_components/neural_point_cloud.py:223-282 find_neighbors_faiss (faiss-gpu IVFFlat
+//       through host numpy round trips -> exact in-kernel radius kNN)
+//   slam/model_components/decoder_pointslam.py:162-273 MLP_geometry.get_feature_at_pos / forward
+//   slam/models/conv_onet_pointslam.py:311-461 render_batch_ray, :144-195 get_loss_dict
+//   slam/model_components/utils.py:247-295 raw2outputs_nerf_color2
+// The 5x32 Fourier MLP is the NICE decoder with sin(2 pi p B) and an externally supplied
+// feature: its kernels are shared (nice.cu, compiled in here as static functions).
+#include <float.h>
+#include <math.h>
+
+#define XRD_NICE_KERNELS_ONLY
+#include "nice.cu"
+
+namespace xrd {
+namespace point {
+
+constexpr int KNN = 8;
+constexpr int CD = 32;
+
+__device__ __forceinline__ uint32_t bucket_of(int ix, int iy, int iz, int table) {
+  return ((uint32_t)ix * 73856093u ^ (uint32_t)iy * 19349663u ^ (uint32_t)iz * 83492791u) &
+         (uint32_t)(table - 1);
+}
+__device__ __forceinline__ float sqdist(const float a[3], const float* b) {
+  const float dx = __fsub_rn(b[0], a[0]), dy = __fsub_rn(b[1], a[1]), dz = __fsub_rn(b[2], a[2]);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+struct KnnParams {
+  XrdPointIndex ix;
+  const float* q;       // [P][3]  or NULL: derive from rays / z
+  const float *rays_o, *rays_d, *z;
+  int S;
+  const float* radius;  // per query (stride 1) or per ray (stride S via division)
+  int radius_div;       // query index / radius_div selects the radius
+  int P;
+  float* D; int* I; int* nn;
+};
+
+__device__ __forceinline__ void query_point(const KnnParams& K, int p, float out[3]) {
+  if (K.q) { out[0] = K.q[p * 3]; out[1] = K.q[p * 3 + 1]; out[2] = K.q[p * 3 + 2]; return; }
+  const int r = p / K.S;
+  const float z = K.z[p];
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+    out[d] = __fadd_rn(K.rays_o[r * 3 + d], __fmul_rn(K.rays_d[r * 3 + d], z));
+}
+
+// exact radius-limited 8-NN, ascending (D, id); missing entries: id -1, D = FLT_MAX (faiss)
+__global__ void __launch_bounds__(128) k_knn(const KnnParams K) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= K.P) return;
+  float q[3];
+  query_point(K, p, q);
+  const float r = K.radius[p / K.radius_div];
+  const float r2 = r * r;
+  float bd[KNN]; int bi[KNN];
+#pragma unroll
+  for (int j = 0; j < KNN; ++j) { bd[j] = FLT_MAX; bi[j] = -1; }
+  int cnt = 0;
+  const float inv = 1.0f / K.ix.cell;
+  int lo[3], hi[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    lo[d] = (int)floorf((q[d] - r) * inv);
+    hi[d] = (int)floorf((q[d] + r) * inv);
+  }
+  for (int iz = lo[2]; iz <= hi[2]; ++iz)
+    for (int iy = lo[1]; iy <= hi[1]; ++iy)
+      for (int ixx = lo[0]; ixx <= hi[0]; ++ixx) {
+        const uint32_t b = bucket_of(ixx, iy, iz, K.ix.table_size);
+        const int s = K.ix.cell_start[b], e = K.ix.cell_end[b];
+        for (int j = s; j < e; ++j) {
+          const int id = K.ix.sorted_ids[j];
+          const float* x = K.ix.pos + (size_t)id * 3;
+          // a bucket can hold several cells: accept the point only in its own cell's turn
+          if ((int)floorf(x[0] * inv) != ixx || (int)floorf(x[1] * inv) != iy ||
+              (int)floorf(x[2] * inv) != iz)
+            continue;
+          const float d2 = sqdist(q, x);
+          if (d2 > r2) continue;
+          if (d2 < bd[KNN - 1] || (d2 == bd[KNN - 1] && id < bi[KNN - 1])) {
+            float cd = d2; int ci = id;  // insert keeping (D, id) ascending
+#pragma unroll
+            for (int t = 0; t < KNN; ++t) {
+              const bool before = cd < bd[t] || (cd == bd[t] && (ci < bi[t] || bi[t] < 0));
+              if (before) { const float td = bd[t]; const int ti = bi[t]; bd[t] = cd; bi[t] = ci; cd = td; ci = ti; }
+            }
+          }
+        }
+      }
+#pragma unroll
+  for (int j = 0; j < KNN; ++j) {
+    K.D[(size_t)p * KNN + j] = bd[j]; K.I[(size_t)p * KNN + j] = bi[j];
+    cnt += (bd[j] < r2);  // neighbor_num = (D < r^2).sum(-1) over the k returned (npc.py:262)
+  }
+  K.nn[p] = cnt;
+}
+
+// ---------------------------------------------------------- interpolation ---
+struct InterpParams {
+  KnnParams K;
+  const float* feats; const unsigned char* fmask;
+  const float* rand_feat;
+  int min_nn;
+  float* c;          // [32][P]
+  unsigned char* has_nb;  // [P]
+  // backward
+  const float* dc;   // [32][P]
+  float* d_feats;
+  float* dp;         // [3][P] accumulated
+  int need_dp;
+};
+
+__device__ __forceinline__ void nb_weights(const InterpParams& Q, int p, const float q[3],
+                                           float w[KNN], float a[KNN], int id[KNN], float& A) {
+  const float r = Q.K.radius[p / Q.K.radius_div];
+  const float r2 = r * r;
+  A = 0.f;
+#pragma unroll
+  for (int j = 0; j < KNN; ++j) {
+    id[j] = Q.K.I[(size_t)p * KNN + j];
+    float aj = 0.f;
+    if (id[j] >= 0) {
+      const float d2 = sqdist(q, Q.K.ix.pos + (size_t)id[j] * 3);  // re-computed (is_tracker path)
+      aj = (d2 > r2) ? 0.f : 1.0f / (d2 + 1e-10f);
+    }
+    a[j] = aj;
+    A += fabsf(aj);
+  }
+  A = fmaxf(A, 1e-12f);  // F.normalize(p=1, eps=1e-12)
+#pragma unroll
+  for (int j = 0; j < KNN; ++j) w[j] = a[j] / A;
+}
+
+__global__ void __launch_bounds__(128) k_interp_fwd(const InterpParams Q) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Q.K.P) return;
+  float q[3];
+  query_point(Q.K, p, q);
+  const bool has = Q.K.nn[p] > Q.min_nn - 1;
+  Q.has_nb[p] = has;
+  float c[CD];
+#pragma unroll
+  for (int m = 0; m < CD; ++m) c[m] = 0.f;
+  if (has) {
+    float w[KNN], a[KNN], A; int id[KNN];
+    nb_weights(Q, p, q, w, a, id, A);
+#pragma unroll
+    for (int j = 0; j < KNN; ++j) {
+      if (id[j] < 0 || w[j] == 0.f) continue;
+      if (Q.fmask && !Q.fmask[id[j]]) continue;  // geo_feats * frustum_mask
+      const float4* f = reinterpret_cast<const float4*>(Q.feats + (size_t)id[j] * CD);
+#pragma unroll
+      for (int m4 = 0; m4 < CD / 4; ++m4) {
+        const float4 v = __ldg(&f[m4]);
+        c[4 * m4] = fmaf(w[j], v.x, c[4 * m4]); c[4 * m4 + 1] = fmaf(w[j], v.y, c[4 * m4 + 1]);
+        c[4 * m4 + 2] = fmaf(w[j], v.z, c[4 * m4 + 2]); c[4 * m4 + 3] = fmaf(w[j], v.w, c[4 * m4 + 3]);
+      }
+    }
+  } else if (Q.rand_feat) {
+#pragma unroll
+    for (int m = 0; m < CD; ++m) c[m] = Q.rand_feat[m];
+  }
+#pragma unroll
+  for (int m = 0; m < CD; ++m) Q.c[(size_t)m * Q.K.P + p] = c[m];
+}
+
+__global__ void __launch_bounds__(128) k_interp_bwd(const InterpParams Q) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Q.K.P) return;
+  if (!Q.has_nb[p]) return;  // constant feature: no gradient
+  float q[3];
+  query_point(Q.K, p, q);
+  float w[KNN], a[KNN], A; int id[KNN];
+  nb_weights(Q, p, q, w, a, id, A);
+  float dc[CD];
+#pragma unroll
+  for (int m = 0; m < CD; ++m) dc[m] = Q.dc[(size_t)m * Q.K.P + p];
+  float dw[KNN];
+  float sw = 0.f;
+#pragma unroll
+  for (int j = 0; j < KNN; ++j) {
+    dw[j] = 0.f;
+    if (id[j] < 0 || a[j] == 0.f) continue;
+    const bool on = !Q.fmask || Q.fmask[id[j]];
+    if (on) {
+      const float4* f = reinterpret_cast<const float4*>(Q.feats + (size_t)id[j] * CD);
+      float s = 0.f;
+#pragma unroll
+      for (int m4 = 0; m4 < CD / 4; ++m4) {
+        const float4 v = __ldg(&f[m4]);
+        s += v.x * dc[4 * m4] + v.y * dc[4 * m4 + 1] + v.z * dc[4 * m4 + 2] + v.w * dc[4 * m4 + 3];
+      }
+      dw[j] = s;
+      if (Q.d_feats)
+#pragma unroll
+        for (int m4 = 0; m4 < CD / 4; ++m4)
+          red_add_v4(Q.d_feats + (size_t)id[j] * CD + 4 * m4, w[j] * dc[4 * m4], w[j] * dc[4 * m4 + 1],
+                     w[j] * dc[4 * m4 + 2], w[j] * dc[4 * m4 + 3]);
+    }
+    sw += w[j] * dw[j];
+  }
+  if (!Q.need_dp) return;
+  // w = a / A (a >= 0): dL/da_j = (dw_j - sum_i w_i dw_i) / A ; a = 1/(D+eps): da/dD = -a^2 ;
+  // D = |x - p|^2: dD/dp = -2 (x - p)
+  float g[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < KNN; ++j) {
+    if (id[j] < 0 || a[j] == 0.f) continue;
+    const float da = (dw[j] - sw) / A;
+    const float dD = -da * a[j] * a[j];
+    const float* x = Q.K.ix.pos + (size_t)id[j] * 3;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) g[d] += dD * (-2.f) * (x[d] - q[d]);
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) Q.dp[(size_t)d * Q.K.P + p] += g[d];
+}
+
+// ------------------------------------------------------------- per ray ---
+struct RayP {
+  int R, S;
+  const float *rays_o, *rays_d, *target_s, *target_d;
+  const float *t_surface, *far;
+  float near_s, far_s, near_end, coef;
+  float* z;                       // [R][S]
+  const float* occ;               // [P]
+  const unsigned char* has_nb;    // [P]
+  int min_valid;                  // int(S/2 + 1)
+  float *o_rgb, *o_depth, *o_var; unsigned char* o_valid;
+  // loss / backward
+  int is_mapping, handle_dynamic;
+  float* gd;                      // [R] d loss / d depth
+  float* tmp;                     // [R]
+  float* losses;
+  float* d_occ;                   // [P]
+};
+
+__global__ void __launch_bounds__(128) k_sample_z(const RayP P) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= P.R) return;
+  const float d = P.target_d[r];
+  const int S = P.S;
+  if (d > 0.f) {
+    const float a = __fmul_rn(P.near_s, d), b = __fmul_rn(P.far_s, d);
+    for (int k = 0; k < S; ++k) {
+      const float t = P.t_surface[k];
+      P.z[r * S + k] = __fadd_rn(__fmul_rn(a, __fsub_rn(1.f, t)), __fmul_rn(b, t));
+    }
+  } else {
+    // torch.linspace(near_end, max(far), S): scalar formula (S < SIMD width)
+    const float end = P.far[0], start = P.near_end;
+    const float step = (end - start) / (float)(S - 1);
+    for (int k = 0; k < S; ++k)
+      P.z[r * S + k] = (k < S / 2) ? __fadd_rn(start, __fmul_rn(step, (float)k))
+                                   : __fsub_rn(end, __fmul_rn(step, (float)(S - 1 - k)));
+  }
+}
+
+// raw2outputs_nerf_color2 (occupancy, normalised by the weight sum), stage geometry: rgb = 0
+__global__ void __launch_bounds__(128) k_composite_fwd(const RayP P) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= P.R) return;
+  const int S = P.S;
+  float T = 1.f, ws = 0.f, nd = 0.f;
+  float w[16];
+  int nvalid = 0;
+  for (int k = 0; k < S; ++k) {
+    const int p = r * S + k;
+    const bool nb = P.has_nb[p];
+    nvalid += nb;
+    const float occ = nb ? P.occ[p] : -100.f;
+    const float alpha = sigmoidf_acc(P.coef * occ);
+    w[k] = alpha * T;
+    T *= (1.f - alpha + 1e-10f);
+    ws += w[k];
+    nd = fmaf(w[k], P.z[p], nd);
+  }
+  const float wsum = ws + 1e-10f;
+  const float depth = nd / wsum;
+  float var = 0.f;
+  for (int k = 0; k < S; ++k) { const float t = P.z[r * S + k] - depth; var = fmaf(w[k] * t, t, var); }
+  const bool nz = P.target_d[r] > 0.f;
+  P.o_depth[r] = nz ? depth : 0.f;   // depth[~gt_non_zero_mask] = 0
+  P.o_var[r] = var;
+  P.o_rgb[r * 3] = P.o_rgb[r * 3 + 1] = P.o_rgb[r * 3 + 2] = 0.f;
+  P.o_valid[r] = !(nvalid < P.min_valid);
+}
+
+__global__ void __launch_bounds__(1024) k_loss(const RayP P) {
+  __shared__ double red[32];
+  __shared__ float s_med;
+  const int tid = threadIdx.x;
+  double ld = 0.0;
+  if (P.is_mapping) {
+    for (int r = tid; r < P.R; r += blockDim.x) {
+      const float D = P.target_d[r], d = P.o_depth[r];
+      const bool m = (D > 0.f) && P.o_valid[r] && !isnan(d);
+      float g = 0.f;
+      if (m) { ld += (double)fabsf(D - d); g = (d > D) ? 1.f : ((d < D) ? -1.f : 0.f); }
+      P.gd[r] = g;
+    }
+  } else {
+    for (int r = tid; r < P.R; r += blockDim.x) {
+      const float e = fabsf(P.target_d[r] - P.o_depth[r]);
+      P.tmp[r] = P.handle_dynamic ? e / sqrtf(P.o_var[r] + 1e-10f) : e;
+    }
+    __syncthreads();
+    const int want = (P.R - 1) / 2;
+    for (int r = tid; r < P.R; r += blockDim.x) {
+      const float v = P.tmp[r];
+      int rank = 0;
+      for (int j = 0; j < P.R; ++j) { const float u = P.tmp[j]; rank += (u < v) || (u == v && j < r); }
+      if (rank == want) s_med = v;
+    }
+    __syncthreads();
+    for (int r = tid; r < P.R; r += blockDim.x) {
+      const float D = P.target_d[r], d = P.o_depth[r], var = P.o_var[r];
+      const bool m = (P.tmp[r] < 10.f * s_med) && (D > 0.f) && !isnan(d) && !isnan(var);
+      float g = 0.f;
+      if (m) {
+        const float inv = 1.0f / sqrtf(var + 1e-10f);
+        const float t = fabsf(D - d) * inv;
+        ld += (double)fminf(fmaxf(t, 0.f), 1e3f);
+        if (t < 1e3f) g = ((d > D) ? inv : ((d < D) ? -inv : 0.f));
+      }
+      P.gd[r] = g;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ld += __shfl_xor_sync(0xffffffffu, ld, o);
+  if ((tid & 31) == 0) red[tid >> 5] = ld;
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) a += red[i];
+    P.losses[0] = (float)a;
+    P.losses[1] = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_composite_bwd(const RayP P) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= P.R) return;
+  const int S = P.S;
+  const bool nz = P.target_d[r] > 0.f;
+  const float gd = nz ? P.gd[r] : 0.f;  // zero-depth rays: depth overwritten by 0 (no gradient)
+  float alpha[16], Tt[16], w[16];
+  float T = 1.f, ws = 0.f, nd = 0.f;
+  for (int k = 0; k < S; ++k) {
+    const int p = r * S + k;
+    const float occ = P.has_nb[p] ? P.occ[p] : -100.f;
+    alpha[k] = sigmoidf_acc(P.coef * occ);
+    Tt[k] = T;
+    w[k] = alpha[k] * T;
+    T *= (1.f - alpha[k] + 1e-10f);
+    ws += w[k];
+    nd = fmaf(w[k], P.z[p], nd);
+  }
+  const float wsum = ws + 1e-10f, depth = nd / wsum;
+  // depth = sum w z / wsum -> dL/dw_k = gd (z_k - depth) / wsum
+  float suffix = 0.f;
+  for (int k = S - 1; k >= 0; --k) {
+    const int p = r * S + k;
+    const float q = gd * (P.z[p] - depth) / wsum;
+    const float da = q * Tt[k] - suffix / (1.f - alpha[k] + 1e-10f);
+    suffix += q * w[k];
+    // raw[~point_mask, -1] = -100 under no_grad: no gradient for samples without neighbours
+    P.d_occ[p] = P.has_nb[p] ? da * P.coef * alpha[k] * (1.f - alpha[k]) : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_rayreduce_f(int R, int S, int P, const float* z,
+                                                     const float* dp, float* d_o, float* d_d) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int k = 0; k < S; ++k) {
+    const size_t p = (size_t)r * S + k;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { const float g = dp[(size_t)d * P + p]; a[d] += g; a[3 + d] += g * z[p]; }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    if (d_o) d_o[r * 3 + d] = a[d];
+    if (d_d) d_d[r * 3 + d] = a[3 + d];
+  }
+}
+
+}  // namespace point
+}  // namespace xrd
+
+using namespace xrd;
+using namespace xrd::point;
+
+extern "C" int xrd_pointslam_knn_query(const XrdPointIndex* index, const float* queries,
+                                       const float* radius, int radius_stride, int n_queries,
+                                       float* D, int32_t* I, int32_t* neighbor_num, void* stream) {
+  if (!index || !queries || !radius || !D || !I || !neighbor_num) return XRD_E_NULL;
+  if (!index->pos || !index->cell_start || !index->cell_end || !index->sorted_ids) return XRD_E_NULL;
+  if (index->table_size < 1 || (index->table_size & (index->table_size - 1)) || !(index->cell > 0.f))
+    return XRD_E_SHAPE;
+  if (n_queries <= 0) return XRD_OK;
+  KnnParams K;
+  K.ix = *index; K.q = queries; K.rays_o = K.rays_d = K.z = nullptr; K.S = 1;
+  K.radius = radius; K.radius_div = radius_stride > 0 ? radius_stride : 1 << 30;
+  K.P = n_queries; K.D = D; K.I = I; K.nn = neighbor_num;
+  k_knn<<<(n_queries + 127) / 128, 128, 0, (cudaStream_t)stream>>>(K);
+  XRD_LAUNCH_CHECK();
+  return XRD_OK;
+}
+
+namespace {
+struct PWs { size_t z, D, I, nn, c, has, occ, d_occ, dc, dp, gd, tmp, masks, total; };
+PWs pws(int R, int S, int with_grads) {
+  PWs L;
+  const size_t P = (size_t)R * S;
+  size_t q = 0;
+  auto take = [&](size_t b) { size_t o = q; q += align_up(b, 256); return o; };
+  L.z = take(P * 4); L.D = take(P * KNN * 4); L.I = take(P * KNN * 4); L.nn = take(P * 4);
+  L.c = take(CD * P * 4); L.has = take(P); L.occ = take(P * 4);
+  L.d_occ = L.dc = L.dp = L.gd = L.tmp = L.masks = 0;
+  if (with_grads) {
+    L.d_occ = take(P * 4); L.dc = take(CD * P * 4); L.dp = take(3 * P * 4);
+    L.gd = take((size_t)R * 4); L.tmp = take((size_t)R * 4); L.masks = take(5 * P * 4);
+  }
+  L.total = q;
+  return L;
+}
+}  // namespace
+
+extern "C" size_t xrd_pointslam_workspace_bytes(int n_rays, int n_surface, int with_grads) {
+  return pws(n_rays, n_surface, with_grads).total;
+}
+
+extern "C" int xrd_pointslam_step(const XrdRays* rays, const XrdPointIndex* index,
+                                  const XrdPointFeats* feats, const XrdNiceDecoder* dec,
+                                  const XrdPointCfg* cfg, XrdPointOut* out, XrdPointGrads* grads,
+                                  void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!rays || !index || !feats || !dec || !cfg || !out || !workspace) return XRD_E_NULL;
+  if (!rays->rays_o || !rays->rays_d || !rays->target_d || !feats->geo_feats) return XRD_E_NULL;
+  if (!cfg->t_surface || !cfg->far || !cfg->radius_query) return XRD_E_NULL;
+  if (!out->rgb || !out->depth || !out->uncertainty || !out->valid_ray_mask) return XRD_E_NULL;
+  if (cfg->stage != 0) return XRD_E_SHAPE;  // stage 'color': next round
+  if (dec->c_dim != CD || dec->n_out != 1) return XRD_E_SHAPE;
+  const int R = rays->n_rays, S = cfg->n_surface;
+  if (R <= 0) return XRD_OK;
+  if (S < 2 || S > 16) return XRD_E_SHAPE;
+  if (grads && !out->losses) return XRD_E_NULL;
+  if (grads && !cfg->is_mapping && R > 8192) return XRD_E_SHAPE;
+  const PWs L = pws(R, S, grads != nullptr);
+  if (workspace_bytes < L.total) return XRD_E_WORKSPACE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  char* ws = reinterpret_cast<char*>(workspace);
+  const int P = R * S;
+  float* z = out->z_vals ? out->z_vals : reinterpret_cast<float*>(ws + L.z);
+
+  RayP Y;
+  Y.R = R; Y.S = S; Y.rays_o = rays->rays_o; Y.rays_d = rays->rays_d;
+  Y.target_s = rays->target_s; Y.target_d = rays->target_d; Y.t_surface = cfg->t_surface;
+  Y.far = cfg->far; Y.near_s = cfg->near_end_surface; Y.far_s = cfg->far_end_surface;
+  Y.near_end = cfg->near_end; Y.coef = cfg->sigmoid_coef; Y.z = z;
+  Y.occ = reinterpret_cast<float*>(ws + L.occ);
+  Y.has_nb = reinterpret_cast<unsigned char*>(ws + L.has);
+  Y.min_valid = S / 2 + 1;
+  Y.o_rgb = out->rgb; Y.o_depth = out->depth; Y.o_var = out->uncertainty; Y.o_valid = out->valid_ray_mask;
+  Y.is_mapping = cfg->is_mapping; Y.handle_dynamic = cfg->handle_dynamic;
+  Y.gd = nullptr; Y.tmp = nullptr; Y.losses = out->losses; Y.d_occ = nullptr;
+  k_sample_z<<<(R + 127) / 128, 128, 0, stream>>>(Y);
+  XRD_LAUNCH_CHECK();
+
+  InterpParams Q;
+  Q.K.ix = *index; Q.K.q = nullptr; Q.K.rays_o = rays->rays_o; Q.K.rays_d = rays->rays_d; Q.K.z = z;
+  Q.K.S = S; Q.K.radius = cfg->radius_query; Q.K.radius_div = S; Q.K.P = P;
+  Q.K.D = reinterpret_cast<float*>(ws + L.D); Q.K.I = reinterpret_cast<int*>(ws + L.I);
+  Q.K.nn = reinterpret_cast<int*>(ws + L.nn);
+  Q.feats = feats->geo_feats; Q.fmask = feats->frustum_mask; Q.rand_feat = cfg->rand_feat;
+  Q.min_nn = cfg->min_nn_num; Q.c = reinterpret_cast<float*>(ws + L.c);
+  Q.has_nb = reinterpret_cast<unsigned char*>(ws + L.has);
+  Q.dc = nullptr; Q.d_feats = nullptr; Q.dp = nullptr; Q.need_dp = 0;
+  {
+    KernelTimer kt(stream);
+    k_knn<<<(P + 127) / 128, 128, 0, stream>>>(Q.K);
+  }
+  XRD_LAUNCH_CHECK();
+  k_interp_fwd<<<(P + 127) / 128, 128, 0, stream>>>(Q);
+  XRD_LAUNCH_CHECK();
+
+  xrd::nice::DecParams D;
+  D.P = P; D.S = S; D.z = nullptr; D.zf = z; D.rays_o = rays->rays_o; D.rays_d = rays->rays_d;
+  for (int k = 0; k < 3; ++k) { D.bmin[k] = 0.0; D.bmax[k] = 1.0; }
+  D.ga.data = nullptr; D.ga.grad = nullptr; D.ga.nx = D.ga.ny = D.ga.nz = 1;
+  D.gb = D.ga;
+  D.dec = *dec;
+  for (int k = 0; k < 4; ++k) { D.out[k] = nullptr; D.dout[k] = nullptr; }
+  D.out[0] = reinterpret_cast<float*>(ws + L.occ);
+  D.masks = grads ? reinterpret_cast<uint32_t*>(ws + L.masks) : nullptr;
+  D.acts = nullptr; D.Pp = P;
+  D.dp = grads ? reinterpret_cast<float*>(ws + L.dp) : nullptr;
+  D.need_dp = grads && (grads->d_rays_o || grads->d_rays_d);
+  D.ext_c = Q.c; D.ext_dc = grads ? reinterpret_cast<float*>(ws + L.dc) : nullptr;
+  D.embed_scale = 6.283185307179586f;  // 2 * math.pi, float32
+  const size_t smem = sizeof(float) * ((size_t)xrd::nice::woff(CD).total +
+                                       (size_t)(xrd::nice::E + xrd::nice::CMAX) * xrd::nice::T);
+  const int tiles = (P + xrd::nice::T - 1) / xrd::nice::T, sms = num_sms();
+  const int gridx = tiles < sms ? tiles : sms;
+  XRD_CUDA_TRY(cudaFuncSetAttribute(xrd::nice::k_decoder_fwd,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  xrd::nice::k_decoder_fwd<<<gridx, xrd::nice::T, smem, stream>>>(D);
+  XRD_LAUNCH_CHECK();
+  k_composite_fwd<<<(R + 127) / 128, 128, 0, stream>>>(Y);
+  XRD_LAUNCH_CHECK();
+  if (!grads) return XRD_OK;
+
+  Y.gd = reinterpret_cast<float*>(ws + L.gd); Y.tmp = reinterpret_cast<float*>(ws + L.tmp);
+  Y.d_occ = reinterpret_cast<float*>(ws + L.d_occ);
+  point::k_loss<<<1, 1024, 0, stream>>>(Y);
+  XRD_LAUNCH_CHECK();
+  k_composite_bwd<<<(R + 127) / 128, 128, 0, stream>>>(Y);
+  XRD_LAUNCH_CHECK();
+  XRD_CUDA_TRY(cudaMemsetAsync(ws + L.dp, 0, 3 * (size_t)P * 4, stream));
+  D.dout[0] = Y.d_occ;
+  XRD_CUDA_TRY(cudaFuncSetAttribute(xrd::nice::k_decoder_bwd,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  xrd::nice::k_decoder_bwd<<<gridx, xrd::nice::T, smem, stream>>>(D);
+  XRD_LAUNCH_CHECK();
+  Q.dc = D.ext_dc; Q.d_feats = grads->d_geo_feats; Q.dp = D.dp; Q.need_dp = D.need_dp;
+  k_interp_bwd<<<(P + 127) / 128, 128, 0, stream>>>(Q);
+  XRD_LAUNCH_CHECK();
+  if (D.need_dp) {
+    k_rayreduce_f<<<(R + 127) / 128, 128, 0, stream>>>(R, S, P, z, D.dp, grads->d_rays_o, grads->d_rays_d);
+    XRD_LAUNCH_CHECK();
+  }
+  return XRD_OK;
+}
