@@ -82,6 +82,38 @@ typedef struct {
  * torch.linspace on the same host (the Python plugin does). */
 int xrd_linspace_f32(float start, float end, int steps, float* out);
 
+/* ---- shared front-end / optimiser ("next" row f1) ---------- */
+
+/* World-frame rays from camera-frame directions and a per-ray pose row:
+ *   rays_d[r] = sum_j dirs_cam[r][j] * poses[id][:3, j],  rays_o[r] = poses[id][:3, 3]
+ * replaces slam/common/common.py:39-53 (get_rays_from_uv) and the per-ray pose gather of
+ * slam/algorithms/coslam.py:208-216.  poses: DEVICE [n_poses,4,4] row-major c2w; pose_ids:
+ * DEVICE [R] int64 or NULL (all rays use pose 0); negative ids index from the end (python). */
+int xrd_rays_from_poses(int n_rays, const float* dirs_cam, const int64_t* pose_ids,
+                        const float* poses, int n_poses, float* rays_o, float* rays_d,
+                        void* stream);
+
+/* Backward of the above: d_poses [n_poses,4,4] (zeroed inside, bottom row stays 0)
+ *   d_poses[id][:3,:3] += outer(d_rays_d[r], dirs_cam[r]),  d_poses[id][:3,3] += d_rays_o[r]
+ * (what torch's index_put(accumulate=True) backward of `poses_all[ids]` computes). */
+int xrd_rays_pose_grads(int n_rays, const float* dirs_cam, const int64_t* pose_ids, int n_poses,
+                        const float* d_rays_o, const float* d_rays_d, float* d_poses,
+                        void* stream);
+
+/* One tensor of a multi-tensor Adam step (torch.optim.Adam, amsgrad=False); all DEVICE fp32.
+ * bias_correction{1,2} = 1 - beta{1,2}^step with step counted from 1 (host, double -> float). */
+#define XRD_ADAM_MAX_TENSORS 24
+typedef struct {
+  float* param; float* grad; float* exp_avg; float* exp_avg_sq;
+  long long n;
+  float lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2;
+} XrdAdamTensor;
+
+/* tensors: HOST array.  zero_grad != 0 also clears every grad (folds zero_grad_all,
+ * slam/engine/optimizers.py:150-162, into the pass).  Replaces optimizer_step_all (:125-148)
+ * for device-resident parameter groups. */
+int xrd_adam_step(const XrdAdamTensor* tensors, int n_tensors, int zero_grad, void* stream);
+
 /* ---- Co-SLAM ------------------------------------------------------------ */
 
 /* Multi-resolution hash grid in tcnn's parameter layout: one flat fp32 array,

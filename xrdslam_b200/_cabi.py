@@ -186,7 +186,17 @@ class XrdPointGrads(C.Structure):
 _lib = None
 
 # name -> (restype, argtypes); every symbol include/xrdslam_b200.h declares
+class XrdAdamTensor(C.Structure):
+    _fields_ = [('param', vp), ('grad', vp), ('exp_avg', vp), ('exp_avg_sq', vp),
+                ('n', C.c_longlong), ('lr', C.c_float), ('beta1', C.c_float),
+                ('beta2', C.c_float), ('eps', C.c_float), ('weight_decay', C.c_float),
+                ('bias_correction1', C.c_float), ('bias_correction2', C.c_float)]
+
+
 SYMBOLS = {
+    'xrd_rays_from_poses': (C.c_int, [C.c_int, vp, vp, vp, C.c_int, vp, vp, vp]),
+    'xrd_rays_pose_grads': (C.c_int, [C.c_int, vp, vp, C.c_int, vp, vp, vp, vp]),
+    'xrd_adam_step': (C.c_int, [C.POINTER(XrdAdamTensor), C.c_int, C.c_int, vp]),
     'xrd_abi_version': (C.c_int, []),
     'xrd_last_cuda_error': (C.c_int, []),
     'xrd_check_device': (C.c_int, [C.c_int]),

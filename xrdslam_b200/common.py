@@ -12,14 +12,62 @@ def _as_dev(x, device, dtype=torch.float32):
     return x.to(device=device, dtype=dtype)
 
 
+class _PosedRays(torch.autograd.Function):
+    """csrc/rays.cu: rays from camera-frame directions + per-ray pose row, and the pose
+    gradient reduction (one launch each; replaces torch's gather / index_put backward)."""
+    @staticmethod
+    def forward(ctx, dirs, ids, poses):
+        import ctypes as C
+        from . import _cabi
+        dirs = dirs.detach().to(torch.float32).contiguous()
+        P = poses.detach().to(torch.float32).contiguous()
+        R = dirs.shape[0]
+        rays_o = torch.empty(R, 3, device=dirs.device)
+        rays_d = torch.empty(R, 3, device=dirs.device)
+        with torch.cuda.device(dirs.device):
+            st = _cabi.lib().xrd_rays_from_poses(
+                R, _cabi.ptr(dirs), _cabi.ptr(ids), _cabi.ptr(P), P.shape[0], _cabi.ptr(rays_o),
+                _cabi.ptr(rays_d), torch.cuda.current_stream(dirs.device).cuda_stream)
+        _cabi.check('xrd_rays_from_poses', st)
+        ctx.save_for_backward(dirs, ids)
+        ctx.n_poses = P.shape[0]
+        return rays_o, rays_d
+
+    @staticmethod
+    def backward(ctx, g_o, g_d):
+        from . import _cabi
+        dirs, ids = ctx.saved_tensors
+        d_poses = torch.empty(ctx.n_poses, 4, 4, device=dirs.device)
+        g_o, g_d = g_o.contiguous(), g_d.contiguous()
+        with torch.cuda.device(dirs.device):
+            st = _cabi.lib().xrd_rays_pose_grads(
+                dirs.shape[0], _cabi.ptr(dirs), _cabi.ptr(ids), ctx.n_poses, _cabi.ptr(g_o),
+                _cabi.ptr(g_d), _cabi.ptr(d_poses),
+                torch.cuda.current_stream(dirs.device).cuda_stream)
+        _cabi.check('xrd_rays_pose_grads', st)
+        return None, None, d_poses
+
+
+def rays_from_poses(dirs_cam, pose_ids, poses):
+    """rays_o, rays_d [R,3] from camera-frame directions [R,3], per-ray pose rows `pose_ids`
+    ([R] int64, negative = from the end, or None: pose 0) and c2w `poses` [n,4,4];
+    differentiable w.r.t. poses (coslam.py:208-216 / common.py:39-53)."""
+    if dirs_cam.is_cuda:
+        if pose_ids is not None:
+            pose_ids = pose_ids.to(dirs_cam.device, torch.int64).contiguous()
+        return _PosedRays.apply(dirs_cam, pose_ids, poses.to(dirs_cam.device))
+    # host tensors (dataset preparation, CPU tests of the host logic): plain torch
+    ids = pose_ids if pose_ids is not None else torch.zeros(dirs_cam.shape[0], dtype=torch.int64)
+    rays_d = torch.sum(dirs_cam[:, None, :] * poses[ids, :3, :3], -1)
+    return poses[ids, :3, -1], rays_d
+
+
 def get_rays_from_uv(i, j, c2w, fx, fy, cx, cy, device):
     """rays for pixel coords (i: column, j: row); differentiable w.r.t. c2w."""
     c2w = _as_dev(c2w, device)
     dirs = torch.stack([(i - cx) / fx, -(j - cy) / fy, -torch.ones_like(i)],
-                       -1).to(device).reshape(-1, 1, 3)
-    rays_d = torch.sum(dirs * c2w[:3, :3], -1)
-    rays_o = c2w[:3, -1].expand(rays_d.shape)
-    return rays_o, rays_d
+                       -1).to(device).reshape(-1, 3)
+    return rays_from_poses(dirs, None, c2w.reshape(1, 4, 4))
 
 
 def get_sample_uv(H0, H1, W0, W1, n, depth, color, device='cuda:0',

@@ -12,8 +12,9 @@ import numpy as np
 import torch
 
 from .algorithm import Algorithm, AlgorithmConfig
-from .common import get_camera_rays, get_rays, get_samples
+from .common import get_camera_rays, get_rays, get_samples, rays_from_poses
 from .joint_encoding import JointEncodingConfig
+from .opt_pose import pose_matrices
 from .optimizers import AdamOptimizerConfig, Optimizers
 
 
@@ -61,6 +62,38 @@ class CoSLAMConfig(AlgorithmConfig):
     optimizers: Dict[str, Any] = field(default_factory=_coslam_optimizers)
 
 
+class _PinnedStaging:
+    """Ring of pinned host blocks for the per-iteration ray rows [n,7] + pose ids [n]: the
+    host gathers into a block, two async copies move it to the device, an event per block
+    guards its reuse (iterations are not synchronised with the host)."""
+    def __init__(self, depth=4):
+        self.depth, self.slots, self.k, self.cur = depth, [], 0, None
+
+    def acquire(self, n):
+        if len(self.slots) < self.depth:
+            self.slots.append(dict(rows=torch.empty(0, 7).pin_memory(),
+                                   ids=torch.empty(0, dtype=torch.int64).pin_memory(),
+                                   ev=None))
+        sl = self.slots[self.k % self.depth]
+        self.k += 1
+        if sl['ev'] is not None:
+            sl['ev'].synchronize()
+        if sl['rows'].shape[0] < n:
+            sl['rows'] = torch.empty(n, 7).pin_memory()
+            sl['ids'] = torch.empty(n, dtype=torch.int64).pin_memory()
+        self.cur = (sl, n)
+        return sl['rows'][:n], sl['ids'][:n]
+
+    def upload(self, dev):
+        sl, n = self.cur
+        rows = sl['rows'][:n].to(dev, non_blocking=True)
+        ids = sl['ids'][:n].to(dev, non_blocking=True)
+        if sl['ev'] is None:
+            sl['ev'] = torch.cuda.Event()
+        sl['ev'].record(torch.cuda.current_stream(dev))
+        return rows, ids
+
+
 class CoSLAM(Algorithm):
     def __init__(self, config: CoSLAMConfig, camera, device: str) -> None:
         super().__init__(config, camera, device)
@@ -74,6 +107,7 @@ class CoSLAM(Algorithm):
         self.num_rays_to_save = int(self.camera.width * self.camera.height *
                                     self.config.rays_to_save_ratio)
         self.rays = None  # [n_kf * num_rays_to_save, 7] pinned host memory
+        self._staging = _PinnedStaging()
         self.model_optimizers = None
         self._rng = np.random.default_rng(random.getrandbits(63))
         self._cam_dirs = get_camera_rays(camera.height, camera.width, camera.fx,
@@ -143,35 +177,41 @@ class CoSLAM(Algorithm):
         cur_frame = optimize_frames[-1]
         dev = self.device
         if is_mapping:
-            ids_all, rays_all, poses_all = [], [], []
+            # host side: choose rows (random.sample semantics) and gather them straight
+            # into a pinned staging block; device side: ONE copy of the rows, one of the
+            # pose ids, rays built by csrc/rays.cu (per-ray pose gather + its backward).
+            n_kf = len(self.keyframe_graph)
+            n_bank = self.config.mapping_sample if n_kf > 0 else 0
             n_cur = self.config.mapping_sample
-            if len(self.keyframe_graph) > 0:
-                sample_rays, frame_ids = self.sample_global_rays(
-                    self.config.mapping_sample)
-                ids_all, rays_all = [frame_ids], [sample_rays]
+            if n_kf > 0:
+                n_cur = int(np.maximum(self.config.mapping_sample // n_kf,
+                                       self.config.min_sample_pixels))
+            n = n_bank + n_cur
+            rows, ids = self._staging.acquire(n) if dev.type == 'cuda' else (
+                torch.empty(n, 7), torch.empty(n, dtype=torch.int64))
+            pose_list, detach = [], []
+            if n_kf > 0:
+                idxs = self._sample_ids(n_kf * self.num_rays_to_save, n_bank)
+                torch.index_select(self.rays, 0, idxs, out=rows[:n_bank])
+                torch.div(idxs, self.num_rays_to_save, rounding_mode='floor',
+                          out=ids[:n_bank])
                 for frame in optimize_frames[:-1]:
-                    pose = frame.get_pose().unsqueeze(0).to(dev)
-                    if frame.fid == 0:
-                        pose = pose.detach()
-                    poses_all.append(pose)
-                n_cur = int(np.maximum(
-                    self.config.mapping_sample // len(self.keyframe_graph),
-                    self.config.min_sample_pixels))
-            rays = self.sample_single_keyframe_rays(cur_frame, n_cur)
-            poses_all.append(cur_frame.get_pose().unsqueeze(0).to(dev))
-            ids_all.append(-torch.ones(len(rays), dtype=torch.int64))
-            rays_all.append(rays)
-            poses_all = torch.cat(poses_all, dim=0)
-            ids_all = torch.cat(ids_all, dim=0).to(dev, non_blocking=True)
-            rays_all = torch.cat(rays_all, dim=0)
+                    pose_list.append(frame.pose)
+                    detach.append(frame.fid == 0)
+            cur_tab = self._frame_rays(cur_frame)
+            torch.index_select(cur_tab, 0, self._sample_ids(cur_tab.shape[0], n_cur),
+                               out=rows[n_bank:])
+            ids[n_bank:] = -1  # the current frame's pose is appended last
+            pose_list.append(cur_frame.pose)
+            detach.append(False)
+            poses_all = pose_matrices(pose_list, detach).to(dev)
             if dev.type == 'cuda':
-                rays_all = rays_all.pin_memory().to(dev, non_blocking=True)
-            d_cam = rays_all[..., :3]
+                rays_all, ids_all = self._staging.upload(dev)
+            else:
+                rays_all, ids_all = rows, ids
             target_s = rays_all[..., 3:6]
             target_d = rays_all[..., 6:7]
-            R = poses_all[ids_all, :3, :3]  # [N,3,3] per-ray pose gather
-            rays_d = torch.sum(d_cam[:, None, :] * R, -1)
-            rays_o = poses_all[ids_all, :3, -1]
+            rays_o, rays_d = rays_from_poses(rays_all[..., :3], ids_all, poses_all)
             first_flag = len(self.keyframe_graph) == 0
         else:
             rays_o, rays_d, target_d, target_s = get_samples(

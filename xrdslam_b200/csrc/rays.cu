@@ -1,0 +1,110 @@
+// Shared front-end on the device ("next" row f1):
+//   world-frame rays from camera-frame directions and a per-ray pose row
+//     rays_d = sum_j dir_cam[j] * c2w[id][:3, j],   rays_o = c2w[id][:3, 3]
+//   (slam/common/common.py:39-53 get_rays_from_uv; slam/algorithms/coslam.py:208-216 per-ray
+//   pose gather `poses_all[ids_all]`), and the reduction of d loss / d rays into d loss / d c2w
+//   that torch does with an index_put(accumulate) sort + scatter (0.5 ms per iteration at
+//   4096 rays, profiles/r01_launches_*.csv) -- here one launch with shared-memory accumulators.
+#include "common.cuh"
+#include "../../include/xrdslam_b200.h"
+
+namespace xrd {
+namespace rays {
+
+constexpr int MAXP = 64;  // poses accumulated in shared memory (bundle window is ~5-20)
+
+struct P {
+  int R, n_poses;
+  const float* dirs; const int64_t* ids; const float* poses;
+  float *rays_o, *rays_d;
+  const float *d_rays_o, *d_rays_d;
+  float* d_poses;
+};
+
+__device__ __forceinline__ int pose_row(const P& p, int r) {
+  long long id = p.ids ? p.ids[r] : 0;
+  if (id < 0) id += p.n_poses;  // python indexing: -1 = the current frame, appended last
+  return (int)id;
+}
+
+__global__ void __launch_bounds__(256) k_fwd(const P p) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= p.R) return;
+  const float* M = p.poses + (size_t)pose_row(p, r) * 16;
+  const float d0 = p.dirs[r * 3], d1 = p.dirs[r * 3 + 1], d2 = p.dirs[r * 3 + 2];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    p.rays_d[r * 3 + c] = __fadd_rn(__fadd_rn(__fmul_rn(d0, M[c * 4]), __fmul_rn(d1, M[c * 4 + 1])),
+                                    __fmul_rn(d2, M[c * 4 + 2]));
+    p.rays_o[r * 3 + c] = M[c * 4 + 3];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_bwd(const P p) {
+  __shared__ float acc[MAXP * 12];
+  const bool use_smem = p.n_poses <= MAXP;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < p.n_poses * 12; i += blockDim.x) acc[i] = 0.f;
+    __syncthreads();
+  }
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < p.R; r += gridDim.x * blockDim.x) {
+    const int id = pose_row(p, r);
+    const float d[3] = {p.dirs[r * 3], p.dirs[r * 3 + 1], p.dirs[r * 3 + 2]};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float gd = p.d_rays_d ? p.d_rays_d[r * 3 + c] : 0.f;
+      const float go = p.d_rays_o ? p.d_rays_o[r * 3 + c] : 0.f;
+      if (use_smem) {
+        float* a = acc + id * 12 + c * 4;
+        atomicAdd(a, gd * d[0]); atomicAdd(a + 1, gd * d[1]); atomicAdd(a + 2, gd * d[2]);
+        atomicAdd(a + 3, go);
+      } else {
+        float* a = p.d_poses + (size_t)id * 16 + c * 4;
+        atomicAdd(a, gd * d[0]); atomicAdd(a + 1, gd * d[1]); atomicAdd(a + 2, gd * d[2]);
+        atomicAdd(a + 3, go);
+      }
+    }
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.n_poses * 12; i += blockDim.x)
+      if (acc[i] != 0.f) atomicAdd(p.d_poses + (size_t)(i / 12) * 16 + (i % 12), acc[i]);
+  }
+}
+
+}  // namespace rays
+}  // namespace xrd
+
+using namespace xrd;
+
+extern "C" int xrd_rays_from_poses(int n_rays, const float* dirs_cam, const int64_t* pose_ids,
+                                   const float* poses, int n_poses, float* rays_o, float* rays_d,
+                                   void* stream) {
+  if (n_rays <= 0) return XRD_OK;
+  if (!dirs_cam || !poses || !rays_o || !rays_d) return XRD_E_NULL;
+  if (n_poses < 1) return XRD_E_SHAPE;
+  rays::P p{};
+  p.R = n_rays; p.n_poses = n_poses; p.dirs = dirs_cam; p.ids = pose_ids; p.poses = poses;
+  p.rays_o = rays_o; p.rays_d = rays_d;
+  rays::k_fwd<<<(n_rays + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
+  XRD_LAUNCH_CHECK();
+  return XRD_OK;
+}
+
+extern "C" int xrd_rays_pose_grads(int n_rays, const float* dirs_cam, const int64_t* pose_ids,
+                                   int n_poses, const float* d_rays_o, const float* d_rays_d,
+                                   float* d_poses, void* stream) {
+  if (!d_poses) return XRD_E_NULL;
+  if (n_poses < 1) return XRD_E_SHAPE;
+  XRD_CUDA_TRY(cudaMemsetAsync(d_poses, 0, (size_t)n_poses * 16 * sizeof(float), (cudaStream_t)stream));
+  if (n_rays <= 0) return XRD_OK;
+  if (!dirs_cam || (!d_rays_o && !d_rays_d)) return XRD_E_NULL;
+  rays::P p{};
+  p.R = n_rays; p.n_poses = n_poses; p.dirs = dirs_cam; p.ids = pose_ids;
+  p.d_rays_o = d_rays_o; p.d_rays_d = d_rays_d; p.d_poses = d_poses;
+  int blocks = (n_rays + 255) / 256;
+  if (blocks > 148) blocks = 148;
+  rays::k_bwd<<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  XRD_LAUNCH_CHECK();
+  return XRD_OK;
+}

@@ -79,3 +79,37 @@ class OptimizablePose(nn.Module):
             raise ValueError(rot_rep)
         return OptimizablePose(torch.cat([u, rot], dim=-1).detach().clone(),
                                separate_LR=separate_LR, rot_rep=rot_rep)
+
+
+def pose_matrices(poses, detach=None):
+    """[n,4,4] c2w of a list of OptimizablePose in ONE batched evaluation (the per-frame
+    `matrix()` costs ~25 small host ops each; bundle adjustment evaluates 5-20 per
+    iteration).  `detach`: optional list of bools (coslam.py:181-182 fixes frame 0)."""
+    n = len(poses)
+    rep, sep = poses[0].rot_rep, poses[0].separate_LR
+    if any(p.rot_rep != rep or p.separate_LR != sep for p in poses):
+        M = torch.stack([p.matrix() for p in poses])
+    else:
+        rot = torch.stack([p._rot_params() for p in poses])
+        t = torch.stack([p.translation() for p in poses])
+        if rep == 'axis_angle':
+            angle = torch.norm(rot, dim=-1, keepdim=True)
+            zero = angle <= 1e-8  # torch.allclose(angle, 0) of the per-frame path
+            safe = torch.where(zero, torch.ones_like(angle), angle)
+            w0, w1, w2 = (rot / safe).unbind(dim=-1)
+            z = torch.zeros_like(w0)
+            wx = torch.stack([torch.stack([z, -w2, w1], dim=-1),
+                              torch.stack([w2, z, -w0], dim=-1),
+                              torch.stack([-w1, w0, z], dim=-1)], dim=-2)
+            eye = torch.eye(3, dtype=rot.dtype, device=rot.device).expand(n, 3, 3)
+            s, c = torch.sin(safe)[..., None], torch.cos(safe)[..., None]
+            Rm = eye + wx * s + (1. - c) * (wx @ wx)
+            Rm = torch.where(zero[..., None], eye, Rm)
+        else:
+            Rm = quaternion_to_matrix(rot)
+        bottom = torch.tensor([0., 0., 0., 1.], dtype=rot.dtype, device=rot.device)
+        M = torch.cat([torch.cat([Rm, t[..., None]], -1), bottom.expand(n, 1, 4)], -2)
+    if detach is not None and any(detach):
+        m = torch.tensor(detach, device=M.device)[:, None, None]
+        M = torch.where(m, M.detach(), M)
+    return M
