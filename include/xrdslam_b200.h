@@ -476,7 +476,7 @@ int xrd_pointslam_knn_query(const XrdPointIndex* index, const float* queries, co
                             int32_t* neighbor_num, void* stream);
 
 typedef struct {
-  int stage;               /* 0 = 'geometry' (stage 'color' -> XRD_E_SHAPE in this round)   */
+  int stage;               /* 0 = 'geometry', 1 = 'color'                                   */
   int is_mapping;
   int n_surface;           /* 5                                                             */
   float near_end_surface;  /* 0.98                                                          */
@@ -492,12 +492,37 @@ typedef struct {
   const float* radius_query; /* DEVICE [R] per-ray dynamic query radius                     */
   const float* rand_feat;  /* DEVICE [32] feature of samples with < min_nn neighbours (Q6)
                               or NULL = zeros                                               */
+  const float* rand_feat_color; /* the colour decoder's own draw (decoder_pointslam.py:463) */
 } XrdPointCfg;
 
 typedef struct {
   const float* geo_feats;      /* DEVICE [N][32]                                            */
-  const uint8_t* frustum_mask; /* DEVICE [N] or NULL                                        */
+  const uint8_t* frustum_mask; /* DEVICE [N] or NULL (multiplies geo_feats only, row P9)     */
+  const float* col_feats;      /* DEVICE [N][32]; stage colour only                         */
 } XrdPointFeats;
+
+/* Colour decoder (slam/model_components/decoder_pointslam.py:313-542 MLP_color + :276-292
+ * MLP_col_neighbor), all row-major [out][in] like nn.Linear:
+ *   per neighbour k: f_k = nb_w2 . softplus100(nb_w1 . [sin, cos(2 pi (x_k - p) B_rel), col_feat_k]) ; c = sum_k w_k f_k
+ *   h = softplus100(w[i] . h + b[i]) + (wc[i] . c + bc[i]),  i = 0..4, input cat after i = 2
+ *   rgb = sigmoid(wo . h + bo);  first input = [sin, cos](2 pi p B). */
+typedef struct {
+  const float* B;      /* [3][20] fixed (GaussianFourierFeatureTransform, not learnable)   */
+  const float* B_rel;  /* [3][10] learnable                                                */
+  const float* nb_w1; const float* nb_b1; /* [128][52], [128]                              */
+  const float* nb_w2; const float* nb_b2; /* [32][128], [32]                               */
+  const float* w[5];  const float* b[5];  /* [128][40|128|128|168|128], [128]              */
+  const float* wc[5]; const float* bc[5]; /* fc_c: [128][32], [128]                        */
+  const float* wo;    const float* bo;    /* [3][128], [3]                                 */
+} XrdPointColorDecoder;
+
+/* Same shapes; every non-NULL array is ACCUMULATED into. */
+typedef struct {
+  float* B_rel;
+  float* nb_w1; float* nb_b1; float* nb_w2; float* nb_b2;
+  float* w[5]; float* b[5]; float* wc[5]; float* bc[5];
+  float* wo; float* bo;
+} XrdPointColorDecoderGrads;
 
 typedef struct {
   float* rgb;              /* [R,3] (zeros in stage geometry)                               */
@@ -505,19 +530,22 @@ typedef struct {
   float* uncertainty;      /* [R]                                                           */
   uint8_t* valid_ray_mask; /* [R]                                                           */
   float* z_vals;           /* [R,n_surface] optional                                        */
-  float* losses;           /* [2] geo_loss, rgb_loss                                        */
+  float* losses;           /* [2] geo_loss, rgb_loss (already weighted)                     */
 } XrdPointOut;
 
 typedef struct {
   float* d_geo_feats;      /* [N][32] ACCUMULATED                                           */
   float* d_rays_o;         /* [R,3] or NULL                                                 */
   float* d_rays_d;
+  float* d_col_feats;      /* [N][32] ACCUMULATED; stage colour, or NULL                    */
+  XrdPointColorDecoderGrads* color; /* colour-decoder gradients or NULL (decoder fixed)     */
 } XrdPointGrads;
 
-size_t xrd_pointslam_workspace_bytes(int n_rays, int n_surface, int with_grads);
+size_t xrd_pointslam_workspace_bytes(int n_rays, int n_surface, int stage, int with_grads);
 
 int xrd_pointslam_step(const XrdRays* rays, const XrdPointIndex* index,
                        const XrdPointFeats* feats, const XrdNiceDecoder* geo_decoder,
+                       const XrdPointColorDecoder* color_decoder /* NULL in stage geometry */,
                        const XrdPointCfg* cfg, XrdPointOut* out, XrdPointGrads* grads,
                        void* workspace, size_t workspace_bytes, void* stream);
 

@@ -58,23 +58,62 @@ class GeoDecoder(nn.Module):
         return self.out(h).squeeze(-1)
 
 
+class ColorDecoder(nn.Module):
+    """MLP_color + MLP_col_neighbor (decoder_pointslam.py:276-292, 313-542): per-neighbour
+    F_theta([sin, cos(2 pi rel B_rel), col_feat]) weighted by the inverse-distance weights,
+    then a 5 x 128 softplus(beta=100) trunk on [sin, cos](2 pi p B) with fc_c(c) added after
+    every block and the embedding re-concatenated after block 2; sigmoid output."""
+    def __init__(self, gen=None):
+        super().__init__()
+        self.B = nn.Parameter(torch.randn(3, 20, generator=gen) * 32, requires_grad=False)
+        self.B_rel = nn.Parameter(torch.randn(3, 10, generator=gen) * 32)
+        self.nb1, self.nb2 = nn.Linear(52, 128), nn.Linear(128, 32)
+        self.fc_c = nn.ModuleList([nn.Linear(32, 128) for _ in range(5)])
+        self.pts = nn.ModuleList([nn.Linear(d, 128) for d in (40, 128, 128, 168, 128)])
+        self.out = nn.Linear(128, 3)
+
+    @staticmethod
+    def embed(x, B):
+        x = (2 * math.pi * x) @ B
+        return torch.cat([torch.sin(x), torch.cos(x)], -1)
+
+    def neighbor_feats(self, rel, feats):
+        """rel [P,8,3], feats [P,8,32] -> [P,8,32]"""
+        e = self.embed(rel.reshape(-1, 3), self.B_rel).reshape(rel.shape[0], -1, 20)
+        return self.nb2(F.softplus(self.nb1(torch.cat([e, feats], -1)), beta=100))
+
+    def forward(self, p, c):
+        e = self.embed(p.float(), self.B)
+        h = e
+        for i in range(5):
+            h = F.softplus(self.pts[i](h), beta=100) + self.fc_c[i](c)
+            if i == 2:
+                h = torch.cat([e, h], -1)
+        return torch.sigmoid(self.out(h))
+
+
 class PointOracle(nn.Module):
     def __init__(self, n_surface=5, seed=0):
         super().__init__()
         g = torch.Generator().manual_seed(seed)
         self.geo = GeoDecoder(g)
+        self.col = ColorDecoder(g)
+        self.col_feats = None
+        self.w_color_map, self.w_color_trk, self.use_color_trk = 0.1, 0.5, True
         self.n_surface = n_surface
         self.near_s, self.far_s, self.near_end, self.coef, self.min_nn = 0.98, 1.02, 0.3, 0.1, 2
         self.cloud = None
         self.geo_feats = None
         self.frustum_mask = None
 
-    def set_cloud(self, pos, geo_feats, mask=None):
+    def set_cloud(self, pos, geo_feats, mask=None, col_feats=None):
         self.cloud = pos.clone()
         self.geo_feats = nn.Parameter(geo_feats.clone())
+        if col_feats is not None:
+            self.col_feats = nn.Parameter(col_feats.clone())
         self.frustum_mask = mask if mask is not None else torch.ones(pos.shape[0], 1, dtype=torch.bool)
 
-    def feature_at(self, p, radius, rand_feat):
+    def feature_at(self, p, radius, rand_feat, color=False):
         D, I = exact_knn(self.cloud, p.detach(), 8)
         bound = radius.reshape(-1, 1)**2
         nn_num = (D < bound).sum(-1)
@@ -84,8 +123,11 @@ class PointOracle(nn.Module):
         w = torch.where(Dg > bound, torch.zeros_like(w), w)
         w = torch.where(I < 0, torch.zeros_like(w), w)
         w = F.normalize(w, p=1, dim=1).unsqueeze(-1)
-        feats = self.geo_feats * self.frustum_mask
-        c = (w * feats[I]).sum(1)
+        if color:  # colour feats are NOT frustum-masked (decoder_pointslam.py:493)
+            nf = self.col.neighbor_feats(self.cloud[I] - p[:, None, :], self.col_feats[I])
+        else:
+            nf = (self.geo_feats * self.frustum_mask)[I]
+        c = (w * nf).sum(1)
         c = torch.where(has[:, None], c, rand_feat[None, :].expand_as(c))
         return c, has
 
@@ -102,7 +144,8 @@ class PointOracle(nn.Module):
             z[~nz] = torch.linspace(self.near_end, float(far), steps=S).repeat(int((~nz).sum()), 1)
         return z, nz
 
-    def render(self, rays_o, rays_d, target_d, radius, rand_feat):
+    def render(self, rays_o, rays_d, target_d, radius, rand_feat, stage='geometry',
+               rand_feat_color=None):
         S = self.n_surface
         z, nz = self.sample_z(target_d)
         pts = (rays_o[..., None, :] + rays_d[..., None, :] * z[..., :, None]).reshape(-1, 3)
@@ -120,8 +163,35 @@ class PointOracle(nn.Module):
         tmp = z - depth.unsqueeze(-1)
         var = (w * tmp * tmp).sum(1)
         depth = torch.where(nz, depth, torch.zeros_like(depth))
-        return dict(depth=depth, uncertainty=var, valid_ray_mask=valid_ray, z_vals=z,
-                    rgb=torch.zeros(rays_o.shape[0], 3))
+        rgb = torch.zeros(rays_o.shape[0], 3)
+        if stage == 'color':
+            cc, _ = self.feature_at(pts, r, rand_feat_color if rand_feat_color is not None
+                                    else torch.zeros(32), color=True)
+            rgb = (w[..., None] * self.col(pts, cc).reshape(-1, S, 3)).sum(-2) / wsum
+        return dict(depth=depth, uncertainty=var, valid_ray_mask=valid_ray, z_vals=z, rgb=rgb,
+                    stage=stage)
+
+    def loss_dict(self, out, target_d, target_s, is_mapping, handle_dynamic=True):
+        """get_loss_dict (conv_onet_pointslam.py:144-195) incl. the colour term."""
+        td = target_d.squeeze()
+        depth, unc = out['depth'], out['uncertainty']
+        d = {}
+        if not is_mapping:
+            unc = unc.detach()
+            nan_mask = (~torch.isnan(depth)) & (~torch.isnan(unc))
+            tmp = torch.abs(td - depth) / torch.sqrt(unc + 1e-10) if handle_dynamic \
+                else torch.abs(td - depth)
+            mask = (tmp < 10 * tmp.median()) & (td > 0) & nan_mask
+            d['geo_loss'] = torch.clamp(torch.abs(td - depth) / torch.sqrt(unc + 1e-10),
+                                        min=0.0, max=1e3)[mask].sum()
+            if self.use_color_trk:
+                d['rgb_loss'] = self.w_color_trk * torch.abs(target_s - out['rgb'])[mask].sum()
+            return d
+        m = (td > 0) & out['valid_ray_mask'] & (~torch.isnan(depth))
+        d['geo_loss'] = torch.abs(td[m] - depth[m]).sum()
+        if out['stage'] == 'color':
+            d['rgb_loss'] = self.w_color_map * torch.abs(target_s[m] - out['rgb'][m]).sum()
+        return d
 
     def loss(self, out, target_d, is_mapping, handle_dynamic=True):
         td = target_d.squeeze()

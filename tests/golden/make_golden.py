@@ -153,11 +153,19 @@ def pointslam(R0=300, R=80, seed=11):
                           batch_dynamic_r_grad=e))
     npc = ref.neural_point_cloud
     gd = ref.decoder.geo_decoder
+    cd = ref.decoder.color_decoder
     with torch.no_grad():
         gd.embedder._B.mul_(0.05)
         for lin in list(gd.fc_c) + list(gd.pts_linears) + [gd.output_linear]:
             lin.bias.copy_(torch.randn(lin.bias.shape, generator=g) * 0.1)
         npc.geo_feats.mul_(5.0)
+        # colour decoder: moderate sin() arguments, non-zero biases, wider activations so the
+        # softplus(beta=100) kinks are exercised
+        cd.embedder._B.mul_(0.05)
+        cd.embedder_rel_pos._B.mul_(0.3)
+        for lin in list(cd.pts_linears) + [cd.output_linear]:
+            lin.bias.copy_(torch.randn(lin.bias.shape, generator=g) * 0.05)
+        npc.col_feats.mul_(5.0)
     rays_o = (torch.randn(R, 3, generator=g) * 0.01).requires_grad_(True)
     rays_d = rd0[:R].clone().requires_grad_(True)
     td = (d0[:R] + torch.randn(R, generator=g) * 0.01).reshape(-1, 1)
@@ -170,11 +178,18 @@ def pointslam(R0=300, R=80, seed=11):
                 target_d=td.numpy(), radius=radius.numpy())
     for k, v in gd.state_dict().items():
         blob['dec.' + k] = v.numpy().copy()
+    for k, v in cd.state_dict().items():
+        blob['cdec.' + k] = v.numpy().copy()
+    blob['cdec.embedder._B'] = cd.embedder._B.numpy().copy()  # plain attribute, not in state_dict
+    blob['col_feats'] = npc.col_feats.detach().numpy().copy()
+    target_s = torch.rand(R, 3, generator=g)
+    blob['target_s'] = target_s.numpy()
     for tag, is_mapping in (('map', True), ('trk', False)):
         for t in [rays_o, rays_d, npc.geo_feats] + list(gd.parameters()):
             t.grad = None
         inp = dict(rays_o=rays_o, rays_d=rays_d, target_d=td, target_s=torch.zeros(R, 3),
                    stage='geometry', batch_dynamic_r=radius)
+        torch.manual_seed(777)  # the decoders' N(0, 0.01) features (Q6) = the draws below
         out = ref(inp)
         ld = ref.get_loss_dict(out, inp, is_mapping)
         ld['geo_loss'].backward()
@@ -185,6 +200,30 @@ def pointslam(R0=300, R=80, seed=11):
         blob[tag + '.d_geo_feats'] = npc.geo_feats.grad.numpy().copy()
         blob[tag + '.d_rays_o'] = rays_o.grad.numpy().copy()
         blob[tag + '.d_rays_d'] = rays_d.grad.numpy().copy()
+    torch.manual_seed(777)  # geometry decoder draws first, then the colour decoder
+    blob['rand_feat'] = torch.zeros(32).normal_(mean=0, std=0.01).numpy()
+    blob['rand_feat_color'] = torch.zeros(32).normal_(mean=0, std=0.01).numpy()
+    # stage 'color'
+    for tag, is_mapping in (('cmap', True), ('ctrk', False)):
+        ps = [rays_o, rays_d, npc.geo_feats, npc.col_feats] + list(cd.parameters())
+        for t in ps:
+            t.grad = None
+        inp = dict(rays_o=rays_o, rays_d=rays_d, target_d=td, target_s=target_s, stage='color',
+                   batch_dynamic_r=radius)
+        torch.manual_seed(777)
+        out = ref(inp)
+        ld = ref.get_loss_dict(out, inp, is_mapping)
+        sum(ld.values()).backward()
+        blob[tag + '.depth'] = out['depth'].detach().numpy()
+        blob[tag + '.rgb'] = out['rgb'].detach().numpy()
+        blob[tag + '.losses'] = np.array([ld['geo_loss'].item(), ld['rgb_loss'].item()],
+                                         np.float32)
+        blob[tag + '.d_geo_feats'] = npc.geo_feats.grad.numpy().copy()
+        blob[tag + '.d_col_feats'] = npc.col_feats.grad.numpy().copy()
+        blob[tag + '.d_rays_o'] = rays_o.grad.numpy().copy()
+        blob[tag + '.d_rays_d'] = rays_d.grad.numpy().copy()
+        for k, v in cd.named_parameters():
+            blob[tag + '.d_cdec.' + k] = v.grad.numpy().copy()
     np.savez_compressed(os.path.join(HERE, 'pointslam_geo_step.npz'), **blob)
     print('wrote pointslam_geo_step.npz', npc.pts_num(), 'points')
 

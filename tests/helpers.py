@@ -165,7 +165,20 @@ def pointslam_from_golden(g, kind, device=None):
                 d.pts[i].bias.copy_(t(pre + f'pts_linears.{i}.bias'))
             d.out.weight.copy_(t(pre + 'output_linear.weight'))
             d.out.bias.copy_(t(pre + 'output_linear.bias'))
-        obj.set_cloud(t('cloud_pos'), t('geo_feats'))
+            c, cp = obj.col, 'cdec.'
+            c.B.copy_(t(cp + 'embedder._B'))
+            c.B_rel.copy_(t(cp + 'embedder_rel_pos._B'))
+            for i in range(5):
+                c.fc_c[i].weight.copy_(t(cp + f'fc_c.{i}.weight'))
+                c.fc_c[i].bias.copy_(t(cp + f'fc_c.{i}.bias'))
+                c.pts[i].weight.copy_(t(cp + f'pts_linears.{i}.weight'))
+                c.pts[i].bias.copy_(t(cp + f'pts_linears.{i}.bias'))
+            for name, lin in (('linear1', c.nb1), ('linear2', c.nb2)):
+                lin.weight.copy_(t(cp + f'mlp_col_neighbor.{name}.weight'))
+                lin.bias.copy_(t(cp + f'mlp_col_neighbor.{name}.bias'))
+            c.out.weight.copy_(t(cp + 'output_linear.weight'))
+            c.out.bias.copy_(t(cp + 'output_linear.bias'))
+        obj.set_cloud(t('cloud_pos'), t('geo_feats'), col_feats=t('col_feats'))
         return obj
     from xrdslam_b200.camera import Camera
     from xrdslam_b200.conv_onet_pointslam import ConvOnet2Config
@@ -175,7 +188,25 @@ def pointslam_from_golden(g, kind, device=None):
     own = obj.decoder.geo_decoder.state_dict().keys()
     sd = {k[len(pre):]: t(k) for k in g if k.startswith(pre) and k[len(pre):] in own}
     obj.decoder.geo_decoder.load_state_dict(sd)
+    csd = {k[len('cdec.'):]: t(k) for k in g if k.startswith('cdec.') and k != 'cdec.embedder._B'}
+    obj.decoder.color_decoder.load_state_dict(csd)  # the reference MLP_color's own keys
+    obj.decoder.color_decoder.embedder._B.copy_(t('cdec.embedder._B'))
     obj.to(device)
     npc = obj.model_update(device)
-    npc.set_cloud(t('cloud_pos'), t('geo_feats'), torch.zeros(g['cloud_pos'].shape[0], 32))
+    npc.set_cloud(t('cloud_pos'), t('geo_feats'), t('col_feats'))
     return obj
+
+
+# oracle ColorDecoder parameter name -> reference MLP_color parameter name
+def oracle_cdec_grads(ora):
+    c = ora.col
+    out = {'embedder_rel_pos._B': c.B_rel.grad}
+    for i in range(5):
+        out[f'fc_c.{i}.weight'], out[f'fc_c.{i}.bias'] = c.fc_c[i].weight.grad, c.fc_c[i].bias.grad
+        out[f'pts_linears.{i}.weight'] = c.pts[i].weight.grad
+        out[f'pts_linears.{i}.bias'] = c.pts[i].bias.grad
+    for name, lin in (('linear1', c.nb1), ('linear2', c.nb2)):
+        out[f'mlp_col_neighbor.{name}.weight'] = lin.weight.grad
+        out[f'mlp_col_neighbor.{name}.bias'] = lin.bias.grad
+    out['output_linear.weight'], out['output_linear.bias'] = c.out.weight.grad, c.out.bias.grad
+    return out

@@ -257,7 +257,7 @@ def test_pointslam_oracle_matches_golden_reference_vectors(tag, is_mapping):
     ro = torch.from_numpy(g['rays_o']).requires_grad_(True)
     rd = torch.from_numpy(g['rays_d']).requires_grad_(True)
     td = torch.from_numpy(g['target_d'])
-    out = ora.render(ro, rd, td, torch.from_numpy(g['radius']), torch.zeros(32))
+    out = ora.render(ro, rd, td, torch.from_numpy(g['radius']), torch.from_numpy(g['rand_feat']))
     loss = ora.loss(out, td, is_mapping)
     loss.backward()
     assert torch.equal(out['valid_ray_mask'], torch.from_numpy(g[tag + '.valid']))
@@ -276,3 +276,30 @@ def test_exact_knn_sentinels_and_ties():
     D, I = exact_knn(cloud, torch.zeros(1, 3), 8)
     assert I[0].tolist() == [0, 1, 2, -1, -1, -1, -1, -1]  # tie 1 vs 2 -> lower id first
     assert D[0, 3:].eq(FLT_MAX).all() and D[0, :3].tolist() == [0.0, 1.0, 1.0]
+
+
+@pytest.mark.parametrize('tag,is_mapping', [('cmap', True), ('ctrk', False)])
+def test_pointslam_oracle_color_stage_matches_golden(tag, is_mapping):
+    """Stage 'color' of oracle/pointslam.py vs the reference ConvOnet2 (MLP_color,
+    MLP_col_neighbor, colour compositing + loss) incl. every colour-decoder gradient."""
+    from helpers import (load_golden_pointslam, max_abs, oracle_cdec_grads,
+                         pointslam_from_golden, rel_err)
+    g = load_golden_pointslam()
+    ora = pointslam_from_golden(g, 'oracle')
+    ro = torch.from_numpy(g['rays_o']).requires_grad_(True)
+    rd = torch.from_numpy(g['rays_d']).requires_grad_(True)
+    td, ts = torch.from_numpy(g['target_d']), torch.from_numpy(g['target_s'])
+    out = ora.render(ro, rd, td, torch.from_numpy(g['radius']), torch.from_numpy(g['rand_feat']),
+                     'color', torch.from_numpy(g['rand_feat_color']))
+    ld = ora.loss_dict(out, td, ts, is_mapping)
+    sum(ld.values()).backward()
+    assert max_abs(out['depth'], g[tag + '.depth']) < 1e-6
+    assert max_abs(out['rgb'], g[tag + '.rgb']) < 1e-5
+    assert abs(float(ld['geo_loss'].detach()) - float(g[tag + '.losses'][0])) < 1e-5 * max(1, float(g[tag + '.losses'][0]))
+    assert abs(float(ld['rgb_loss'].detach()) - float(g[tag + '.losses'][1])) < 1e-4 * max(1, float(g[tag + '.losses'][1]))
+    assert rel_err(ora.geo_feats.grad, g[tag + '.d_geo_feats']) < 1e-4
+    assert rel_err(ora.col_feats.grad, g[tag + '.d_col_feats']) < 1e-4
+    assert rel_err(ro.grad, g[tag + '.d_rays_o']) < 1e-3
+    assert rel_err(rd.grad, g[tag + '.d_rays_d']) < 1e-3
+    for k, v in oracle_cdec_grads(ora).items():
+        assert rel_err(v, g[tag + '.d_cdec.' + k]) < 1e-3, k

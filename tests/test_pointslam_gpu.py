@@ -71,17 +71,24 @@ def test_add_neural_points_matches_reference(cuda_dev):
                                  dynamic_radius=torch.full((rd.shape[0],), 0.04)) == 0
 
 
-def _run(model, g, is_mapping, dev, grads=True):
+def _run(model, g, is_mapping, dev, grads=True, stage='geometry'):
     ro = torch.from_numpy(g['rays_o']).to(dev).requires_grad_(grads)
     rd = torch.from_numpy(g['rays_d']).to(dev).requires_grad_(grads)
+    ts = torch.from_numpy(g['target_s']).to(dev) if 'target_s' in g and stage == 'color' \
+        else torch.zeros(ro.shape[0], 3, device=dev)
     inp = dict(rays_o=ro, rays_d=rd, target_d=torch.from_numpy(g['target_d']).to(dev),
-               target_s=torch.zeros(ro.shape[0], 3, device=dev), stage='geometry',
+               target_s=ts, stage=stage,
                batch_dynamic_r=torch.from_numpy(g['radius']).to(dev), is_mapping=is_mapping)
+    for k in ('rand_feat', 'rand_feat_color'):
+        if k in g:
+            inp[k] = torch.as_tensor(g[k]).to(dev)
     out = model(inp)
     ld = model.get_loss_dict(out, inp, is_mapping)
     if grads:
-        model.neural_point_cloud.geo_feats.grad = None
-        ld['geo_loss'].backward()
+        npc = model.neural_point_cloud
+        for t in [npc.geo_feats, npc.col_feats] + list(model.decoder.parameters()):
+            t.grad = None
+        (sum(ld.values()) if stage == 'color' else ld['geo_loss']).backward()
     return out, ld, ro, rd
 
 
@@ -154,9 +161,80 @@ def test_pointslam_step_vs_oracle(cuda_dev, is_mapping):
 
 
 @pytest.mark.gpu
-def test_pointslam_color_stage_fails_loudly(cuda_dev):
+@pytest.mark.parametrize('tag,is_mapping', [('cmap', True), ('ctrk', False)])
+def test_pointslam_color_golden(cuda_dev, tag, is_mapping):
+    """Stage 'color' against the reference ConvOnet2's outputs, losses and every gradient
+    (geo/col features, rays, all colour-decoder tensors).  fp32 SIMT GEMMs; the softplus
+    (beta = 100) trunk amplifies rounding differences ~10x relative to the geometry stage."""
     g = load_golden_pointslam()
     model = pointslam_from_golden(g, 'b200', cuda_dev)
-    with pytest.raises(NotImplementedError):
-        model._launch('color', True, *([torch.zeros(4, 3, device=cuda_dev)] * 3),
-                      torch.ones(4, device=cuda_dev), torch.ones(4, device=cuda_dev), None, False)
+    out, ld, ro, rd = _run(model, g, is_mapping, cuda_dev, stage='color')
+    assert max_abs(out['depth'], g[tag + '.depth']) < 2e-5
+    assert max_abs(out['rgb'], g[tag + '.rgb']) < 2e-5
+    for i, k in enumerate(('geo_loss', 'rgb_loss')):
+        ref = float(g[tag + '.losses'][i])
+        assert abs(float(ld[k].detach()) - ref) < 2e-4 * max(1, abs(ref)), k
+    npc = model.neural_point_cloud
+    assert rel_err(npc.geo_feats.grad, g[tag + '.d_geo_feats']) < 1e-3
+    assert rel_err(npc.col_feats.grad, g[tag + '.d_col_feats']) < 1e-3
+    assert rel_err(ro.grad, g[tag + '.d_rays_o']) < 2e-3
+    assert rel_err(rd.grad, g[tag + '.d_rays_d']) < 2e-3
+    for k, v in model.decoder.color_decoder.named_parameters():
+        assert rel_err(v.grad, g[tag + '.d_cdec.' + k]) < 2e-3, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('is_mapping', [True, False])
+def test_pointslam_color_step_vs_oracle(cuda_dev, is_mapping):
+    """Seeded case with R*S not a multiple of 4 (padded columns) and rays without
+    neighbours; every gradient against oracle/pointslam.py."""
+    from helpers import oracle_cdec_grads
+    g = dict(load_golden_pointslam())
+    R = 61  # 305 points: exercises the Pp != P padding of the neighbour GEMMs
+    for k in ('rays_o', 'rays_d', 'target_d', 'radius', 'target_s'):
+        g[k] = g[k][:R].copy()
+    g['target_d'][3] = 0  # a zero-depth ray sampled far from the cloud
+    g['rays_d'][7] = -g['rays_d'][7]  # a ray that looks away from every point
+    model = pointslam_from_golden(g, 'b200', cuda_dev)
+    ora = pointslam_from_golden(g, 'oracle')
+    out, ld, ro, rd = _run(model, g, is_mapping, cuda_dev, stage='color')
+    ro_o = torch.from_numpy(g['rays_o']).requires_grad_(True)
+    rd_o = torch.from_numpy(g['rays_d']).requires_grad_(True)
+    td, ts = torch.from_numpy(g['target_d']), torch.from_numpy(g['target_s'])
+    out_o = ora.render(ro_o, rd_o, td, torch.from_numpy(g['radius']),
+                       torch.from_numpy(g['rand_feat']), 'color',
+                       torch.from_numpy(g['rand_feat_color']))
+    ld_o = ora.loss_dict(out_o, td, ts, is_mapping)
+    sum(ld_o.values()).backward()
+    assert torch.equal(out['valid_ray_mask'].cpu(), out_o['valid_ray_mask'])
+    assert not out_o['valid_ray_mask'].all()
+    assert max_abs(out['depth'], out_o['depth']) < 2e-5
+    assert max_abs(out['rgb'], out_o['rgb']) < 2e-5
+    for k in ld_o:
+        ref = float(ld_o[k].detach())
+        assert abs(float(ld[k].detach()) - ref) < 2e-4 * max(1, abs(ref)), k
+    npc = model.neural_point_cloud
+    assert rel_err(npc.geo_feats.grad, ora.geo_feats.grad) < 1e-3
+    assert rel_err(npc.col_feats.grad, ora.col_feats.grad) < 1e-3
+    assert rel_err(ro.grad, ro_o.grad) < 2e-3
+    assert rel_err(rd.grad, rd_o.grad) < 2e-3
+    og = oracle_cdec_grads(ora)
+    for k, v in model.decoder.color_decoder.named_parameters():
+        assert rel_err(v.grad, og[k]) < 2e-3, k
+
+
+@pytest.mark.gpu
+def test_pointslam_color_forward_only_matches_fused(cuda_dev):
+    """render_img path (no grad) returns the same colours/depths as the fused step."""
+    g = load_golden_pointslam()
+    model = pointslam_from_golden(g, 'b200', cuda_dev)
+    out, _, _, _ = _run(model, g, True, cuda_dev, stage='color')
+    with torch.no_grad():
+        inp = dict(rays_o=torch.from_numpy(g['rays_o']).to(cuda_dev),
+                   rays_d=torch.from_numpy(g['rays_d']).to(cuda_dev),
+                   target_d=torch.from_numpy(g['target_d']).to(cuda_dev), target_s=None,
+                   stage='color', batch_dynamic_r=torch.from_numpy(g['radius']).to(cuda_dev),
+                   rand_feat=torch.from_numpy(g['rand_feat']).to(cuda_dev),
+                   rand_feat_color=torch.from_numpy(g['rand_feat_color']).to(cuda_dev))
+        o2 = model(inp)
+    assert torch.equal(o2['rgb'], out['rgb']) and torch.equal(o2['depth'], out['depth'])

@@ -167,11 +167,23 @@ class XrdPointCfg(C.Structure):
                 ('near_end', C.c_float), ('sigmoid_coef', C.c_float), ('min_nn_num', C.c_int),
                 ('w_color', C.c_float), ('handle_dynamic', C.c_int),
                 ('use_color_in_tracking', C.c_int), ('t_surface', vp), ('far', vp),
-                ('radius_query', vp), ('rand_feat', vp)]
+                ('radius_query', vp), ('rand_feat', vp), ('rand_feat_color', vp)]
 
 
 class XrdPointFeats(C.Structure):
-    _fields_ = [('geo_feats', vp), ('frustum_mask', vp)]
+    _fields_ = [('geo_feats', vp), ('frustum_mask', vp), ('col_feats', vp)]
+
+
+class XrdPointColorDecoder(C.Structure):
+    _fields_ = [('B', vp), ('B_rel', vp), ('nb_w1', vp), ('nb_b1', vp), ('nb_w2', vp),
+                ('nb_b2', vp), ('w', vp * 5), ('b', vp * 5), ('wc', vp * 5), ('bc', vp * 5),
+                ('wo', vp), ('bo', vp)]
+
+
+class XrdPointColorDecoderGrads(C.Structure):
+    _fields_ = [('B_rel', vp), ('nb_w1', vp), ('nb_b1', vp), ('nb_w2', vp), ('nb_b2', vp),
+                ('w', vp * 5), ('b', vp * 5), ('wc', vp * 5), ('bc', vp * 5), ('wo', vp),
+                ('bo', vp)]
 
 
 class XrdPointOut(C.Structure):
@@ -180,7 +192,8 @@ class XrdPointOut(C.Structure):
 
 
 class XrdPointGrads(C.Structure):
-    _fields_ = [('d_geo_feats', vp), ('d_rays_o', vp), ('d_rays_d', vp)]
+    _fields_ = [('d_geo_feats', vp), ('d_rays_o', vp), ('d_rays_d', vp), ('d_col_feats', vp),
+                ('color', C.POINTER(XrdPointColorDecoderGrads))]
 
 
 _lib = None
@@ -238,11 +251,11 @@ SYMBOLS = {
         C.POINTER(XrdVoxOut), C.POINTER(XrdVoxGrads), vp, C.c_size_t, vp]),
     'xrd_pointslam_knn_query': (C.c_int, [C.POINTER(XrdPointIndex), vp, vp, C.c_int, C.c_int,
                                           vp, vp, vp, vp]),
-    'xrd_pointslam_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    'xrd_pointslam_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     'xrd_pointslam_step': (C.c_int, [
         C.POINTER(XrdRays), C.POINTER(XrdPointIndex), C.POINTER(XrdPointFeats),
-        C.POINTER(XrdNiceDecoder), C.POINTER(XrdPointCfg), C.POINTER(XrdPointOut),
-        C.POINTER(XrdPointGrads), vp, C.c_size_t, vp]),
+        C.POINTER(XrdNiceDecoder), C.POINTER(XrdPointColorDecoder), C.POINTER(XrdPointCfg),
+        C.POINTER(XrdPointOut), C.POINTER(XrdPointGrads), vp, C.c_size_t, vp]),
     'xrd_nice_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     'xrd_nice_step': (C.c_int, [
         C.POINTER(XrdRays), C.POINTER(XrdNiceGrid), C.POINTER(XrdNiceDecoder),

@@ -1,0 +1,124 @@
+// Generic fp32 SIMT GEMM on [feature][point] activations (points contiguous), used by the
+// wide per-point MLPs whose layers are real GEMMs (Point-SLAM colour decoder: 128-wide trunk
+// over R*5 points and the per-neighbour MLP over 8x as many columns):
+//   C[m][n] = epi( sum_k A(m,k) * B[k][n] ),   A(m,k) = transA ? A[k*lda+m] : A[m*lda+k]
+//   epi(v)  = act(v + bias[m]);  act_out[m][n] = epi(v) (optional);  + addend[m][n] (optional);
+//             accumulate: C += that.
+// 64 x 128 tile, BK = 16, 256 threads, 4 x 8 register tile per thread, fp32 FMA (exact-order
+// independent of the tile position, so results do not depend on how points are batched).
+#pragma once
+#include "common.cuh"
+
+namespace xrd {
+
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SOFTPLUS100 = 2, ACT_SIGMOID = 3 };
+
+struct GemmArgs {
+  int M, N, K;
+  const float* A; int lda; int transA;
+  const float* B; int ldb;
+  float* C; int ldc;
+  const float* bias;
+  int act;
+  const float* addend; int ldadd;
+  float* act_out; int ldact;
+  int accumulate;
+};
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  switch (act) {
+    case ACT_RELU: return fmaxf(v, 0.f);
+    case ACT_SOFTPLUS100: return (v * 100.f > 20.f) ? v : log1pf(expf(v * 100.f)) / 100.f;  // nn.Softplus(beta=100)
+    case ACT_SIGMOID: return sigmoidf_acc(v);
+    default: return v;
+  }
+}
+
+constexpr int GBM = 64, GBN = 128, GBK = 16;
+
+static __global__ void __launch_bounds__(256) k_gemm(const GemmArgs G) {
+  __shared__ __align__(16) float As[GBK][GBM + 4];
+  __shared__ __align__(16) float Bs[GBK][GBN + 4];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  const bool b_vec = ((G.ldb & 3) == 0) && ((((uintptr_t)G.B) & 15) == 0);
+  for (int k0 = 0; k0 < G.K; k0 += GBK) {
+    // A tile: 64 x 16
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = tid + q * 256;
+      int m, k;
+      if (G.transA) { k = e >> 6; m = e & 63; } else { m = e >> 4; k = e & 15; }
+      const int gm = m0 + m, gk = k0 + k;
+      float v = 0.f;
+      if (gm < G.M && gk < G.K) v = G.transA ? G.A[(size_t)gk * G.lda + gm] : G.A[(size_t)gm * G.lda + gk];
+      As[k][m] = v;
+    }
+    // B tile: 16 x 128 (two float4 per thread)
+    {
+      const int k = tid >> 4, c = (tid & 15) * 8;
+      const int gk = k0 + k;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int gn = n0 + c + 4 * h;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gk < G.K) {
+          const float* src = G.B + (size_t)gk * G.ldb + gn;
+          if (b_vec && gn + 3 < G.N) {
+            v = *reinterpret_cast<const float4*>(src);
+          } else {
+            if (gn < G.N) v.x = src[0];
+            if (gn + 1 < G.N) v.y = src[1];
+            if (gn + 2 < G.N) v.z = src[2];
+            if (gn + 3 < G.N) v.w = src[3];
+          }
+        }
+        *reinterpret_cast<float4*>(&Bs[k][c + 4 * h]) = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GBK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= G.M) continue;
+    const float bias = G.bias ? G.bias[gm] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int gn = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (gn >= G.N) continue;
+      float v = act_apply(acc[i][j] + bias, G.act);
+      if (G.act_out) G.act_out[(size_t)gm * G.ldact + gn] = v;
+      if (G.addend) v += G.addend[(size_t)gm * G.ldadd + gn];
+      float* c = G.C + (size_t)gm * G.ldc + gn;
+      *c = G.accumulate ? (*c + v) : v;
+    }
+  }
+}
+
+static inline cudaError_t launch_gemm(const GemmArgs& G, cudaStream_t stream) {
+  if (G.M <= 0 || G.N <= 0) return cudaSuccess;
+  dim3 grid((G.N + GBN - 1) / GBN, (G.M + GBM - 1) / GBM);
+  k_gemm<<<grid, 256, 0, stream>>>(G);
+  return cudaGetLastError();
+}
+
+}  // namespace xrd

@@ -1,4 +1,4 @@
-// Point-SLAM render-and-optimise step, stage 'geometry' (sm_100a): exact hash-grid kNN, inverse-
+// Point-SLAM render-and-optimise step, stages 'geometry' and 'color' (sm_100a): exact hash-grid kNN, inverse-
 // distance feature interpolation over the neural point cloud, Fourier MLP, normalised occupancy
 // compositing, losses and backward.
 //
@@ -15,6 +15,7 @@
 
 #define XRD_NICE_KERNELS_ONLY
 #include "nice.cu"
+#include "gemm.cuh"
 
 namespace xrd {
 namespace point {
@@ -240,6 +241,12 @@ struct RayP {
   float* tmp;                     // [R]
   float* losses;
   float* d_occ;                   // [P]
+  // stage colour
+  int stage, Pp, use_color_trk;
+  float w_color;
+  const float* rgb3;              // [3][Pp] per-sample sigmoid colour
+  float* grgb;                    // [R][3] d loss / d rgb_map
+  float* d_raw3;                  // [3][Pp] d loss / d (pre-sigmoid colour)
 };
 
 __global__ void __launch_bounds__(128) k_sample_z(const RayP P) {
@@ -289,15 +296,33 @@ __global__ void __launch_bounds__(128) k_composite_fwd(const RayP P) {
   const bool nz = P.target_d[r] > 0.f;
   P.o_depth[r] = nz ? depth : 0.f;   // depth[~gt_non_zero_mask] = 0
   P.o_var[r] = var;
-  P.o_rgb[r * 3] = P.o_rgb[r * 3 + 1] = P.o_rgb[r * 3 + 2] = 0.f;
+  for (int c = 0; c < 3; ++c) {
+    float acc = 0.f;
+    if (P.stage == 1)
+      for (int k = 0; k < S; ++k) acc = fmaf(w[k], P.rgb3[(size_t)c * P.Pp + r * S + k], acc);
+    P.o_rgb[r * 3 + c] = acc / wsum;
+  }
   P.o_valid[r] = !(nvalid < P.min_valid);
 }
 
 __global__ void __launch_bounds__(1024) k_loss(const RayP P) {
-  __shared__ double red[32];
+  __shared__ double red[32], redc[32];
   __shared__ float s_med;
   const int tid = threadIdx.x;
-  double ld = 0.0;
+  double ld = 0.0, lc = 0.0;
+  const bool col = P.is_mapping ? (P.stage == 1) : (P.use_color_trk != 0);
+  auto colour = [&](int r, bool m) {  // w_color * sum |target - colour| over the masked rays
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float g = 0.f;
+      if (m && col && P.target_s) {
+        const float t = P.target_s[r * 3 + c], v = P.o_rgb[r * 3 + c];
+        lc += (double)fabsf(t - v);
+        g = P.w_color * ((v > t) ? 1.f : ((v < t) ? -1.f : 0.f));
+      }
+      P.grgb[r * 3 + c] = g;
+    }
+  };
   if (P.is_mapping) {
     for (int r = tid; r < P.R; r += blockDim.x) {
       const float D = P.target_d[r], d = P.o_depth[r];
@@ -305,6 +330,7 @@ __global__ void __launch_bounds__(1024) k_loss(const RayP P) {
       float g = 0.f;
       if (m) { ld += (double)fabsf(D - d); g = (d > D) ? 1.f : ((d < D) ? -1.f : 0.f); }
       P.gd[r] = g;
+      colour(r, m);
     }
   } else {
     for (int r = tid; r < P.R; r += blockDim.x) {
@@ -331,17 +357,21 @@ __global__ void __launch_bounds__(1024) k_loss(const RayP P) {
         if (t < 1e3f) g = ((d > D) ? inv : ((d < D) ? -inv : 0.f));
       }
       P.gd[r] = g;
+      colour(r, m);
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ld += __shfl_xor_sync(0xffffffffu, ld, o);
-  if ((tid & 31) == 0) red[tid >> 5] = ld;
+  for (int o = 16; o > 0; o >>= 1) {
+    ld += __shfl_xor_sync(0xffffffffu, ld, o);
+    lc += __shfl_xor_sync(0xffffffffu, lc, o);
+  }
+  if ((tid & 31) == 0) { red[tid >> 5] = ld; redc[tid >> 5] = lc; }
   __syncthreads();
   if (tid == 0) {
-    double a = 0.0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) a += red[i];
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += red[i]; b += redc[i]; }
     P.losses[0] = (float)a;
-    P.losses[1] = 0.f;
+    P.losses[1] = P.w_color * (float)b;
   }
 }
 
@@ -364,11 +394,20 @@ __global__ void __launch_bounds__(128) k_composite_bwd(const RayP P) {
     nd = fmaf(w[k], P.z[p], nd);
   }
   const float wsum = ws + 1e-10f, depth = nd / wsum;
-  // depth = sum w z / wsum -> dL/dw_k = gd (z_k - depth) / wsum
+  float gc[3] = {0.f, 0.f, 0.f}, cmap[3] = {0.f, 0.f, 0.f};
+  if (P.stage == 1)
+    for (int c = 0; c < 3; ++c) { gc[c] = P.grgb[r * 3 + c]; cmap[c] = P.o_rgb[r * 3 + c]; }
+  // depth = sum w z / wsum, rgb = sum w c / wsum -> dL/dw_k = [gd (z_k - depth) + g.(c_k - rgb)] / wsum
   float suffix = 0.f;
   for (int k = S - 1; k >= 0; --k) {
     const int p = r * S + k;
-    const float q = gd * (P.z[p] - depth) / wsum;
+    float q = gd * (P.z[p] - depth) / wsum;
+    if (P.stage == 1)
+      for (int c = 0; c < 3; ++c) {
+        const float v = P.rgb3[(size_t)c * P.Pp + p];
+        q += gc[c] * (v - cmap[c]) / wsum;
+        P.d_raw3[(size_t)c * P.Pp + p] = gc[c] * w[k] / wsum * v * (1.f - v);
+      }
     const float da = q * Tt[k] - suffix / (1.f - alpha[k] + 1e-10f);
     suffix += q * w[k];
     // raw[~point_mask, -1] = -100 under no_grad: no gradient for samples without neighbours
@@ -392,6 +431,8 @@ __global__ void __launch_bounds__(128) k_rayreduce_f(int R, int S, int P, const 
     if (d_d) d_d[r * 3 + d] = a[3 + d];
   }
 }
+
+#include "pointslam_color.cuh"
 
 }  // namespace point
 }  // namespace xrd
@@ -417,44 +458,197 @@ extern "C" int xrd_pointslam_knn_query(const XrdPointIndex* index, const float* 
 }
 
 namespace {
-struct PWs { size_t z, D, I, nn, c, has, occ, d_occ, dc, dp, gd, tmp, masks, total; };
-PWs pws(int R, int S, int with_grads) {
-  PWs L;
+struct PWs {
+  size_t z, D, I, nn, c, has, occ, d_occ, dc, dp, gd, tmp, masks;
+  // stage colour ([rows][Pp] / [rows][8 Pp] float arrays)
+  size_t wn, Xn, Hn, Fn, cc, X3, act, H, T, rgb3, d_raw3, g0, g1, gp, dX3, dcc, dFn, dHn, dXn, grgb;
+  size_t total;
+  int Pp;
+};
+PWs pws(int R, int S, int stage, int with_grads) {
+  PWs L{};
   const size_t P = (size_t)R * S;
+  const size_t Pp = (P + 3) / 4 * 4, Np = 8 * Pp;
+  L.Pp = (int)Pp;
   size_t q = 0;
   auto take = [&](size_t b) { size_t o = q; q += align_up(b, 256); return o; };
   L.z = take(P * 4); L.D = take(P * KNN * 4); L.I = take(P * KNN * 4); L.nn = take(P * 4);
   L.c = take(CD * P * 4); L.has = take(P); L.occ = take(P * 4);
-  L.d_occ = L.dc = L.dp = L.gd = L.tmp = L.masks = 0;
   if (with_grads) {
     L.d_occ = take(P * 4); L.dc = take(CD * P * 4); L.dp = take(3 * P * 4);
     L.gd = take((size_t)R * 4); L.tmp = take((size_t)R * 4); L.masks = take(5 * P * 4);
+    L.grgb = take((size_t)R * 3 * 4);
+  }
+  if (stage == 1) {
+    L.wn = take(8 * Pp * 4); L.Xn = take(CNI * Np * 4); L.Hn = take(CW * Np * 4);
+    L.Fn = take(CD * Np * 4); L.cc = take(CD * Pp * 4); L.X3 = take(CX3 * Pp * 4);
+    L.act = take(5 * CW * Pp * 4); L.H = take(4 * CW * Pp * 4); L.T = take(CW * Pp * 4);
+    L.rgb3 = take(3 * Pp * 4);
+    if (with_grads) {
+      L.d_raw3 = take(3 * Pp * 4); L.g0 = take(CW * Pp * 4); L.g1 = take(CW * Pp * 4);
+      L.gp = take(CW * Pp * 4); L.dX3 = take(CX3 * Pp * 4); L.dcc = take(CD * Pp * 4);
+      L.dFn = take(CD * Np * 4); L.dHn = take(CW * Np * 4); L.dXn = take(CNI * Np * 4);
+    }
   }
   L.total = q;
   return L;
 }
+
+#define XRD_GEMM(...)                                         \
+  do {                                                        \
+    GemmArgs g_ = __VA_ARGS__;                                \
+    XRD_CUDA_TRY(launch_gemm(g_, stream));                    \
+  } while (0)
+
+// ---- stage colour: forward -----------------------------------------------------------------
+int color_forward(const ColorP& C0, const PWs& L, char* ws, int P, cudaStream_t stream) {
+  const XrdPointColorDecoder& d = C0.dec;
+  const int Pp = L.Pp, Np = 8 * Pp;
+  auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+  float *Xn = F(L.Xn), *Hn = F(L.Hn), *Fn = F(L.Fn), *cc = F(L.cc), *X3 = F(L.X3), *T = F(L.T);
+  // only the first P of every Pp-wide slot holds data; the neighbour GEMMs (and their weight
+  // gradients) run over the padded width: pad columns must be zero
+  if (Pp != P) XRD_CUDA_TRY(cudaMemsetAsync(Xn, 0, (size_t)CNI * Np * sizeof(float), stream));
+  k_nb_build<<<(P + 127) / 128, 128, 0, stream>>>(C0);
+  XRD_LAUNCH_CHECK();
+  XRD_GEMM({CW, Np, CNI, d.nb_w1, CNI, 0, Xn, Np, Hn, Np, d.nb_b1, ACT_SOFTPLUS100, nullptr, 0, nullptr, 0, 0});
+  XRD_GEMM({CD, Np, CW, d.nb_w2, CW, 0, Hn, Np, Fn, Np, d.nb_b2, ACT_NONE, nullptr, 0, nullptr, 0, 0});
+  k_nb_reduce<<<(P + 127) / 128, 128, 0, stream>>>(C0);
+  XRD_LAUNCH_CHECK();
+  // trunk: inputs  emb(40) | H0 | H1 | X3 = [emb, H2](168) | H3 ; outputs H0 H1 H2(in X3) H3 H4
+  float* Hs[5] = {F(L.H), F(L.H) + (size_t)CW * Pp, X3 + (size_t)2 * CE * Pp,
+                  F(L.H) + (size_t)2 * CW * Pp, F(L.H) + (size_t)3 * CW * Pp};
+  const float* in[5] = {X3, Hs[0], Hs[1], X3, Hs[3]};
+  const int kin[5] = {2 * CE, CW, CW, CX3, CW};
+  for (int i = 0; i < 5; ++i) {
+    XRD_GEMM({CW, P, CD, d.wc[i], CD, 0, cc, Pp, T, Pp, d.bc[i], ACT_NONE, nullptr, 0, nullptr, 0, 0});
+    XRD_GEMM({CW, P, kin[i], d.w[i], kin[i], 0, in[i], Pp, Hs[i], Pp, d.b[i], ACT_SOFTPLUS100, T, Pp,
+              F(L.act) + (size_t)i * CW * Pp, Pp, 0});
+  }
+  XRD_GEMM({3, P, CW, d.wo, CW, 0, Hs[4], Pp, F(L.rgb3), Pp, d.bo, ACT_SIGMOID, nullptr, 0, nullptr, 0, 0});
+  return XRD_OK;
+}
+
+// ---- stage colour: backward (d_raw3 -> decoder grads, d col_feats, d p) ----------------------
+int color_backward(ColorP C, const PWs& L, char* ws, int P, const XrdPointColorDecoderGrads* G,
+                   cudaStream_t stream) {
+  const XrdPointColorDecoder& d = C.dec;
+  const int Pp = L.Pp, Np = 8 * Pp;
+  auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+  float *Xn = F(L.Xn), *Hn = F(L.Hn), *cc = F(L.cc), *X3 = F(L.X3);
+  float *g0 = F(L.g0), *g1 = F(L.g1), *gp = F(L.gp), *dX3 = F(L.dX3), *dcc = F(L.dcc);
+  float *dFn = F(L.dFn), *dHn = F(L.dHn), *dXn = F(L.dXn), *d_raw3 = F(L.d_raw3);
+  float* Hs[5] = {F(L.H), F(L.H) + (size_t)CW * Pp, X3 + (size_t)2 * CE * Pp,
+                  F(L.H) + (size_t)2 * CW * Pp, F(L.H) + (size_t)3 * CW * Pp};
+  const float* in[5] = {X3, Hs[0], Hs[1], X3, Hs[3]};
+  const int kin[5] = {2 * CE, CW, CW, CX3, CW};
+  DwParams Dw;
+  auto dw_begin = [&](int cols, int ld) { Dw.n_jobs = 0; Dw.P = cols; Dw.Pp = ld; Dw.chunk = 1024; };
+  auto dw_add = [&](const float* a, int nA, const float* b, int nB, float* o, int ldo, float* bias) {
+    // out[j][i] += sum_p b_j[p] a_i[p], rows of b in groups of 32
+    if (!o && !bias) return;
+    for (int c = 0; c < nB; c += 32) {
+      DwJob& J = Dw.jobs[Dw.n_jobs++];
+      J.A = a; J.nA = o ? nA : 0; J.B = b + (size_t)c * Dw.Pp; J.nB = nB - c < 32 ? nB - c : 32;
+      J.mask = nullptr; J.out = o ? o + (size_t)c * ldo : nullptr; J.sj = ldo; J.si = 1;
+      J.bias = bias ? bias + c : nullptr;
+    }
+  };
+  auto dw_run = [&]() -> int {
+    if (Dw.n_jobs == 0) return XRD_OK;
+    if (Dw.n_jobs > DW_MAX_JOBS) return XRD_E_SHAPE;
+    k_dw<<<(Dw.P + Dw.chunk - 1) / Dw.chunk, 256, 0, stream>>>(Dw);
+    XRD_LAUNCH_CHECK();
+    return XRD_OK;
+  };
+  int st;
+  // output layer
+  XRD_GEMM({CW, P, 3, d.wo, CW, 1, d_raw3, Pp, g0, Pp, nullptr, ACT_NONE, nullptr, 0, nullptr, 0, 0});
+  if (G) {
+    dw_begin(P, Pp);
+    dw_add(Hs[4], CW, d_raw3, 3, G->wo, CW, G->bo);
+    if ((st = dw_run()) != XRD_OK) return st;
+  }
+  float* dH[5] = {g1, g0, dX3 + (size_t)2 * CE * Pp, g1, g0};  // where dH_i lives
+  float* dIn[5] = {dX3, g1, g0, dX3, g1};                       // where W_i^T dPre_i goes
+  for (int i = 4; i >= 0; --i) {
+    // fc_c branch: dc += wc_i^T dH_i
+    XRD_GEMM({CD, P, CW, d.wc[i], CD, 1, dH[i], Pp, dcc, Pp, nullptr, ACT_NONE, nullptr, 0, nullptr, 0, i == 4 ? 0 : 1});
+    const size_t n = (size_t)CW * Pp;
+    k_dsoftplus<<<592, 256, 0, stream>>>(n, dH[i], F(L.act) + (size_t)i * CW * Pp, gp);
+    XRD_LAUNCH_CHECK();
+    if (G) {
+      dw_begin(P, Pp);
+      dw_add(cc, CD, dH[i], CW, G->wc[i], CD, G->bc[i]);
+      dw_add(in[i], kin[i], gp, CW, G->w[i], kin[i], G->b[i]);
+      if ((st = dw_run()) != XRD_OK) return st;
+    }
+    if (i > 0) {
+      XRD_GEMM({kin[i], P, CW, d.w[i], kin[i], 1, gp, Pp, dIn[i], Pp, nullptr, ACT_NONE, nullptr, 0, nullptr, 0, 0});
+    } else if (C.need_dp) {  // layer 0: d embedding accumulates onto block 3's share
+      XRD_GEMM({kin[0], P, CW, d.w[0], kin[0], 1, gp, Pp, dX3, Pp, nullptr, ACT_NONE, nullptr, 0, nullptr, 0, 1});
+    }
+  }
+  // neighbour MLP
+  C.dcc = dcc; C.dFn = dFn; C.dXn = dXn; C.dX3 = dX3;
+  C.d_B_rel = G ? G->B_rel : nullptr;
+  if (Pp != P) XRD_CUDA_TRY(cudaMemsetAsync(dFn, 0, (size_t)CD * Np * sizeof(float), stream));
+  k_nb_reduce_bwd<<<(P + 127) / 128, 128, 0, stream>>>(C);
+  XRD_LAUNCH_CHECK();
+  XRD_GEMM({CW, Np, CD, d.nb_w2, CW, 1, dFn, Np, dHn, Np, nullptr, ACT_NONE, nullptr, 0, nullptr, 0, 0});
+  k_dsoftplus<<<1184, 256, 0, stream>>>((size_t)CW * Np, dHn, Hn, dHn);
+  XRD_LAUNCH_CHECK();
+  if (G) {
+    dw_begin(Np, Np);
+    dw_add(Hn, CW, dFn, CD, G->nb_w2, CW, G->nb_b2);
+    dw_add(Xn, CNI, dHn, CW, G->nb_w1, CNI, G->nb_b1);
+    if ((st = dw_run()) != XRD_OK) return st;
+  }
+  XRD_GEMM({CNI, Np, CW, d.nb_w1, CNI, 1, dHn, Np, dXn, Np, nullptr, ACT_NONE, nullptr, 0, nullptr, 0, 0});
+  k_nb_build_bwd<<<(P + 127) / 128, 128, 0, stream>>>(C);
+  XRD_LAUNCH_CHECK();
+  return XRD_OK;
+}
 }  // namespace
 
-extern "C" size_t xrd_pointslam_workspace_bytes(int n_rays, int n_surface, int with_grads) {
-  return pws(n_rays, n_surface, with_grads).total;
+extern "C" size_t xrd_pointslam_workspace_bytes(int n_rays, int n_surface, int stage, int with_grads) {
+  return pws(n_rays, n_surface, stage, with_grads).total;
 }
 
 extern "C" int xrd_pointslam_step(const XrdRays* rays, const XrdPointIndex* index,
                                   const XrdPointFeats* feats, const XrdNiceDecoder* dec,
-                                  const XrdPointCfg* cfg, XrdPointOut* out, XrdPointGrads* grads,
+                                  const XrdPointColorDecoder* cdec, const XrdPointCfg* cfg,
+                                  XrdPointOut* out, XrdPointGrads* grads,
                                   void* workspace, size_t workspace_bytes, void* stream_) {
   if (!rays || !index || !feats || !dec || !cfg || !out || !workspace) return XRD_E_NULL;
   if (!rays->rays_o || !rays->rays_d || !rays->target_d || !feats->geo_feats) return XRD_E_NULL;
   if (!cfg->t_surface || !cfg->far || !cfg->radius_query) return XRD_E_NULL;
   if (!out->rgb || !out->depth || !out->uncertainty || !out->valid_ray_mask) return XRD_E_NULL;
-  if (cfg->stage != 0) return XRD_E_SHAPE;  // stage 'color': next round
+  const int stage = cfg->stage;
+  if (stage != 0 && stage != 1) return XRD_E_SHAPE;
+  if (stage == 1) {
+    if (!cdec || !feats->col_feats) return XRD_E_NULL;
+    const float* const* arrs[4] = {cdec->w, cdec->b, cdec->wc, cdec->bc};
+    for (auto a : arrs) for (int i = 0; i < 5; ++i) if (!a[i]) return XRD_E_NULL;
+    if (!cdec->B || !cdec->B_rel || !cdec->nb_w1 || !cdec->nb_b1 || !cdec->nb_w2 || !cdec->nb_b2 ||
+        !cdec->wo || !cdec->bo)
+      return XRD_E_NULL;
+    if (grads && !rays->target_s) return XRD_E_NULL;
+    if (grads && grads->color) {  // colour-decoder gradients are all-or-nothing
+      const XrdPointColorDecoderGrads* G = grads->color;
+      float* const* ga[4] = {G->w, G->b, G->wc, G->bc};
+      for (auto a : ga) for (int i = 0; i < 5; ++i) if (!a[i]) return XRD_E_NULL;
+      if (!G->B_rel || !G->nb_w1 || !G->nb_b1 || !G->nb_w2 || !G->nb_b2 || !G->wo || !G->bo)
+        return XRD_E_NULL;
+    }
+  }
   if (dec->c_dim != CD || dec->n_out != 1) return XRD_E_SHAPE;
   const int R = rays->n_rays, S = cfg->n_surface;
   if (R <= 0) return XRD_OK;
   if (S < 2 || S > 16) return XRD_E_SHAPE;
   if (grads && !out->losses) return XRD_E_NULL;
   if (grads && !cfg->is_mapping && R > 8192) return XRD_E_SHAPE;
-  const PWs L = pws(R, S, grads != nullptr);
+  const PWs L = pws(R, S, stage, grads != nullptr);
   if (workspace_bytes < L.total) return XRD_E_WORKSPACE;
   cudaStream_t stream = (cudaStream_t)stream_;
   char* ws = reinterpret_cast<char*>(workspace);
@@ -472,6 +666,9 @@ extern "C" int xrd_pointslam_step(const XrdRays* rays, const XrdPointIndex* inde
   Y.o_rgb = out->rgb; Y.o_depth = out->depth; Y.o_var = out->uncertainty; Y.o_valid = out->valid_ray_mask;
   Y.is_mapping = cfg->is_mapping; Y.handle_dynamic = cfg->handle_dynamic;
   Y.gd = nullptr; Y.tmp = nullptr; Y.losses = out->losses; Y.d_occ = nullptr;
+  Y.stage = stage; Y.Pp = L.Pp; Y.use_color_trk = cfg->use_color_in_tracking; Y.w_color = cfg->w_color;
+  Y.rgb3 = stage == 1 ? reinterpret_cast<float*>(ws + L.rgb3) : nullptr;
+  Y.grgb = nullptr; Y.d_raw3 = nullptr;
   k_sample_z<<<(R + 127) / 128, 128, 0, stream>>>(Y);
   XRD_LAUNCH_CHECK();
 
@@ -514,12 +711,24 @@ extern "C" int xrd_pointslam_step(const XrdRays* rays, const XrdPointIndex* inde
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   xrd::nice::k_decoder_fwd<<<gridx, xrd::nice::T, smem, stream>>>(D);
   XRD_LAUNCH_CHECK();
+  ColorP C{};
+  if (stage == 1) {
+    C.K = Q.K; C.Pp = L.Pp; C.min_nn = cfg->min_nn_num; C.col_feats = feats->col_feats;
+    C.rand_feat = cfg->rand_feat_color; C.dec = *cdec;
+    C.wn = reinterpret_cast<float*>(ws + L.wn); C.Xn = reinterpret_cast<float*>(ws + L.Xn);
+    C.Fn = reinterpret_cast<float*>(ws + L.Fn); C.cc = reinterpret_cast<float*>(ws + L.cc);
+    C.X3 = reinterpret_cast<float*>(ws + L.X3); C.has_nb = Q.has_nb;
+    const int st = color_forward(C, L, ws, P, stream);
+    if (st != XRD_OK) return st;
+  }
   k_composite_fwd<<<(R + 127) / 128, 128, 0, stream>>>(Y);
   XRD_LAUNCH_CHECK();
   if (!grads) return XRD_OK;
 
   Y.gd = reinterpret_cast<float*>(ws + L.gd); Y.tmp = reinterpret_cast<float*>(ws + L.tmp);
   Y.d_occ = reinterpret_cast<float*>(ws + L.d_occ);
+  Y.grgb = reinterpret_cast<float*>(ws + L.grgb);
+  Y.d_raw3 = stage == 1 ? reinterpret_cast<float*>(ws + L.d_raw3) : nullptr;
   point::k_loss<<<1, 1024, 0, stream>>>(Y);
   XRD_LAUNCH_CHECK();
   k_composite_bwd<<<(R + 127) / 128, 128, 0, stream>>>(Y);
@@ -533,6 +742,11 @@ extern "C" int xrd_pointslam_step(const XrdRays* rays, const XrdPointIndex* inde
   Q.dc = D.ext_dc; Q.d_feats = grads->d_geo_feats; Q.dp = D.dp; Q.need_dp = D.need_dp;
   k_interp_bwd<<<(P + 127) / 128, 128, 0, stream>>>(Q);
   XRD_LAUNCH_CHECK();
+  if (stage == 1) {
+    C.dp = D.dp; C.need_dp = D.need_dp; C.d_col_feats = grads->d_col_feats;
+    const int st = color_backward(C, L, ws, P, grads->color, stream);
+    if (st != XRD_OK) return st;
+  }
   if (D.need_dp) {
     k_rayreduce_f<<<(R + 127) / 128, 128, 0, stream>>>(R, S, P, z, D.dp, grads->d_rays_o, grads->d_rays_d);
     XRD_LAUNCH_CHECK();
