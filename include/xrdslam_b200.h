@@ -107,6 +107,12 @@ typedef struct {
   float* param; float* grad; float* exp_avg; float* exp_avg_sq;
   long long n;
   float lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2;
+  /* optional row mask: element i is updated only if row_mask[i / row_len] != 0.  This is the
+   * frustum feature selection of NICE-SLAM (slam/models/conv_onet.py:94-114,187-211: the
+   * reference optimises a compacted copy val[mask] and scatters it back into the full grid
+   * every iteration); rows = voxels of the channel-last grid, row_len = 32. */
+  const uint8_t* row_mask;
+  int row_len;
 } XrdAdamTensor;
 
 /* tensors: HOST array.  zero_grad != 0 also clears every grad (folds zero_grad_all,

@@ -303,3 +303,31 @@ def test_pointslam_oracle_color_stage_matches_golden(tag, is_mapping):
     assert rel_err(rd.grad, g[tag + '.d_rays_d']) < 1e-3
     for k, v in oracle_cdec_grads(ora).items():
         assert rel_err(v, g[tag + '.d_cdec.' + k]) < 1e-3, k
+
+
+def test_stage_schedulers_and_stage_selection():
+    """B4: LambdaLR factors = stage learning rates; stage boundaries of nice / point."""
+    from xrdslam_b200.schedulers import (LRconfig, NiceSLAMSchedulerConfig,
+                                         PointSLAMSchedulerConfig)
+    p = torch.nn.Parameter(torch.zeros(3))
+    opt = torch.optim.Adam([p], lr=5.0)  # lr = factor 5.0 (mapping_lr_first_factor)
+    cfg = NiceSLAMSchedulerConfig(coarse=False, stage_lr=LRconfig(0.0, 0.1, 0.005, 0.002),
+                                  max_steps=10)
+    sch = cfg.setup().get_scheduler(opt, 5.0)
+    lrs = []
+    for _ in range(10):
+        lrs.append(opt.param_groups[0]['lr'])
+        opt.step()
+        sch.step()
+    assert np.allclose(lrs, [0.5] * 5 + [0.025] * 2 + [0.01] * 3)
+    pc = PointSLAMSchedulerConfig(start_lr=0.03, end_lr=0.005, max_steps=10, geo_iter_ratio=0.4)
+    assert [pc.setup().factor(s) for s in (0, 4, 5, 9)] == [0.03, 0.03, 0.005, 0.005]
+
+
+def test_remap_linear_bilinear_and_border():
+    from xrdslam_b200.keyframe_selection import remap_linear
+    img = torch.arange(12.).reshape(3, 4)
+    uv = torch.tensor([[0., 0.], [1.5, 0.5], [3.0, 2.0], [3.5, 2.0], [-0.5, 0.], [1.03, 1.0]])
+    out = remap_linear(img, uv)
+    # 1.03 -> 33/32: OpenCV's 1/32-pixel coordinate quantisation
+    assert torch.allclose(out, torch.tensor([0., 3.5, 11., 5.5, 0., 5. + 1. / 32]))

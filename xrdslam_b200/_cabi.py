@@ -203,7 +203,8 @@ class XrdAdamTensor(C.Structure):
     _fields_ = [('param', vp), ('grad', vp), ('exp_avg', vp), ('exp_avg_sq', vp),
                 ('n', C.c_longlong), ('lr', C.c_float), ('beta1', C.c_float),
                 ('beta2', C.c_float), ('eps', C.c_float), ('weight_decay', C.c_float),
-                ('bias_correction1', C.c_float), ('bias_correction2', C.c_float)]
+                ('bias_correction1', C.c_float), ('bias_correction2', C.c_float),
+                ('row_mask', vp), ('row_len', C.c_int)]
 
 
 SYMBOLS = {

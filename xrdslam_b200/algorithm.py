@@ -77,6 +77,50 @@ class Algorithm():
     def device(self):
         return self.model.device
 
+    def _frame_tensor(self, frame, which):
+        """Upload a frame's image once and keep it resident on the device (the reference
+        re-uploads the full image every iteration, common.py:67-68 -- SURVEY row f1)."""
+        import numpy as np
+        key = '_dev_' + which
+        t = frame.__dict__.get(key)
+        if t is None:
+            t = torch.as_tensor(np.asarray(getattr(frame, which), dtype=np.float32)
+                                ).to(self.device)
+            frame.__dict__[key] = t
+        return t
+
+    def _sample_frames(self, frames, n, Hedge=0, Wedge=0, **kw):
+        """get_samples per frame (shared by nice / vox / point get_model_input)."""
+        from .common import get_samples
+        return [get_samples(self.camera, n, f.get_pose(), self._frame_tensor(f, 'depth'),
+                            self._frame_tensor(f, 'rgb'), device=self.device, Hedge=Hedge,
+                            Wedge=Wedge, **kw) for f in frames]
+
+    def _render_full(self, c2w, gt_depth, extra=None, per_pixel=None):
+        """render_img body shared by the algorithms: all H*W rays in ray_batch_size chunks."""
+        import numpy as np
+        from .common import get_rays
+        dev = self.device
+        rays_o, rays_d = get_rays(self.camera, torch.as_tensor(c2w), device=dev)
+        rays_o, rays_d = rays_o.reshape(-1, 3), rays_d.reshape(-1, 3)
+        if gt_depth is not None:
+            gt_depth = torch.as_tensor(np.asarray(gt_depth), dtype=torch.float32).to(dev
+                                                                                     ).reshape(-1, 1)
+        depths, colors = [], []
+        bs = self.config.ray_batch_size
+        for i in range(0, rays_d.shape[0], bs):
+            batch = {'rays_o': rays_o[i:i + bs], 'rays_d': rays_d[i:i + bs], 'target_s': None,
+                     'target_d': gt_depth[i:i + bs] if gt_depth is not None else None}
+            batch.update(extra or {})
+            for k, v in (per_pixel or {}).items():
+                batch[k] = v[i:i + bs]
+            out = self.model(batch)
+            depths.append(out['depth'].double())
+            colors.append(out['rgb'])
+        H, W = self.camera.height, self.camera.width
+        return (torch.cat(colors, 0).reshape(H, W, 3).cpu().numpy(),
+                torch.cat(depths, 0).reshape(H, W).cpu().numpy())
+
     # ---- bookkeeping ------------------------------------------------------
     def add_framepose(self, c2w, gt_c2w, gt_c2w_ori):
         with self.lock:

@@ -318,8 +318,38 @@ class ConvOnet(Model):
             d['rgb_loss'] = ls[1]
         return d
 
+    # ---- frustum feature selection (conv_onet.py:94-130, rows N2 / N3) -------------------
+    def pre_precessing(self, cur_frame):
+        """Voxel masks of the current frustum (utils.py:298-375), one uint8 per voxel of the
+        channel-last grids.  The reference then optimises a compacted copy of the masked
+        voxels and scatters it back into the full 43 MB grid every iteration
+        (grid_processing / post_processing); here the full grid stays the parameter and the
+        Adam kernel skips the rows outside the mask -- same values, no scatter."""
+        if not self.config.mapping_frustum_feature_selection:
+            return
+        from .keyframe_selection import frustum_mask
+        dev = self.device
+        bb = self.bounding_box
+        c2w = cur_frame.get_pose().detach()
+        for key, g in self.grids.items():
+            Z, Y, X = g.shape[:3]
+            zs = torch.linspace(float(bb[2][0]), float(bb[2][1]), Z)
+            ys = torch.linspace(float(bb[1][0]), float(bb[1][1]), Y)
+            xs = torch.linspace(float(bb[0][0]), float(bb[0][1]), X)
+            gz, gy, gx = torch.meshgrid(zs, ys, xs, indexing='ij')  # [Z,Y,X] storage order
+            pts = torch.stack([gx, gy, gz], -1).reshape(-1, 3).to(dev)
+            m = frustum_mask(self.camera, c2w, pts, cur_frame.depth, edge=0, near_cam=0.5)
+            self.grid_opti_mask[key] = m.reshape(Z, Y, X).to(torch.uint8).contiguous()
+
+    def grid_processing(self, coarse=False):
+        """No-op: see pre_precessing (the reference re-scatters val[mask] = val_grad here)."""
+
+    def post_processing(self, coarse=False):
+        """No-op: the full grid is the parameter; nothing to write back."""
+
     def get_param_groups(self) -> Dict[str, List[Parameter]]:
-        """conv_onet.py:187-211 (frustum-masked sub-selection is SURVEY row f2)."""
+        """conv_onet.py:187-211; with frustum selection the grids carry a row mask that the
+        fused Adam honours (optimizers.FusedAdam)."""
         groups = {}
         dec = []
         if not self.config.mapping_fix_fine:
@@ -329,5 +359,8 @@ class ConvOnet(Model):
         if dec:
             groups['decoder'] = dec
         for key in ('grid_middle', 'grid_fine', 'grid_color'):
-            groups[key] = [self.grids[key]]
+            p = self.grids[key]
+            p._xrd_row_mask = self.grid_opti_mask.get(key) \
+                if self.config.mapping_frustum_feature_selection else None
+            groups[key] = [p]
         return groups

@@ -229,16 +229,6 @@ class CoSLAM(Algorithm):
             'first': first_flag,
         }
 
-    def _frame_tensor(self, frame, which):
-        """Upload a frame's image once and keep it resident (row f1)."""
-        key = '_dev_' + which
-        t = frame.__dict__.get(key)
-        if t is None:
-            t = torch.as_tensor(np.asarray(getattr(frame, which),
-                                           dtype=np.float32)).to(self.device)
-            frame.__dict__[key] = t
-        return t
-
     def get_loss(self, optimize_frames, is_mapping, step=None, n_iters=None,
                  coarse=False):
         # tracking optimises the pose only: no map gradients are needed

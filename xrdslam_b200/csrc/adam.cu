@@ -37,9 +37,11 @@ __global__ void __launch_bounds__(256) k_adam(const Args A) {
   const long long n = T.n;
   const bool vec = ((((uintptr_t)T.param | (uintptr_t)T.grad | (uintptr_t)T.exp_avg |
                       (uintptr_t)T.exp_avg_sq) & 15) == 0);
-  const long long n4 = vec ? n / 4 : 0;
+  const bool masked = T.row_mask != nullptr;
+  const long long n4 = (vec && (!masked || (T.row_len & 3) == 0)) ? n / 4 : 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
+    if (masked && !T.row_mask[(i * 4) / T.row_len]) continue;  // row_len % 4 == 0: one row per float4
     float4 p = reinterpret_cast<float4*>(T.param)[i];
     float4 g = reinterpret_cast<float4*>(T.grad)[i];
     float4 m = reinterpret_cast<float4*>(T.exp_avg)[i];
@@ -55,6 +57,7 @@ __global__ void __launch_bounds__(256) k_adam(const Args A) {
   }
   for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
+    if (masked && !T.row_mask[i / T.row_len]) continue;
     float p = T.param[i], g = T.grad[i], m = T.exp_avg[i], v = T.exp_avg_sq[i];
     upd(p, g, m, v, T, step_size, inv_sqrt_bc2);
     T.param[i] = p; T.exp_avg[i] = m; T.exp_avg_sq[i] = v;
@@ -81,6 +84,7 @@ extern "C" int xrd_adam_step(const XrdAdamTensor* tensors, int n_tensors, int ze
       if (!A.t[i].param || !A.t[i].grad || !A.t[i].exp_avg || !A.t[i].exp_avg_sq) return XRD_E_NULL;
       if (A.t[i].n < 0 || A.t[i].bias_correction1 <= 0.f || A.t[i].bias_correction2 <= 0.f)
         return XRD_E_SHAPE;
+      if (A.t[i].row_mask && A.t[i].row_len < 1) return XRD_E_SHAPE;
       if (A.t[i].n > nmax) nmax = A.t[i].n;
     }
     long long bx = (nmax / 4 + 255) / 256;

@@ -12,7 +12,9 @@ from torch.nn.parameter import Parameter
 class FusedAdam(torch.optim.Optimizer):
     """torch.optim.Adam (amsgrad=False) for device-resident fp32 parameters: every tensor of
     the group is updated by ONE launch of csrc/adam.cu (xrd_adam_step) instead of torch's
-    ~10 foreach launches.  State keys are torch's (`step`, `exp_avg`, `exp_avg_sq`) so
+    ~10 foreach launches.  A parameter may carry `_xrd_row_mask` (uint8, one entry per row):
+    rows whose mask is 0 are left untouched (NICE-SLAM frustum feature selection without the
+    reference's compact-copy / scatter-back round trip).  State keys are torch's (`step`, `exp_avg`, `exp_avg_sq`) so
     optimizer checkpoints interchange with torch.optim.Adam."""
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
@@ -49,6 +51,11 @@ class FusedAdam(torch.optim.Optimizer):
             a.exp_avg, a.exp_avg_sq = st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr()
             a.n, a.lr, a.beta1, a.beta2, a.eps = p.numel(), lr, b1, b2, eps
             a.weight_decay, a.bias_correction1, a.bias_correction2 = wd, c1, c2
+            mask = getattr(p, '_xrd_row_mask', None)  # frustum feature selection (NICE-SLAM)
+            if mask is not None:
+                assert mask.is_cuda and mask.dtype == torch.uint8 and mask.is_contiguous() and \
+                    p.numel() % mask.numel() == 0
+                a.row_mask, a.row_len = mask.data_ptr(), p.numel() // mask.numel()
         with torch.cuda.device(dev):
             rc = _cabi.lib().xrd_adam_step(arr, len(descs), 0,
                                            torch.cuda.current_stream(dev).cuda_stream)
