@@ -202,15 +202,28 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- value: batches resident in HBM -----------------------
+    # N = 1: the mapping iteration is ONE CUDA graph (xrdslam_b200/coslam_graph.py) replayed
+    # from a device-resident batch; N > 1: sharded autograd path + NCCL all-reduce.
+    use_graph = world == 1 and algo._graph_ok(frames)
+    sess = None
     batches = []
-    for _ in range(K + W):
-        b = make_batch()
-        b = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in b.items()}
-        b['rays_o'].requires_grad_(True)  # bundle adjustment: pose gradients are
-        b['rays_d'].requires_grad_(True)  # part of the step (d loss / d rays)
-        batches.append(b)
+    if use_graph:
+        algo.config.min_sample_pixels = MAP_CUR
+        algo.bundle_adjust = True
+        sess = algo.mapping_session(frames)
+        sess.begin(frames)
+        batches = [sess.make_resident_batch(frames) for _ in range(K + W)]
+        run_step = lambda i: sess.step_resident(i, batches[i])
+    else:
+        for _ in range(K + W):
+            b = make_batch()
+            b = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in b.items()}
+            b['rays_o'].requires_grad_(True)  # bundle adjustment: pose gradients are
+            b['rays_d'].requires_grad_(True)  # part of the step (d loss / d rays)
+            batches.append(b)
+        run_step = lambda i: device_step(batches[i])
     for i in range(W):
-        device_step(batches[i])
+        run_step(i)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(K)]
     clocks = ClockSampler(local)
@@ -221,7 +234,7 @@ def run_ours(args):
     for i in range(K):
         flush.zero_()  # L2 flush (256 MB > 126 MB L2), outside the timed events
         ev[i][0].record()
-        device_step(batches[W + i])
+        run_step(W + i)
         ev[i][1].record()
     barrier()
     wall = time.perf_counter() - t0
@@ -232,6 +245,15 @@ def run_ours(args):
     ms_total = float(t.item())
     clk = clocks.stop() if rank == 0 else None
     value = world * R * K / (ms_total * 1e-3)
+    if use_graph:  # the roofline leg below goes through Model.forward: needs autograd batches
+        gen = []
+        for _ in range(K + W):
+            b = make_batch()
+            b = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in b.items()}
+            b['rays_o'].requires_grad_(True)
+            b['rays_d'].requires_grad_(True)
+            gen.append(b)
+        batches = gen
 
     # ---------------- roofline: the fused kernel alone ---------------------
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -264,26 +286,31 @@ def run_ours(args):
 
     # ---------------- e2e: through the plugin, host ray bank ---------------
     algo.config.min_sample_pixels = MAP_CUR
-    h2d = R * 7 * 4 + R * 8 + len(frames) * 16 * 4  # batch rows + ids + poses
+    h2d = R * 7 * 4 + R * 8 + 128  # sampled rows + pose ids + per-iteration scalar block
     d2h = 4
+    if use_graph:
+        def e2e_step(i):
+            return sess.step(i, frames).item()  # H2D rows/ids/scalars, graph, D2H loss
+    else:
+        h2d = R * 7 * 4 + R * 8 + len(frames) * 16 * 4
+
+        def e2e_step(i):
+            optim.zero_grad_all()
+            loss = algo.get_loss(frames, True, i, K)
+            loss.backward()
+            allreduce_grads(dp)
+            optim.optimizer_step_all(step=i)
+            return loss.item()  # D2H read of the step's result
     for i in range(W):
-        optim.zero_grad_all()
-        loss = algo.get_loss(frames, True, i, K)
-        loss.backward()
-        allreduce_grads(dp)
-        optim.optimizer_step_all(step=i)
-        loss.item()
+        e2e_step(i)
     barrier()
     t0 = time.perf_counter()
     for i in range(K):
-        optim.zero_grad_all()
-        loss = algo.get_loss(frames, True, i, K)
-        loss.backward()
-        allreduce_grads(dp)
-        optim.optimizer_step_all(step=i)
-        lv = loss.item()  # D2H read of the step's result
+        lv = e2e_step(i)
     barrier()
     e2e_s = time.perf_counter() - t0
+    if use_graph:
+        sess.end(frames)
     t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -332,11 +359,20 @@ def run_ours(args):
                        'l2': 'flushed between timed steps (256 MB write); ray batches differ every step'},
             'e2e': {'value': e2e_value, 'unit': 'rays/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h,
-                    'path': 'CoSLAM.get_loss (host pinned ray bank, random.sample, H2D) -> '
-                            'loss.backward -> Optimizers.optimizer_step_all -> loss.item()'},
-            'gpu_launches': K * 6,
-            'gpu_launches_note': 'per step: k_sample, k_fused<true>, k_finalize, k_smooth_fwd, '
-                                 'k_smooth_bwd, k_smooth_finalize (torch Adam/elementwise not counted)',
+                    'path': ('CoSLAM.mapping_session(frames).step(): host pinned ray bank, '
+                             'random.sample, H2D, one CUDA graph (poses, rays, sample, fused '
+                             'fwd/loss/bwd, smoothness, pose grads, Adam), loss.item()')
+                    if use_graph else
+                    ('CoSLAM.get_loss (host pinned ray bank, random.sample, H2D) -> '
+                     'loss.backward -> all-reduce -> Optimizers.optimizer_step_all -> loss.item()')},
+            'gpu_launches': K * (11 if use_graph else 9) + (K // 5 if use_graph else 0),
+            'gpu_launches_note': ('per step (one graph): pose::k_fwd, rays::k_fwd, k_sample, '
+                                  'k_fused<true>, k_finalize, k_smooth_fwd, k_smooth_bwd, '
+                                  'k_smooth_finalize, rays::k_bwd, pose::k_bwd, k_adam (+ k_adam on '
+                                  'the poses every 5th step)') if use_graph else
+                                 ('per step: rays::k_fwd, k_sample, k_fused<true>, k_finalize, '
+                                  'k_smooth_fwd/bwd/finalize, rays::k_bwd, k_adam x2 (torch glue '
+                                  'not counted)'),
             'clocks': clk, 'roofline': roofline, 'cpu_baseline': cpu,
             'iters': {'mapping_iters_per_s': K / (ms_total * 1e-3),
                       **(trk or {})},

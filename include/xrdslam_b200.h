@@ -100,6 +100,17 @@ int xrd_rays_pose_grads(int n_rays, const float* dirs_cam, const int64_t* pose_i
                         const float* d_rays_o, const float* d_rays_d, float* d_poses,
                         void* stream);
 
+/* c2w [n,4,4] from axis-angle `rot` [n,3] and translation `trans` [n,3] (all DEVICE):
+ * slam/utils/opt_pose.py:51-55,77-95 (OptimizablePose.matrix / Rodrigues). */
+int xrd_pose_matrices(int n_poses, const float* rot, const float* trans, float* c2w, void* stream);
+
+/* Backward of the above (what torch autograd computes through opt_pose.py): d_rot / d_trans
+ * [n,3] are ACCUMULATED into (Co-SLAM steps its mapping poses every 5th iteration on the summed
+ * gradients).  fixed: DEVICE [n] or NULL; rows with fixed != 0 receive nothing
+ * (the first frame of the window, coslam.py:181-182 / base_algorithm.py:196-199). */
+int xrd_pose_matrices_grads(int n_poses, const float* rot, const float* d_c2w,
+                            const uint8_t* fixed, float* d_rot, float* d_trans, void* stream);
+
 /* One tensor of a multi-tensor Adam step (torch.optim.Adam, amsgrad=False); all DEVICE fp32.
  * bias_correction{1,2} = 1 - beta{1,2}^step with step counted from 1 (host, double -> float). */
 #define XRD_ADAM_MAX_TENSORS 24
@@ -113,6 +124,9 @@ typedef struct {
    * every iteration); rows = voxels of the channel-last grid, row_len = 32. */
   const uint8_t* row_mask;
   int row_len;
+  /* optional DEVICE [3] = {lr, bias_correction1, bias_correction2} overriding the host values:
+   * lets a captured CUDA graph replay the step with per-iteration scalars. */
+  const float* dyn;
 } XrdAdamTensor;
 
 /* tensors: HOST array.  zero_grad != 0 also clears every grad (folds zero_grad_all,
@@ -176,6 +190,8 @@ typedef struct {
   const int* counts_global;  /* DEVICE [3] n_fs, n_sdf, n_valid of the all-rank
                               * batch; NULL = this call's own counts            */
   int* counts_out;           /* DEVICE [4], written in phase 1                  */
+  const uint64_t* seed_dev;  /* DEVICE scalar overriding `seed` (read by the kernel:
+                              * a captured CUDA graph replays with a fresh seed)  */
 } XrdCoslamCfg;
 
 /* Per-ray / per-sample outputs (DEVICE, any may be NULL except losses when
@@ -224,7 +240,14 @@ size_t xrd_coslam_smoothness_workspace_bytes(int sample_points);
  * smooth_rand: HOST [6] = torch.rand(3) ++ torch.rand((1,1,1,3)).  Writes
  * weight*loss to DEVICE loss[0]; if d_table != NULL accumulates
  * grad_scale*weight*dloss/dtable into it. */
+/* (xrd_coslam_smoothness_dev: the same with smooth_rand in DEVICE memory, read by the
+ * kernels -- for CUDA-graph replay.) */
 int xrd_coslam_smoothness(const XrdHashGrid* grid, int sample_points,
+                          double voxel_size, double margin, float weight,
+                          const float* smooth_rand, float* loss, float* d_table,
+                          float grad_scale, void* workspace,
+                          size_t workspace_bytes, void* stream);
+int xrd_coslam_smoothness_dev(const XrdHashGrid* grid, int sample_points,
                           double voxel_size, double margin, float weight,
                           const float* smooth_rand, float* loss, float* d_table,
                           float grad_scale, void* workspace,

@@ -67,7 +67,7 @@ class XrdCoslamCfg(C.Structure):
                 ('lin_full', vp), ('seed', C.c_uint64),
                 ('rays_per_tile', C.c_int), ('precision', C.c_int),
                 ('phase', C.c_int), ('n_rays_global', C.c_int),
-                ('counts_global', vp), ('counts_out', vp)]
+                ('counts_global', vp), ('counts_out', vp), ('seed_dev', vp)]
 
 
 class XrdCoslamOut(C.Structure):
@@ -204,13 +204,15 @@ class XrdAdamTensor(C.Structure):
                 ('n', C.c_longlong), ('lr', C.c_float), ('beta1', C.c_float),
                 ('beta2', C.c_float), ('eps', C.c_float), ('weight_decay', C.c_float),
                 ('bias_correction1', C.c_float), ('bias_correction2', C.c_float),
-                ('row_mask', vp), ('row_len', C.c_int)]
+                ('row_mask', vp), ('row_len', C.c_int), ('dyn', vp)]
 
 
 SYMBOLS = {
     'xrd_rays_from_poses': (C.c_int, [C.c_int, vp, vp, vp, C.c_int, vp, vp, vp]),
     'xrd_rays_pose_grads': (C.c_int, [C.c_int, vp, vp, C.c_int, vp, vp, vp, vp]),
     'xrd_adam_step': (C.c_int, [C.POINTER(XrdAdamTensor), C.c_int, C.c_int, vp]),
+    'xrd_pose_matrices': (C.c_int, [C.c_int, vp, vp, vp, vp]),
+    'xrd_pose_matrices_grads': (C.c_int, [C.c_int, vp, vp, vp, vp, vp, vp]),
     'xrd_abi_version': (C.c_int, []),
     'xrd_last_cuda_error': (C.c_int, []),
     'xrd_check_device': (C.c_int, [C.c_int]),
@@ -230,6 +232,10 @@ SYMBOLS = {
     'xrd_coslam_smoothness_workspace_bytes': (C.c_size_t, [C.c_int]),
     'xrd_coslam_smoothness': (C.c_int, [
         C.POINTER(XrdHashGrid), C.c_int, C.c_double, C.c_double, C.c_float, fp,
+        vp, vp, C.c_float, vp, C.c_size_t, vp
+    ]),
+    'xrd_coslam_smoothness_dev': (C.c_int, [
+        C.POINTER(XrdHashGrid), C.c_int, C.c_double, C.c_double, C.c_float, vp,
         vp, vp, C.c_float, vp, C.c_size_t, vp
     ]),
     'xrd_hashgrid_encode':

@@ -293,10 +293,15 @@ class ConvOnet(Model):
         fused = torch.is_grad_enabled() and target_s is not None and 'is_mapping' in input
         if fused:
             cparams = self.decoder.color_decoder.tensors()
+            grids = [self.grids[k] for k in ('grid_middle', 'grid_fine', 'grid_color')]
+            if getattr(self, 'freeze_map_grads', False):
+                # tracking optimises the pose only: skip grid / decoder gradients (the
+                # reference computes and discards them)
+                cparams = [t.detach() for t in cparams]
+                grids = [g.detach() for g in grids]
             losses, rgb, depth, unc = _NiceStep.apply(
                 self, stage, input['is_mapping'], target_s, target_d, rays_o, rays_d,
-                self.grids['grid_middle'], self.grids['grid_fine'], self.grids['grid_color'],
-                *cparams)
+                *grids, *cparams)
             return {'rgb': rgb, 'depth': depth, 'uncertainty': unc, '_losses': losses}
         o, _ = self._launch(stage, True, rays_o, rays_d, target_s, target_d, False)
         o.pop('losses')

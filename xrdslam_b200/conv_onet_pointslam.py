@@ -276,10 +276,12 @@ class ConvOnet2(Model):
         npc = self.neural_point_cloud
         fused = torch.is_grad_enabled() and 'is_mapping' in input
         if fused:
+            gf, cf, cp = npc.geo_feats, npc.col_feats, self.decoder.color_decoder.tensors()
+            if getattr(self, 'freeze_map_grads', False):  # tracking: pose gradients only
+                gf, cf, cp = gf.detach(), cf.detach(), [t.detach() for t in cp]
             losses, rgb, depth, unc, valid = _PointStep.apply(
                 self, stage, input['is_mapping'], ts, td, radius, input.get('rand_feat'),
-                input.get('rand_feat_color'), rays_o, rays_d, npc.geo_feats, npc.col_feats,
-                *self.decoder.color_decoder.tensors())
+                input.get('rand_feat_color'), rays_o, rays_d, gf, cf, *cp)
             return {'rgb': rgb, 'depth': depth, 'uncertainty': unc, 'valid_ray_mask': valid,
                     'stage': stage, '_losses': losses}
         o, _ = self._launch(stage, True, rays_o, rays_d, ts, td, radius, input.get('rand_feat'),

@@ -60,6 +60,8 @@ class CoSLAMConfig(AlgorithmConfig):
     mapping_bound: List[List[float]] = field(
         default_factory=lambda: [[-3, 3], [-4, 2.5], [-2, 2.5]])
     optimizers: Dict[str, Any] = field(default_factory=_coslam_optimizers)
+    # B200: run the mapping iterations as one CUDA graph each (coslam_graph.py)
+    graph_mapping: bool = True
 
 
 class _PinnedStaging:
@@ -228,6 +230,44 @@ class CoSLAM(Algorithm):
             'target_d': target_d.float(),
             'first': first_flag,
         }
+
+    # ---- CUDA-graph mapping (row f1) -------------------------------------------------
+    def _graph_ok(self, optimize_frames):
+        cfg = self.config
+        dp = getattr(self.model, 'dp', None)
+        if not (cfg.graph_mapping and self.device.type == 'cuda' and cfg.separate_LR
+                and cfg.rot_rep == 'axis_angle') or (dp is not None and dp.world > 1):
+            return False
+        n_kf = len(self.keyframe_graph)
+        return n_kf == 0 or len(optimize_frames) == n_kf + 1  # ids index the window 1:1
+
+    def mapping_session(self, optimize_frames):
+        """The captured iteration for this window shape (cached by shape)."""
+        from .coslam_graph import MappingGraphSession
+        n_kf = len(self.keyframe_graph)
+        first = n_kf == 0
+        n_bank = 0 if first else self.config.mapping_sample
+        n_cur = self.config.mapping_sample if first else int(np.maximum(
+            self.config.mapping_sample // n_kf, self.config.min_sample_pixels))
+        ba = self.bundle_adjust and len(optimize_frames) > 1
+        key = (n_bank, n_cur, len(optimize_frames), first, ba)
+        cache = self.__dict__.setdefault('_graph_sessions', {})
+        if key not in cache:
+            cache[key] = MappingGraphSession(self, n_bank, n_cur, len(optimize_frames), first, ba)
+        return cache[key]
+
+    def optimize_update(self, n_iters, optimize_frames, is_mapping, coarse=False):
+        if not is_mapping or not self._graph_ok(optimize_frames):
+            return super().optimize_update(n_iters, optimize_frames, is_mapping, coarse=coarse)
+        with self.lock:
+            self.pre_precessing(optimize_frames[-1], True)
+            self.setup_optimizers(n_iters, optimize_frames, True, coarse=coarse)
+            sess = self.mapping_session(optimize_frames)
+            sess.begin(optimize_frames)
+            for step in range(n_iters):
+                sess.step(step, optimize_frames)
+            sess.end(optimize_frames)
+            return None
 
     def get_loss(self, optimize_frames, is_mapping, step=None, n_iters=None,
                  coarse=False):

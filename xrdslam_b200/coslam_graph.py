@@ -1,0 +1,300 @@
+"""Co-SLAM mapping iteration as ONE CUDA graph ("CUDA-graph the whole
+optimize_update body incl. Adam").
+
+What Algorithm.optimize_update does per iteration through torch autograd --
+get_model_input -> Model.forward -> get_loss_dict -> loss.backward -> optimizer_step_all
+(slam/algorithms/base_algorithm.py:255-273, coslam.py:152-243) -- is here a fixed sequence
+of C-ABI launches captured once and replayed:
+
+    H2D  sampled rows [R,7] + pose ids [R] + a 128-byte block of per-iteration scalars
+    graph: zero grads | poses -> c2w | rays from poses | sample + fused fwd/loss/bwd |
+           smoothness | pose-gradient reduction -> d(axis-angle, t) | Adam on table + decoder
+    host  every 5th iteration (accum_step, Q11): one Adam launch on the pose block
+
+Poses are uploaded at begin() and written back into the Frame parameters at end(); the
+host does no autograd and no per-iteration synchronisation.  The per-parameter-group Adam
+state is the persistent FusedAdam state of CoSLAM.model_optimizers, so generic and graph
+iterations can be mixed.  Parity with the generic path: tests/test_coslam_graph_gpu.py."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import (XrdAdamTensor, XrdCoslamCfg, XrdCoslamGrads, XrdCoslamMlp, XrdCoslamOut,
+                    XrdRays, check, ptr)
+from .optimizers import FusedAdam
+
+
+class MappingGraphSession:
+    def __init__(self, algo, n_bank, n_cur, n_poses, first, bundle_adjust):
+        self.algo, self.model = algo, algo.model
+        model, cfg, dev = algo.model, algo.model.config, algo.device
+        self.dev = dev
+        self.n_bank, self.n_cur, self.n_poses = n_bank, n_cur, n_poses
+        self.first, self.ba = first, bundle_adjust
+        R = self.R = n_bank + n_cur
+        S = cfg.training_n_sample_d + cfg.training_n_range_d
+        f32 = dict(dtype=torch.float32, device=dev)
+        z = lambda *s: torch.zeros(*s, **f32)
+        # ---- device-resident state of one iteration
+        self.rows, self.ids = z(R, 7), torch.zeros(R, dtype=torch.int64, device=dev)
+        self.rot, self.trans = z(n_poses, 3), z(n_poses, 3)
+        self.fixed = torch.zeros(n_poses, dtype=torch.uint8, device=dev)
+        self.poses, self.d_poses = z(n_poses, 4, 4), z(n_poses, 4, 4)
+        self.d_rot, self.d_trans = z(n_poses, 3), z(n_poses, 3)
+        self.rays_o, self.rays_d = z(R, 3), z(R, 3)
+        self.d_rays_o, self.d_rays_d = z(R, 3), z(R, 3)
+        self.out = dict(rgb=z(R, 3), depth=z(R), disp=z(R), acc=z(R), var=z(R), z_vals=z(R, S),
+                        raw=z(R, S, 4))
+        self.losses, self.smooth_loss = z(4), z(1)
+        lib = _cabi.lib()
+        self.ws = torch.empty(lib.xrd_coslam_workspace_bytes(R, S), dtype=torch.uint8, device=dev)
+        self.ws_s = torch.empty(lib.xrd_coslam_smoothness_workspace_bytes(cfg.trainging_smooth_pts),
+                                dtype=torch.uint8, device=dev)
+        # per-iteration scalars: [seed u64 | smooth_rand f32 x6 | (lr, bc1, bc2) per group]
+        self.dyn = torch.zeros(128, dtype=torch.uint8, device=dev)
+        self._dyn_ring = [torch.zeros(128, dtype=torch.uint8).pin_memory() for _ in range(8)]
+        self._dyn_ev = [None] * 8
+        self._dyn_k = 0
+        # ---- model parameters, their persistent gradient buffers and Adam state
+        self.table = model.embed_fn.params
+        self.weights = list(model._weights())
+        self.opt_groups = []  # (FusedAdam, [params])
+        for name in ('embed_fn', 'decoder'):
+            opt = algo.model_optimizers.optimizers[name]
+            if not isinstance(opt, FusedAdam) or len(opt.param_groups) != 1:
+                raise RuntimeError('graph mapping needs FusedAdam model optimizers')
+            self.opt_groups.append((opt, list(opt.param_groups[0]['params'])))
+        self.grads = {}
+        for _, params in self.opt_groups:
+            for p in params:
+                self.grads[p] = torch.zeros_like(p)
+        self.pose_state = None
+        # Adam state must exist BEFORE capture: tensors created while capturing come from the
+        # graph's private pool and their zero-fill would be replayed every iteration
+        for opt, params in self.opt_groups:
+            for p in params:
+                st = opt.state[p]
+                if not st:
+                    st['step'] = torch.tensor(0.0)
+                    st['exp_avg'] = torch.zeros_like(p)
+                    st['exp_avg_sq'] = torch.zeros_like(p)
+        self.graph = torch.cuda.CUDAGraph()
+        self._capture()
+
+    # ------------------------------------------------------------------ capture ---
+    def _adam_descs(self):
+        descs = []
+        for gi, (opt, params) in enumerate(self.opt_groups):
+            g = opt.param_groups[0]
+            for p in params:
+                st = opt.state[p]
+                a = XrdAdamTensor()
+                a.param, a.grad = p.data_ptr(), self.grads[p].data_ptr()
+                a.exp_avg, a.exp_avg_sq = st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr()
+                a.n, a.lr, a.beta1, a.beta2 = p.numel(), g['lr'], g['betas'][0], g['betas'][1]
+                a.eps, a.weight_decay = g['eps'], g['weight_decay']
+                a.bias_correction1 = a.bias_correction2 = 1.0
+                a.dyn = self.dyn.data_ptr() + 32 + 12 * gi
+                descs.append(a)
+        return descs
+
+    def _sequence(self, stream, with_adam):
+        """The launches of one iteration on `stream` (eagerly for warm-up, then captured)."""
+        model, cfg, lib = self.model, self.model.config, _cabi.lib()
+        R, n = self.R, self.n_poses
+        S = cfg.training_n_sample_d + cfg.training_n_range_d
+        for g in self.grads.values():
+            g.zero_()
+        self.dirs = self.rows[:, :3].contiguous()
+        self.ts = self.rows[:, 3:6].contiguous()
+        self.td = self.rows[:, 6].contiguous()
+        check('xrd_pose_matrices',
+              lib.xrd_pose_matrices(n, ptr(self.rot), ptr(self.trans), ptr(self.poses), stream))
+        check('xrd_rays_from_poses',
+              lib.xrd_rays_from_poses(R, ptr(self.dirs), ptr(self.ids), ptr(self.poses), n,
+                                      ptr(self.rays_o), ptr(self.rays_d), stream))
+        rays = XrdRays(R, ptr(self.rays_o), ptr(self.rays_d), ptr(self.ts), ptr(self.td))
+        grid = model._grid_struct(self.table.detach())
+        w = [t.detach() for t in self.weights]
+        mlp = XrdCoslamMlp(*(ptr(t) for t in w))
+        c = XrdCoslamCfg(
+            S, cfg.training_n_sample_d, cfg.training_n_range_d,
+            int(cfg.training_perturb > 0), cfg.training_trunc * cfg.data_sc_factor,
+            cfg.cam_depth_trunc, cfg.trainging_rgb_weight, cfg.trainging_depth_weight,
+            cfg.trainging_sdf_weight, cfg.trainging_fs_weight, ptr(model._lin_uniform),
+            ptr(model._lin_range), ptr(model._lin_nodepth), ptr(model._lin_full), 0,
+            cfg.rays_per_tile, cfg.precision, 0, 0, None, None, self.dyn.data_ptr())
+        o = self.out
+        out = XrdCoslamOut(ptr(o['rgb']), ptr(o['depth']), ptr(o['disp']), ptr(o['acc']),
+                           ptr(o['var']), ptr(o['z_vals']), ptr(o['raw']), ptr(self.losses))
+        G = self.grads
+        gs = XrdCoslamGrads(ptr(G[self.table]), *(ptr(G[t]) for t in self.weights),
+                            ptr(self.d_rays_o) if self.ba else None,
+                            ptr(self.d_rays_d) if self.ba else None,
+                            (C.c_float * 4)(1.0, 1.0, 1.0, 1.0))
+        check('xrd_coslam_step',
+              lib.xrd_coslam_step(C.byref(rays), C.byref(grid), C.byref(mlp), C.byref(c), None,
+                                  C.byref(out), C.byref(gs), ptr(self.ws), self.ws.numel(), stream))
+        if not self.first:
+            check('xrd_coslam_smoothness_dev', lib.xrd_coslam_smoothness_dev(
+                C.byref(grid), cfg.trainging_smooth_pts, cfg.trainging_smooth_vox,
+                cfg.trainging_smooth_margin, cfg.trainging_smooth_weight,
+                self.dyn.data_ptr() + 8, ptr(self.smooth_loss), ptr(G[self.table]), 1.0,
+                ptr(self.ws_s), self.ws_s.numel(), stream))
+        if self.ba:
+            check('xrd_rays_pose_grads', lib.xrd_rays_pose_grads(
+                R, ptr(self.dirs), ptr(self.ids), n, ptr(self.d_rays_o), ptr(self.d_rays_d),
+                ptr(self.d_poses), stream))
+            check('xrd_pose_matrices_grads', lib.xrd_pose_matrices_grads(
+                n, ptr(self.rot), ptr(self.d_poses), ptr(self.fixed), ptr(self.d_rot),
+                ptr(self.d_trans), stream))
+        if with_adam:
+            descs = self._adam_descs()
+        else:  # warm-up: load the kernel on scratch tensors, leave the model untouched
+            t = [torch.zeros(8, device=self.dev) for _ in range(4)]
+            self._scratch = t
+            a = XrdAdamTensor()
+            a.param, a.grad, a.exp_avg, a.exp_avg_sq = (x.data_ptr() for x in t)
+            a.n, a.lr, a.beta1, a.beta2, a.eps, a.weight_decay = 8, 0.0, 0.9, 0.999, 1e-8, 0.0
+            a.bias_correction1 = a.bias_correction2 = 1.0
+            descs = [a]
+        arr = (XrdAdamTensor * len(descs))(*descs)
+        check('xrd_adam_step', lib.xrd_adam_step(arr, len(descs), 0, stream))
+        self.loss_total = self.losses.sum() + (0 if self.first else self.smooth_loss[0])
+
+    def _capture(self):
+        dev = self.dev
+        with torch.cuda.device(dev):
+            # eager warm-up (lazy module loading, attribute calls), then capture
+            self.rows[:, 2] = -1.0
+            self.rows[:, 6] = 1.0
+            self._sequence(torch.cuda.current_stream(dev).cuda_stream, with_adam=False)
+            torch.cuda.synchronize(dev)
+            with torch.cuda.graph(self.graph, capture_error_mode='relaxed'):
+                self._sequence(torch.cuda.current_stream(dev).cuda_stream, with_adam=True)
+        self.d_rot.zero_()
+        self.d_trans.zero_()
+
+    # ------------------------------------------------------------------ running ---
+    def begin(self, optimize_frames):
+        """Upload the window's poses; (re)start the pose optimiser (fresh Adam state per
+        mapping call, like the reference's setup_optimizers)."""
+        frames = optimize_frames
+        assert len(frames) == self.n_poses
+        rot = torch.stack([f.pose.data_r.detach() for f in frames]).float()
+        trans = torch.stack([f.pose.data_t.detach() for f in frames]).float()
+        fixed = torch.tensor([1 if (i == 0 or f.fid == 0 or not self.ba) else 0
+                              for i, f in enumerate(frames)], dtype=torch.uint8)
+        self.rot.copy_(rot)
+        self.trans.copy_(trans)
+        self.fixed.copy_(fixed)
+        self.d_rot.zero_()
+        self.d_trans.zero_()
+        z = torch.zeros_like
+        self.pose_state = dict(t=0, m_r=z(self.rot), v_r=z(self.rot), m_t=z(self.trans),
+                               v_t=z(self.trans))
+        for p, g in self.grads.items():
+            p.grad = g  # visible to callers (DP all-reduce, inspection)
+
+    def _stage(self, frames):
+        """Host sampling into the pinned staging block (coslam.py:114-150, 152-200)."""
+        a = self.algo
+        rows, ids = a._staging.acquire(self.R)
+        nb = self.n_bank
+        if nb > 0:
+            idxs = a._sample_ids(len(a.keyframe_graph) * a.num_rays_to_save, nb)
+            torch.index_select(a.rays, 0, idxs, out=rows[:nb])
+            torch.div(idxs, a.num_rays_to_save, rounding_mode='floor', out=ids[:nb])
+        cur_tab = a._frame_rays(frames[-1])
+        torch.index_select(cur_tab, 0, a._sample_ids(cur_tab.shape[0], self.n_cur), out=rows[nb:])
+        ids[nb:] = -1
+        return rows, ids
+
+    def step(self, step, frames):
+        """One mapping iteration; returns the loss as a DEVICE scalar (no synchronisation)."""
+        rows, ids = self._stage(frames)
+        self.rows.copy_(rows, non_blocking=True)
+        self.ids.copy_(ids, non_blocking=True)
+        sl = self.algo._staging.cur[0]
+        if sl['ev'] is None:
+            sl['ev'] = torch.cuda.Event()
+        sl['ev'].record(torch.cuda.current_stream(self.dev))
+        return self._launch(step)
+
+    def _launch(self, step):
+        model, cfg = self.model, self.model.config
+        k = self._dyn_k % 8  # pinned ring: the host may run several iterations ahead
+        self._dyn_k += 1
+        if self._dyn_ev[k] is not None:
+            self._dyn_ev[k].synchronize()
+        dyn_host = self._dyn_ring[k]
+        d = dyn_host.numpy()
+        model._step_count += 1
+        d[0:8].view(np.uint64)[0] = (cfg.seed << 32) + model._step_count
+        if not self.first:
+            r6 = torch.cat([torch.rand(3), torch.rand((1, 1, 1, 3)).reshape(3)])
+            d[8:32].view(np.float32)[:] = r6.numpy()
+        for gi, (opt, params) in enumerate(self.opt_groups):
+            g = opt.param_groups[0]
+            t = float(opt.state[params[0]]['step']) + 1.0
+            for p in params:
+                opt.state[p]['step'] += 1
+            d[32 + 12 * gi:44 + 12 * gi].view(np.float32)[:] = (
+                g['lr'], 1.0 - g['betas'][0]**t, 1.0 - g['betas'][1]**t)
+        self.dyn.copy_(dyn_host, non_blocking=True)
+        if self._dyn_ev[k] is None:
+            self._dyn_ev[k] = torch.cuda.Event()
+        self._dyn_ev[k].record(torch.cuda.current_stream(self.dev))
+        self.graph.replay()
+        if self.ba:
+            self._pose_step(step)
+        return self.loss_total
+
+    def make_resident_batch(self, frames):
+        """Stage one iteration's inputs and park them in HBM (bench `value` leg: inputs
+        resident on the device before the timed region)."""
+        rows, ids = self._stage(frames)
+        return rows.to(self.dev), ids.to(self.dev)
+
+    def step_resident(self, step, batch):
+        """One iteration from a device-resident batch: only the 128-byte scalar block (seed,
+        smoothness offsets, Adam bias corrections) crosses PCIe."""
+        self.rows.copy_(batch[0])
+        self.ids.copy_(batch[1])
+        return self._launch(step)
+
+    def _pose_step(self, step):
+        """Adam on the pose block every accum_step-th iteration on the summed gradients."""
+        oc = self.algo.config.optimizers
+        acc = oc['mapping_pose_r']['optimizer'].accum_step or 1
+        if (step + 1) % acc != 0:
+            return
+        ps = self.pose_state
+        ps['t'] += 1
+        t = ps['t']
+        arr = (XrdAdamTensor * 2)()
+        for a, name, p, g, m, v in ((arr[0], 'mapping_pose_r', self.rot, self.d_rot, ps['m_r'], ps['v_r']),
+                                    (arr[1], 'mapping_pose_t', self.trans, self.d_trans, ps['m_t'], ps['v_t'])):
+            o = oc[name]['optimizer']
+            a.param, a.grad, a.exp_avg, a.exp_avg_sq = p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr()
+            a.n, a.lr, a.beta1, a.beta2, a.eps = p.numel(), o.lr, o.betas[0], o.betas[1], o.eps
+            a.weight_decay = getattr(o, 'weight_decay', 0)
+            a.bias_correction1, a.bias_correction2 = 1.0 - o.betas[0]**t, 1.0 - o.betas[1]**t
+        with torch.cuda.device(self.dev):
+            # zero_grad = 1: the accumulated pose gradients restart after the step
+            check('xrd_adam_step', _cabi.lib().xrd_adam_step(
+                arr, 2, 1, torch.cuda.current_stream(self.dev).cuda_stream))
+
+    def end(self, optimize_frames):
+        """Write the optimised poses back into the Frame parameters (host)."""
+        rot, trans = self.rot.cpu(), self.trans.cpu()
+        fixed = self.fixed.cpu()
+        with torch.no_grad():
+            for i, f in enumerate(optimize_frames):
+                if not fixed[i]:
+                    f.pose.data_r.copy_(rot[i])
+                    f.pose.data_t.copy_(trans[i])

@@ -32,8 +32,9 @@ __device__ __forceinline__ void upd(float& p, float& g, float& m, float& v, cons
 
 __global__ void __launch_bounds__(256) k_adam(const Args A) {
   const XrdAdamTensor& T = A.t[blockIdx.y];
-  const float step_size = T.lr / T.bias_correction1;
-  const float inv_sqrt_bc2 = 1.0f / sqrtf(T.bias_correction2);
+  const float lr = T.dyn ? T.dyn[0] : T.lr;
+  const float step_size = lr / (T.dyn ? T.dyn[1] : T.bias_correction1);
+  const float inv_sqrt_bc2 = 1.0f / sqrtf(T.dyn ? T.dyn[2] : T.bias_correction2);
   const long long n = T.n;
   const bool vec = ((((uintptr_t)T.param | (uintptr_t)T.grad | (uintptr_t)T.exp_avg |
                       (uintptr_t)T.exp_avg_sq) & 15) == 0);
@@ -82,7 +83,7 @@ extern "C" int xrd_adam_step(const XrdAdamTensor* tensors, int n_tensors, int ze
     for (int i = 0; i < A.n; ++i) {
       A.t[i] = tensors[base + i];
       if (!A.t[i].param || !A.t[i].grad || !A.t[i].exp_avg || !A.t[i].exp_avg_sq) return XRD_E_NULL;
-      if (A.t[i].n < 0 || A.t[i].bias_correction1 <= 0.f || A.t[i].bias_correction2 <= 0.f)
+      if (A.t[i].n < 0 || (!A.t[i].dyn && (A.t[i].bias_correction1 <= 0.f || A.t[i].bias_correction2 <= 0.f)))
         return XRD_E_SHAPE;
       if (A.t[i].row_mask && A.t[i].row_len < 1) return XRD_E_SHAPE;
       if (A.t[i].n > nmax) nmax = A.t[i].n;

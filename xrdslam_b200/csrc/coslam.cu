@@ -75,6 +75,7 @@ struct SampleParams {
   const float *target_d, *lin_uniform, *lin_range, *lin_nodepth, *lin_full, *noise;
   float trunc, depth_trunc;
   uint64_t seed;
+  const uint64_t* seed_dev;
   float* z_vals;
   int* counts;
 };
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(128) k_sample(SampleParams p) {
           u = p.noise[(size_t)r * S + k];
         } else {
           float q[4];
-          philox4(p.seed, (uint64_t)r * S + k, q);
+          philox4(p.seed_dev ? *p.seed_dev : p.seed, (uint64_t)r * S + k, q);
           u = q[0];
         }
         zv = __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), u));
@@ -949,6 +950,8 @@ struct SmoothParams {
   const float* table;
   int n;  // lattice side (sample_points - 1)
   double voxel, off[3], rnd[3];
+  const float* rand_dev;  // DEVICE [6] overriding off/rnd (graph replay)
+  double offmax[3], margin;
   float* feat;    // [n^3, 32]
   float* d_table;
   double* loss_acc;
@@ -961,7 +964,9 @@ __device__ __forceinline__ void smooth_xn(const SmoothParams& p, int ix, int iy,
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     // pts = (coords + rand) * voxel + bb_min + offset ; then (pts - bb_min)/(bb_max-bb_min), all f64
-    double pt = ((double)(float)c[d] + p.rnd[d]) * p.voxel + p.g.bmin[d] + p.off[d];
+    const double rnd = p.rand_dev ? (double)p.rand_dev[3 + d] : p.rnd[d];
+    const double off = p.rand_dev ? (double)p.rand_dev[d] * p.offmax[d] + p.margin : p.off[d];
+    double pt = ((double)(float)c[d] + rnd) * p.voxel + p.g.bmin[d] + off;
     xn[d] = (float)((pt - p.g.bmin[d]) / (p.g.bmax[d] - p.g.bmin[d]));
   }
 }
@@ -1146,6 +1151,7 @@ extern "C" int xrd_coslam_step(const XrdRays* rays, const XrdHashGrid* grid,
   sp.target_d = rays->target_d; sp.lin_uniform = cfg->lin_uniform; sp.lin_range = cfg->lin_range;
   sp.lin_nodepth = cfg->lin_nodepth; sp.lin_full = cfg->lin_full; sp.noise = noise;
   sp.trunc = cfg->trunc; sp.depth_trunc = cfg->depth_trunc; sp.seed = cfg->seed;
+  sp.seed_dev = cfg->seed_dev;
   sp.z_vals = z_vals; sp.counts = counts;
   if (phase != 2) {
     k_sample<<<(R + 3) / 4, 128, 0, stream>>>(sp);
@@ -1221,10 +1227,10 @@ extern "C" size_t xrd_coslam_smoothness_workspace_bytes(int sample_points) {
   return 256 + n * n * n * 32 * sizeof(float);
 }
 
-extern "C" int xrd_coslam_smoothness(const XrdHashGrid* grid, int sample_points, double voxel_size,
-                                     double margin, float weight, const float* smooth_rand,
-                                     float* loss, float* d_table, float grad_scale,
-                                     void* workspace, size_t workspace_bytes, void* stream_) {
+static int smoothness_impl(const XrdHashGrid* grid, int sample_points, double voxel_size,
+                           double margin, float weight, const float* smooth_rand, bool rand_on_device,
+                           float* loss, float* d_table, float grad_scale,
+                           void* workspace, size_t workspace_bytes, void* stream_) {
   if (!grid || !grid->table || !smooth_rand || !loss || !workspace) return XRD_E_NULL;
   if (sample_points < 3) return XRD_E_SHAPE;
   if (workspace_bytes < xrd_coslam_smoothness_workspace_bytes(sample_points)) return XRD_E_WORKSPACE;
@@ -1240,9 +1246,12 @@ extern "C" int xrd_coslam_smoothness(const XrdHashGrid* grid, int sample_points,
   const double grid_size = (double)(sample_points - 1) * voxel_size;
   for (int d = 0; d < 3; ++d) {
     double offset_max = grid->bbox_max[d] - grid->bbox_min[d] - grid_size - 2.0 * margin;
-    p.off[d] = (double)smooth_rand[d] * offset_max + margin;
-    p.rnd[d] = (double)smooth_rand[3 + d];
+    p.offmax[d] = offset_max;
+    p.off[d] = rand_on_device ? 0.0 : (double)smooth_rand[d] * offset_max + margin;
+    p.rnd[d] = rand_on_device ? 0.0 : (double)smooth_rand[3 + d];
   }
+  p.margin = margin;
+  p.rand_dev = rand_on_device ? smooth_rand : nullptr;
   p.loss_acc = reinterpret_cast<double*>(workspace);
   p.feat = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
   p.d_table = d_table;
@@ -1258,6 +1267,22 @@ extern "C" int xrd_coslam_smoothness(const XrdHashGrid* grid, int sample_points,
   k_smooth_finalize<<<1, 32, 0, stream>>>(p.loss_acc, loss, (float)((double)weight / sp3));
   XRD_LAUNCH_CHECK();
   return XRD_OK;
+}
+
+extern "C" int xrd_coslam_smoothness(const XrdHashGrid* grid, int sample_points, double voxel_size,
+                                     double margin, float weight, const float* smooth_rand,
+                                     float* loss, float* d_table, float grad_scale,
+                                     void* workspace, size_t workspace_bytes, void* stream_) {
+  return smoothness_impl(grid, sample_points, voxel_size, margin, weight, smooth_rand, false, loss,
+                         d_table, grad_scale, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int xrd_coslam_smoothness_dev(const XrdHashGrid* grid, int sample_points, double voxel_size,
+                                         double margin, float weight, const float* smooth_rand,
+                                         float* loss, float* d_table, float grad_scale,
+                                         void* workspace, size_t workspace_bytes, void* stream_) {
+  return smoothness_impl(grid, sample_points, voxel_size, margin, weight, smooth_rand, true, loss,
+                         d_table, grad_scale, workspace, workspace_bytes, stream_);
 }
 
 extern "C" int xrd_hashgrid_encode(const XrdHashGrid* grid, const float* x, int n_points,

@@ -26,8 +26,8 @@ static __global__ void __launch_bounds__(256) k_dw(const DwParams Q) {
   const int tid = threadIdx.x, ta = tid >> 3, tb = tid & 7;
   const int p_lo = blockIdx.x * Q.chunk, p_hi = min(Q.P, p_lo + Q.chunk);
   if (p_lo >= p_hi) return;
-  for (int jb = 0; jb < Q.n_jobs; ++jb) {
-    const DwJob J = Q.jobs[jb];
+  {  // one (chunk of points, job) pair per CTA: grid = (chunks, n_jobs)
+    const DwJob J = Q.jobs[blockIdx.y];
     for (int a0 = 0; a0 < J.nA; a0 += 128) {
       const int na = min(128, J.nA - a0);
       float acc[4][4];
@@ -85,5 +85,21 @@ static __global__ void __launch_bounds__(256) k_dw(const DwParams Q) {
   }
 }
 
+// chunk: as many points per CTA as still give >= ~4 CTAs per SM over (chunks x jobs); a
+// multiple of the 64-point staging tile.  Fewer, longer chunks mean fewer red.global.add.
+static inline cudaError_t launch_dw(DwParams& Q, cudaStream_t stream) {
+  if (Q.n_jobs <= 0 || Q.P <= 0) return cudaSuccess;
+  const long long want = 4LL * 148;
+  long long chunks = (want + Q.n_jobs - 1) / Q.n_jobs;
+  if (chunks < 1) chunks = 1;
+  long long chunk = ((long long)Q.P + chunks - 1) / chunks;
+  chunk = (chunk + 63) / 64 * 64;
+  if (chunk < 128) chunk = 128;
+  if (chunk > 4096) chunk = 4096;
+  Q.chunk = (int)chunk;
+  dim3 grid((unsigned)((Q.P + Q.chunk - 1) / Q.chunk), (unsigned)Q.n_jobs);
+  k_dw<<<grid, 256, 0, stream>>>(Q);
+  return cudaGetLastError();
+}
 
 }  // namespace xrd

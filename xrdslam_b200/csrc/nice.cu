@@ -997,8 +997,7 @@ extern "C" int xrd_nice_step(const XrdRays* rays, const XrdNiceGrid grids[3],
     // embedder: dB[k][m] = sum_p pf[k] gm[m]  (A = gm rows, B = pf rows)
     add(rowp(row_gm(cd)), E, rowp(row_pf(cd)), 3, nullptr, G->B, E, 1, nullptr);
     if (Q.n_jobs > DW_MAX_JOBS) return XRD_E_SHAPE;
-    k_dw<<<(P + Q.chunk - 1) / Q.chunk, 256, 0, stream>>>(Q);
-    XRD_LAUNCH_CHECK();
+    XRD_CUDA_TRY(launch_dw(Q, stream));
   }
   if (grads->d_rays_o || grads->d_rays_d) {
     k_rayreduce<<<(R + 3) / 4, 128, 0, stream>>>(R, S, P, z, reinterpret_cast<const float*>(ws + L.dp),

@@ -557,8 +557,7 @@ int color_backward(ColorP C, const PWs& L, char* ws, int P, const XrdPointColorD
   auto dw_run = [&]() -> int {
     if (Dw.n_jobs == 0) return XRD_OK;
     if (Dw.n_jobs > DW_MAX_JOBS) return XRD_E_SHAPE;
-    k_dw<<<(Dw.P + Dw.chunk - 1) / Dw.chunk, 256, 0, stream>>>(Dw);
-    XRD_LAUNCH_CHECK();
+    XRD_CUDA_TRY(launch_dw(Dw, stream));
     return XRD_OK;
   };
   int st;

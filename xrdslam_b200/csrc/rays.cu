@@ -47,21 +47,44 @@ __global__ void __launch_bounds__(256) k_bwd(const P p) {
     for (int i = threadIdx.x; i < p.n_poses * 12; i += blockDim.x) acc[i] = 0.f;
     __syncthreads();
   }
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < p.R; r += gridDim.x * blockDim.x) {
-    const int id = pose_row(p, r);
-    const float d[3] = {p.dirs[r * 3], p.dirs[r * 3 + 1], p.dirs[r * 3 + 2]};
+  const int lane = threadIdx.x & 31;
+  // whole warps iterate together (r0 is warp-uniform) so the shuffles below are convergent
+  for (int r0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; r0 < p.R; r0 += gridDim.x * blockDim.x) {
+    const int r = r0 + lane;
+    const bool live = r < p.R;
+    const int id = live ? pose_row(p, r) : -1;
+    float v[12];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float gd = p.d_rays_d ? p.d_rays_d[r * 3 + c] : 0.f;
-      const float go = p.d_rays_o ? p.d_rays_o[r * 3 + c] : 0.f;
-      if (use_smem) {
-        float* a = acc + id * 12 + c * 4;
-        atomicAdd(a, gd * d[0]); atomicAdd(a + 1, gd * d[1]); atomicAdd(a + 2, gd * d[2]);
-        atomicAdd(a + 3, go);
-      } else {
-        float* a = p.d_poses + (size_t)id * 16 + c * 4;
-        atomicAdd(a, gd * d[0]); atomicAdd(a + 1, gd * d[1]); atomicAdd(a + 2, gd * d[2]);
-        atomicAdd(a + 3, go);
+      const float gd = (live && p.d_rays_d) ? p.d_rays_d[r * 3 + c] : 0.f;
+      const float go = (live && p.d_rays_o) ? p.d_rays_o[r * 3 + c] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) v[c * 4 + j] = live ? gd * p.dirs[r * 3 + j] : 0.f;
+      v[c * 4 + 3] = go;
+    }
+    // rays of one frame are contiguous: usually the whole warp shares the pose row ->
+    // shuffle-reduce and issue 12 atomics per warp instead of 12 per lane
+    const int id0 = __shfl_sync(0xffffffffu, id, 0);
+    const bool uniform = __all_sync(0xffffffffu, id == id0 || !live) && id0 >= 0;
+    if (uniform) {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+      }
+      if (lane == 0) {
+        float* a = use_smem ? acc + id0 * 12 : nullptr;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+          if (use_smem) atomicAdd(a + k, v[k]);
+          else atomicAdd(p.d_poses + (size_t)id0 * 16 + k, v[k]);
+        }
+      }
+    } else if (live) {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        if (use_smem) atomicAdd(acc + id * 12 + k, v[k]);
+        else atomicAdd(p.d_poses + (size_t)id * 16 + k, v[k]);
       }
     }
   }

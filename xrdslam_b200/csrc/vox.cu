@@ -995,8 +995,7 @@ extern "C" int xrd_voxfusion_render(const XrdRays* rays, const XrdVoxMap* map,
     add(ar(ra_h2()), W, gr(rg_dso() + W), 1, G->ws ? G->ws + (size_t)W * W : nullptr, W, 1, G->bs ? G->bs + W : nullptr);
     add(ar(ra_c1()), W, gr(rg_do()), 3, G->wc1, W, 1, G->bc1);
     if (D.n_jobs > DW_MAX_JOBS) return XRD_E_SHAPE;
-    k_dw<<<(Pn + D.chunk - 1) / D.chunk, 256, 0, stream>>>(D);
-    XRD_LAUNCH_CHECK();
+    XRD_CUDA_TRY(launch_dw(D, stream));
   }
   if (Q.need_dp) {
     k_rayreduce<<<(R + 3) / 4, 128, 0, stream>>>(R, mcfg->max_samples, Pn, march->smp_count,

@@ -311,7 +311,7 @@ class JointEncoding(Model):
             cfg.trainging_sdf_weight, cfg.trainging_fs_weight,
             ptr(self._lin_uniform), ptr(self._lin_range),
             ptr(self._lin_nodepth), ptr(self._lin_full),
-            seed, cfg.rays_per_tile, cfg.precision, 0, 0, None, None)
+            seed, cfg.rays_per_tile, cfg.precision, 0, 0, None, None, None)
         out = XrdCoslamOut(ptr(o['rgb']), ptr(o['depth']), ptr(o['disp_map']),
                            ptr(o['acc_map']), ptr(o['depth_var']),
                            ptr(o['z_vals']), ptr(o['raw']), ptr(o['losses']))

@@ -153,6 +153,7 @@ class NiceSLAM(Algorithm):
         self.set_stage(is_mapping, step, n_iters, coarse=coarse)
         if is_mapping:
             self.model.grid_processing(coarse=coarse)
+        self.model.freeze_map_grads = not is_mapping  # tracking optimises the pose only
         model_input = self.get_model_input(optimize_frames, is_mapping)
         model_outputs = self.model(model_input)
         loss_dict = self.model.get_loss_dict(model_outputs, model_input, is_mapping, self.stage)

@@ -289,9 +289,11 @@ class SparseVoxel(Model):
         fused = torch.is_grad_enabled() and target_s is not None and target_d is not None
         if fused:
             try:
+                emb, dec = self.embeddings, self.decoder.tensors()
+                if getattr(self, 'freeze_map_grads', False):  # tracking: pose gradients only
+                    emb, dec = emb.detach(), [t.detach() for t in dec]
                 losses, rgb, depth, ray_mask = _VoxStep.apply(
-                    self, target_s, target_d, noise, rays_o, rays_d, self.embeddings,
-                    *self.decoder.tensors())
+                    self, target_s, target_d, noise, rays_o, rays_d, emb, *dec)
             except RuntimeError as e:
                 if 'no ray hit' in str(e):
                     print('\n\n', '!' * 20, 'render_rays. no hit', '!' * 20, '\n\n')

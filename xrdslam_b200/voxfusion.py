@@ -78,6 +78,7 @@ class VoxFusion(Algorithm):
             self.create_voxels(cur_frame)
 
     def get_loss(self, optimize_frames, is_mapping, step=None, n_iters=None, coarse=False):
+        self.model.freeze_map_grads = not is_mapping  # tracking optimises the pose only
         model_input = self.get_model_input(optimize_frames, is_mapping)
         model_outputs = self.model(model_input)
         if model_outputs is None:  # no ray hit the map (sparse_voxel.py:197-199)
