@@ -155,26 +155,45 @@ __global__ void __launch_bounds__(128) k_sample(SampleParams p) {
 
 // --------------------------------------------------------------- encoding ---
 
-__device__ __forceinline__ uint32_t grid_index(const GridDev& g, int l, uint32_t x,
-                                               uint32_t y, uint32_t z) {
-  const uint32_t size = g.size[l];
+// Per-level constants, staged in SHARED memory: the level index differs between the lanes
+// of a warp in the hash backward (fragment layout: l = 4 nt + t) and in the smoothness
+// kernels, and a lane-varying index into the kernel-parameter constant bank serialises
+// (ncu source view: ~20 % of the samples of k_fused sat on these loads).
+struct __align__(16) Lv {
+  float scale;
+  uint32_t res, size, offset;
+  uint32_t hashed, magic, pad0, pad1;
+};
+
+__device__ __forceinline__ void load_levels(Lv* s, const GridDev& g) {
+  if (threadIdx.x < kL) {
+    const int l = threadIdx.x;
+    Lv v;
+    v.scale = g.scale[l]; v.res = g.res[l]; v.size = g.size[l]; v.offset = g.offset[l];
+    v.hashed = g.hashed[l]; v.magic = g.magic[l]; v.pad0 = v.pad1 = 0;
+    s[l] = v;
+  }
+}
+
+__device__ __forceinline__ uint32_t grid_index(const Lv& L, uint32_t x, uint32_t y, uint32_t z) {
+  const uint32_t size = L.size;
   uint32_t index;
-  if (g.hashed[l]) {
+  if (L.hashed) {
     index = x ^ (y * 2654435761u) ^ (z * 805459861u);
   } else {
     // dense stride walk (stride <= size is true for all three dims on a dense level)
-    const uint32_t res = g.res[l];
+    const uint32_t res = L.res;
     index = x + y * res + z * res * res;
   }
   // index % size: sizes of hashed levels are powers of two; in-range dense cells are < size
   if ((size & (size - 1)) == 0) {
     index &= size - 1;
   } else if (index >= size) {  // points outside the bound wrap around (tcnn does not clamp)
-    index -= __umulhi(index, g.magic[l]) * size;  // exact remainder or remainder + size
+    index -= __umulhi(index, L.magic) * size;  // exact remainder or remainder + size
     if (index >= size) index -= size;
     if (index >= size) index -= size;
   }
-  return index + g.offset[l];
+  return index + L.offset;
 }
 
 __device__ __forceinline__ void pos_fract(float x, float scale, float& w, uint32_t& c) {
@@ -247,8 +266,8 @@ __device__ __forceinline__ void blob_backward(const float xn[3], F dblob, float 
   }
 }
 
-__device__ __forceinline__ void encode_point(const Params& P, const float xn[3],
-                                             float* __restrict__ rec) {
+__device__ __forceinline__ void encode_point(const Params& P, const Lv* __restrict__ lv,
+                                             const float xn[3], float* __restrict__ rec) {
   const float2* __restrict__ tab = reinterpret_cast<const float2*>(P.table);
 #pragma unroll 4
   for (int l = 0; l < kL; ++l) {
@@ -259,13 +278,14 @@ __device__ __forceinline__ void encode_point(const Params& P, const float xn[3],
     }
     float w[3];
     uint32_t c[3];
-    pos_fract(xn[0], P.g.scale[l], w[0], c[0]);
-    pos_fract(xn[1], P.g.scale[l], w[1], c[1]);
-    pos_fract(xn[2], P.g.scale[l], w[2], c[2]);
+    const Lv L = lv[l];
+    pos_fract(xn[0], L.scale, w[0], c[0]);
+    pos_fract(xn[1], L.scale, w[1], c[1]);
+    pos_fract(xn[2], L.scale, w[2], c[2]);
     float2 v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      uint32_t idx = grid_index(P.g, l, c[0] + (k & 1), c[1] + ((k >> 1) & 1),
+      uint32_t idx = grid_index(L, c[0] + (k & 1), c[1] + ((k >> 1) & 1),
                                 c[2] + ((k >> 2) & 1));
       v[k] = __ldg(&tab[idx]);
     }
@@ -285,21 +305,23 @@ __device__ __forceinline__ void encode_point(const Params& P, const float xn[3],
 // one (point, level) item of the hash backward: scatter (g0,g1), optional d/dx.
 // Deliberately not inlined: 16 call sites per warp tile, and instruction-cache
 // footprint is what bounds this kernel (see profiles/).
-__device__ __noinline__ float3 hash_backward_item(const Params& P, int l, float x0, float x1,
+__device__ __noinline__ float3 hash_backward_item(const Params& P, const Lv* __restrict__ lv,
+                                                  int l, float x0, float x1,
                                                   float x2, float g0, float g1, bool need_dx,
                                                   bool scatter) {
   const float2* __restrict__ tab = reinterpret_cast<const float2*>(P.table);
   float w[3];
   uint32_t c[3];
   float dx[3] = {0.f, 0.f, 0.f};
-  const float sc = P.g.scale[l];
+  const Lv L = lv[l];
+  const float sc = L.scale;
   pos_fract(x0, sc, w[0], c[0]);
   pos_fract(x1, sc, w[1], c[1]);
   pos_fract(x2, sc, w[2], c[2]);
   uint32_t idx[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k)
-    idx[k] = grid_index(P.g, l, c[0] + (k & 1), c[1] + ((k >> 1) & 1), c[2] + ((k >> 2) & 1));
+    idx[k] = grid_index(L, c[0] + (k & 1), c[1] + ((k >> 1) & 1), c[2] + ((k >> 2) & 1));
   if (need_dx) {
     float t[8];  // <table entry, dfeat>
 #pragma unroll
@@ -484,6 +506,8 @@ __global__ void __launch_bounds__(256) k_fused(const Params P) {
   const int nwarps = blockDim.x >> 5;
   const int S = P.S;
 
+  __shared__ Lv s_lv[kL];
+  load_levels(s_lv, P.g);
   // stage transposed weights (zero padding included)
   for (int q = tid; q < SW_TOTAL; q += blockDim.x) sw[q] = 0.f;
   __syncthreads();
@@ -549,7 +573,7 @@ __global__ void __launch_bounds__(256) k_fused(const Params P) {
         xn[d] = normalise(pt, P.g.bmin[d], P.g.bmax[d]);
         xnb[tid * 3 + d] = xn[d];
       }
-      encode_point(P, xn, rec);
+      encode_point(P, s_lv, xn, rec);
     } else {
       // inactive rows must read as zero in every GEMM (k-dimension of the dW tiles)
 #pragma unroll 1
@@ -830,7 +854,7 @@ __global__ void __launch_bounds__(256) k_fused(const Params P) {
                 const int l = 4 * nt + t;
                 const float g0 = c[mt][nt][2 * h], g1 = c[mt][nt][2 * h + 1];
                 if (l < P.g.n_levels && (g0 != 0.f || g1 != 0.f)) {
-                  const float3 d3 = hash_backward_item(P, l, x3[0], x3[1], x3[2], g0, g1,
+                  const float3 d3 = hash_backward_item(P, s_lv, l, x3[0], x3[1], x3[2], g0, g1,
                                                        need_dx, map_grads);
                   hdx[mt][h][0] += d3.x; hdx[mt][h][1] += d3.y; hdx[mt][h][2] += d3.z;
                 }
@@ -973,6 +997,9 @@ __device__ __forceinline__ void smooth_xn(const SmoothParams& p, int ix, int iy,
 
 __global__ void __launch_bounds__(256) k_smooth_fwd(SmoothParams p) {
   const int n = p.n, N = n * n * n;
+  __shared__ Lv s_lv[kL];
+  load_levels(s_lv, p.g);
+  __syncthreads();
   const int q = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (point, level)
   const int pt = q / kL, l = q % kL;
   if (pt >= N || l >= p.g.n_levels) return;
@@ -982,11 +1009,12 @@ __global__ void __launch_bounds__(256) k_smooth_fwd(SmoothParams p) {
   const float2* tab = reinterpret_cast<const float2*>(p.table);
   float w[3];
   uint32_t c[3];
-  for (int d = 0; d < 3; ++d) pos_fract(xn[d], p.g.scale[l], w[d], c[d]);
+  const Lv L = s_lv[l];
+  for (int d = 0; d < 3; ++d) pos_fract(xn[d], L.scale, w[d], c[d]);
   float f0 = 0.f, f1 = 0.f;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    uint32_t idx = grid_index(p.g, l, c[0] + (k & 1), c[1] + ((k >> 1) & 1), c[2] + ((k >> 2) & 1));
+    uint32_t idx = grid_index(L, c[0] + (k & 1), c[1] + ((k >> 1) & 1), c[2] + ((k >> 2) & 1));
     float wk = ((k & 1) ? w[0] : 1.f - w[0]) * ((k & 2) ? w[1] : 1.f - w[1]) *
                ((k & 4) ? w[2] : 1.f - w[2]);
     float2 v = __ldg(&tab[idx]);
@@ -997,6 +1025,9 @@ __global__ void __launch_bounds__(256) k_smooth_fwd(SmoothParams p) {
 }
 
 __global__ void __launch_bounds__(256) k_smooth_bwd(SmoothParams p) {
+  __shared__ Lv s_lv[kL];
+  load_levels(s_lv, p.g);
+  __syncthreads();
   const int n = p.n, N = n * n * n;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const int pt = q / kL, l = q % kL;
@@ -1027,10 +1058,11 @@ __global__ void __launch_bounds__(256) k_smooth_bwd(SmoothParams p) {
       smooth_xn(p, ix, iy, iz, xn);
       float w[3];
       uint32_t c[3];
-      for (int d = 0; d < 3; ++d) pos_fract(xn[d], p.g.scale[l], w[d], c[d]);
+      const Lv L = s_lv[l];
+      for (int d = 0; d < 3; ++d) pos_fract(xn[d], L.scale, w[d], c[d]);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        uint32_t idx = grid_index(p.g, l, c[0] + (k & 1), c[1] + ((k >> 1) & 1), c[2] + ((k >> 2) & 1));
+        uint32_t idx = grid_index(L, c[0] + (k & 1), c[1] + ((k >> 1) & 1), c[2] + ((k >> 2) & 1));
         float wk = ((k & 1) ? w[0] : 1.f - w[0]) * ((k & 2) ? w[1] : 1.f - w[1]) *
                    ((k & 4) ? w[2] : 1.f - w[2]);
         red_add_v2(p.d_table + 2 * (size_t)idx, wk * g0, wk * g1);
@@ -1048,17 +1080,21 @@ __global__ void k_smooth_finalize(const double* acc, float* loss, float scale) {
 // hash encode only
 __global__ void __launch_bounds__(256) k_encode(GridDev g, const float* table, const float* x,
                                                 int n, float* feat, uint32_t* idx_out) {
+  __shared__ Lv s_lv[kL];
+  load_levels(s_lv, g);
+  __syncthreads();
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const int pt = q / kL, l = q % kL;
   if (pt >= n || l >= g.n_levels) return;
+  const Lv L = s_lv[l];
   const float2* tab = reinterpret_cast<const float2*>(table);
   float w[3];
   uint32_t c[3];
-  for (int d = 0; d < 3; ++d) pos_fract(x[pt * 3 + d], g.scale[l], w[d], c[d]);
+  for (int d = 0; d < 3; ++d) pos_fract(x[pt * 3 + d], L.scale, w[d], c[d]);
   float f0 = 0.f, f1 = 0.f;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    uint32_t idx = grid_index(g, l, c[0] + (k & 1), c[1] + ((k >> 1) & 1), c[2] + ((k >> 2) & 1));
+    uint32_t idx = grid_index(L, c[0] + (k & 1), c[1] + ((k >> 1) & 1), c[2] + ((k >> 2) & 1));
     if (idx_out) idx_out[((size_t)pt * g.n_levels + l) * 8 + k] = idx;
     float wk = ((k & 1) ? w[0] : 1.f - w[0]) * ((k & 2) ? w[1] : 1.f - w[1]) *
                ((k & 4) ? w[2] : 1.f - w[2]);
