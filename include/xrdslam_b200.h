@@ -100,6 +100,27 @@ int xrd_rays_pose_grads(int n_rays, const float* dirs_cam, const int64_t* pose_i
                         const float* d_rays_o, const float* d_rays_d, float* d_poses,
                         void* stream);
 
+/* Pixel sampling for a window of frames in one launch: gathers depth / colour of the chosen
+ * pixels of device-resident frames and builds the camera-frame directions
+ *   dirs = [(i - cx) / fx, -(j - cy) / fy, -1],  i = idx % (W1 - W0) + W0,  j = idx / (W1 - W0) + H0
+ * (slam/common/common.py:56-71 select_uv, :109-122 get_sample_uv, :45-47; the reference
+ * re-uploads both full images for every frame of every iteration).  indices: DEVICE
+ * [n_frames * n_per_frame] int64 into the cropped region (row-major), frame-major; the draw
+ * itself (torch.randint, with replacement, Q7) stays with the caller.  depth_imgs / rgb_imgs:
+ * HOST arrays of n_frames DEVICE pointers ([H,W] and [H,W,3] fp32).  Outputs are frame-major;
+ * pose_ids[q] = frame index (feeds xrd_rays_from_poses); ij: optional [n,2] (column, row). */
+typedef struct {
+  int n_frames;    /* <= 32 */
+  int n_per_frame;
+  int H, W;        /* image size */
+  int H0, H1, W0, W1; /* sampled region (Hedge / Wedge crop) */
+  float fx, fy, cx, cy;
+} XrdPixelSampleCfg;
+
+int xrd_sample_pixels(const XrdPixelSampleCfg* cfg, const float* const* depth_imgs,
+                      const float* const* rgb_imgs, const int64_t* indices, float* dirs,
+                      float* depth, float* rgb, int64_t* pose_ids, int64_t* ij, void* stream);
+
 /* c2w [n,4,4] from axis-angle `rot` [n,3] and translation `trans` [n,3] (all DEVICE):
  * slam/utils/opt_pose.py:51-55,77-95 (OptimizablePose.matrix / Rodrigues). */
 int xrd_pose_matrices(int n_poses, const float* rot, const float* trans, float* c2w, void* stream);
@@ -569,6 +590,10 @@ typedef struct {
   float* d_col_feats;      /* [N][32] ACCUMULATED; stage colour, or NULL                    */
   XrdPointColorDecoderGrads* color; /* colour-decoder gradients or NULL (decoder fixed)     */
 } XrdPointGrads;
+
+/* Measurement / parity hook: arithmetic of the wide-MLP GEMMs (Point-SLAM colour stage):
+ * 0 = fp32 SIMT, 1 = 3xTF32 tensor cores (default, fp32-level accuracy), 2 = plain TF32. */
+int xrd_debug_gemm_mode(int mode);
 
 size_t xrd_pointslam_workspace_bytes(int n_rays, int n_surface, int stage, int with_grads);
 

@@ -103,3 +103,40 @@ def test_coslam_model_input_on_device(cuda_dev):
     g0 = frames[0].pose.data_t.grad  # frame 0 is fixed (coslam.py:181-182): no gradient
     assert frames[0].fid == 0 and (g0 is None or g0.abs().sum() == 0)
     assert cur.pose.data_t.grad is not None and cur.pose.data_r.grad.abs().sum() > 0
+
+
+@pytest.mark.gpu
+def test_sample_window_matches_per_frame_get_samples(cuda_dev):
+    """xrd_sample_pixels + rays_from_poses for a 3-frame window == get_samples per frame with
+    the same pixel indices (common.py:188-227 as called by nice_slam.py:141-171)."""
+    import numpy as np
+    from xrdslam_b200.common import get_samples, sample_window
+    from xrdslam_b200.frame import Frame
+    from xrdslam_b200.opt_pose import pose_matrices
+    from xrdslam_b200.synthetic import make_sequence
+    cam, poses, fr = make_sequence(3, width=160, height=120)
+    frames = [Frame(k, fr[k][0], fr[k][1], init_pose=poses[k], rot_rep='quat') for k in range(3)]
+    n, He, We = 257, 7, 11
+    g = torch.Generator().manual_seed(0)
+    idx = torch.randint((120 - 2 * He) * (160 - 2 * We), (3 * n,), generator=g)
+    dimg = [torch.from_numpy(f.depth).to(cuda_dev) for f in frames]
+    cimg = [torch.from_numpy(f.rgb).to(cuda_dev) for f in frames]
+    P = pose_matrices([f.pose for f in frames])
+    ro, rd, d, c, i, j = sample_window(cam, dimg, cimg, P.to(cuda_dev), n, He, We,
+                                       indices=idx.to(cuda_dev), return_index=True)
+    (rd.sum() + 3 * ro.sum()).backward()
+    g_batched = [p.grad.clone() for f in frames for p in f.pose.parameters()]
+    for f in frames:
+        for p in f.pose.parameters():
+            p.grad = None
+    parts = [get_samples(cam, n, f.get_pose(), dimg[k], cimg[k], cuda_dev, Hedge=He, Wedge=We,
+                         return_index=True, indices=idx[k * n:(k + 1) * n].to(cuda_dev))
+             for k, f in enumerate(frames)]
+    cat = lambda q: torch.cat([p[q] for p in parts])
+    assert torch.equal(ro, cat(0)) and (rd - cat(1)).abs().max() < 1e-6
+    assert torch.equal(d, cat(2)) and torch.equal(c, cat(3))
+    assert torch.equal(i, cat(4)) and torch.equal(j, cat(5))
+    (cat(1).sum() + 3 * cat(0).sum()).backward()
+    g_frames = [p.grad for f in frames for p in f.pose.parameters()]
+    for a, b in zip(g_batched, g_frames):
+        assert (a - b).abs().max() <= 2e-5 * max(1.0, float(b.abs().max()))

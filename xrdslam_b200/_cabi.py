@@ -207,7 +207,15 @@ class XrdAdamTensor(C.Structure):
                 ('row_mask', vp), ('row_len', C.c_int), ('dyn', vp)]
 
 
+class XrdPixelSampleCfg(C.Structure):
+    _fields_ = [('n_frames', C.c_int), ('n_per_frame', C.c_int), ('H', C.c_int), ('W', C.c_int),
+                ('H0', C.c_int), ('H1', C.c_int), ('W0', C.c_int), ('W1', C.c_int),
+                ('fx', C.c_float), ('fy', C.c_float), ('cx', C.c_float), ('cy', C.c_float)]
+
+
 SYMBOLS = {
+    'xrd_sample_pixels': (C.c_int, [C.POINTER(XrdPixelSampleCfg), C.POINTER(vp), C.POINTER(vp), vp,
+                                    vp, vp, vp, vp, vp, vp]),
     'xrd_rays_from_poses': (C.c_int, [C.c_int, vp, vp, vp, C.c_int, vp, vp, vp]),
     'xrd_rays_pose_grads': (C.c_int, [C.c_int, vp, vp, C.c_int, vp, vp, vp, vp]),
     'xrd_adam_step': (C.c_int, [C.POINTER(XrdAdamTensor), C.c_int, C.c_int, vp]),
@@ -258,6 +266,7 @@ SYMBOLS = {
         C.POINTER(XrdVoxOut), C.POINTER(XrdVoxGrads), vp, C.c_size_t, vp]),
     'xrd_pointslam_knn_query': (C.c_int, [C.POINTER(XrdPointIndex), vp, vp, C.c_int, C.c_int,
                                           vp, vp, vp, vp]),
+    'xrd_debug_gemm_mode': (C.c_int, [C.c_int]),
     'xrd_pointslam_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     'xrd_pointslam_step': (C.c_int, [
         C.POINTER(XrdRays), C.POINTER(XrdPointIndex), C.POINTER(XrdPointFeats),

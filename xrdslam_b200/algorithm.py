@@ -96,6 +96,17 @@ class Algorithm():
                             self._frame_tensor(f, 'rgb'), device=self.device, Hedge=Hedge,
                             Wedge=Wedge, **kw) for f in frames]
 
+    def _sample_window(self, frames, n, Hedge=0, Wedge=0, return_index=False):
+        """All frames of the window at once: one batched pose evaluation, one H2D, three
+        launches (csrc/rays.cu) -- instead of ~150 ATen launches and a host Rodrigues /
+        quaternion chain per frame."""
+        from .common import sample_window
+        from .opt_pose import pose_matrices
+        poses = pose_matrices([f.pose for f in frames]).to(self.device)
+        return sample_window(self.camera, [self._frame_tensor(f, 'depth') for f in frames],
+                             [self._frame_tensor(f, 'rgb') for f in frames], poses, n, Hedge,
+                             Wedge, return_index=return_index)
+
     def _render_full(self, c2w, gt_depth, extra=None, per_pixel=None):
         """render_img body shared by the algorithms: all H*W rays in ray_batch_size chunks."""
         import numpy as np

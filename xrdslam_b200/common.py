@@ -62,6 +62,46 @@ def rays_from_poses(dirs_cam, pose_ids, poses):
     return poses[ids, :3, -1], rays_d
 
 
+def sample_window(camera, depth_imgs, rgb_imgs, poses, n, Hedge=0, Wedge=0, indices=None,
+                  return_index=False):
+    """get_samples for every frame of a window in THREE launches (draw, gather, rays):
+    depth_imgs / rgb_imgs: lists of device-resident [H,W] / [H,W,3] fp32 frames, poses:
+    [F,4,4] c2w on the device (differentiable).  Frame-major outputs
+    rays_o, rays_d [F*n,3], depth [F*n,1], colour [F*n,3] (+ i, j int64 column / row).
+    Mirrors common.py:188-227 applied per frame and concatenated (nice_slam.py:141-171)."""
+    import ctypes as C
+    from . import _cabi
+    dev = poses.device
+    if dev.type != 'cuda':
+        raise RuntimeError('xrdslam_b200 has no CPU path')
+    F = len(depth_imgs)
+    H, W = camera.height, camera.width
+    H0, H1, W0, W1 = Hedge, H - Hedge, Wedge, W - Wedge
+    if indices is None:
+        indices = torch.randint((H1 - H0) * (W1 - W0), (F * n, ), device=dev)
+    indices = indices.to(dev, torch.int64).contiguous()
+    tot = F * n
+    dirs = torch.empty(tot, 3, device=dev)
+    depth = torch.empty(tot, 1, device=dev)
+    rgb = torch.empty(tot, 3, device=dev)
+    ids = torch.empty(tot, dtype=torch.int64, device=dev)
+    ij = torch.empty(tot, 2, dtype=torch.int64, device=dev) if return_index else None
+    cfg = _cabi.XrdPixelSampleCfg(F, n, H, W, H0, H1, W0, W1, camera.fx, camera.fy, camera.cx,
+                                  camera.cy)
+    dp = (C.c_void_p * F)(*[_cabi.ptr(t) for t in depth_imgs])
+    cp = (C.c_void_p * F)(*[_cabi.ptr(t) for t in rgb_imgs])
+    with torch.cuda.device(dev):
+        st = _cabi.lib().xrd_sample_pixels(
+            C.byref(cfg), dp, cp, _cabi.ptr(indices), _cabi.ptr(dirs), _cabi.ptr(depth),
+            _cabi.ptr(rgb), _cabi.ptr(ids), _cabi.ptr(ij),
+            torch.cuda.current_stream(dev).cuda_stream)
+    _cabi.check('xrd_sample_pixels', st)
+    rays_o, rays_d = _PosedRays.apply(dirs, ids, poses)
+    if return_index:
+        return rays_o, rays_d, depth, rgb, ij[:, 0], ij[:, 1]
+    return rays_o, rays_d, depth, rgb
+
+
 def get_rays_from_uv(i, j, c2w, fx, fy, cx, cy, device):
     """rays for pixel coords (i: column, j: row); differentiable w.r.t. c2w."""
     c2w = _as_dev(c2w, device)

@@ -216,12 +216,9 @@ class CoSLAM(Algorithm):
             rays_o, rays_d = rays_from_poses(rays_all[..., :3], ids_all, poses_all)
             first_flag = len(self.keyframe_graph) == 0
         else:
-            rays_o, rays_d, target_d, target_s = get_samples(
-                self.camera, self.config.tracking_sample, cur_frame.get_pose(),
-                self._frame_tensor(cur_frame, 'depth'),
-                self._frame_tensor(cur_frame, 'rgb'), device=dev,
-                Hedge=self.config.tracking_Hedge,
-                Wedge=self.config.tracking_Wedge)
+            rays_o, rays_d, target_d, target_s = self._sample_window(
+                [cur_frame], self.config.tracking_sample, self.config.tracking_Hedge,
+                self.config.tracking_Wedge)
             first_flag = False
         return {
             'rays_o': rays_o.float(),

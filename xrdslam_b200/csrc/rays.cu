@@ -95,10 +95,67 @@ __global__ void __launch_bounds__(256) k_bwd(const P p) {
   }
 }
 
+// ---- pixel sampling for a window of frames -------------------
+constexpr int MAXF = 32;
+struct PixP {
+  XrdPixelSampleCfg c;
+  const float* depth[MAXF];
+  const float* rgb[MAXF];
+  const int64_t* indices;
+  float *dirs, *o_depth, *o_rgb;
+  int64_t *pose_ids, *ij;
+};
+
+__global__ void __launch_bounds__(256) k_pixels(const PixP p) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = p.c.n_per_frame;
+  if (q >= p.c.n_frames * n) return;
+  const int f = q / n;
+  const int w = p.c.W1 - p.c.W0;
+  const long long idx = p.indices[q];
+  const int ii = (int)(idx % w) + p.c.W0;       // column
+  const int jj = (int)(idx / w) + p.c.H0;       // row
+  const size_t pix = (size_t)jj * p.c.W + ii;
+  p.o_depth[q] = p.depth[f][pix];
+  const float* c = p.rgb[f] + pix * 3;
+  p.o_rgb[q * 3] = c[0]; p.o_rgb[q * 3 + 1] = c[1]; p.o_rgb[q * 3 + 2] = c[2];
+  // dirs = [(i - cx) / fx, -(j - cy) / fy, -1]   (common.py:45-47)
+  p.dirs[q * 3] = __fdiv_rn(__fsub_rn((float)ii, p.c.cx), p.c.fx);
+  p.dirs[q * 3 + 1] = -__fdiv_rn(__fsub_rn((float)jj, p.c.cy), p.c.fy);
+  p.dirs[q * 3 + 2] = -1.0f;
+  p.pose_ids[q] = f;
+  if (p.ij) { p.ij[q * 2] = ii; p.ij[q * 2 + 1] = jj; }
+}
+
 }  // namespace rays
 }  // namespace xrd
 
 using namespace xrd;
+
+extern "C" int xrd_sample_pixels(const XrdPixelSampleCfg* cfg, const float* const* depth_imgs,
+                                 const float* const* rgb_imgs, const int64_t* indices, float* dirs,
+                                 float* depth, float* rgb, int64_t* pose_ids, int64_t* ij,
+                                 void* stream) {
+  if (!cfg || !depth_imgs || !rgb_imgs || !indices || !dirs || !depth || !rgb || !pose_ids)
+    return XRD_E_NULL;
+  if (cfg->n_frames < 1 || cfg->n_frames > rays::MAXF || cfg->n_per_frame < 0) return XRD_E_SHAPE;
+  if (cfg->H0 < 0 || cfg->W0 < 0 || cfg->H1 > cfg->H || cfg->W1 > cfg->W || cfg->H1 <= cfg->H0 ||
+      cfg->W1 <= cfg->W0)
+    return XRD_E_SHAPE;
+  const int total = cfg->n_frames * cfg->n_per_frame;
+  if (total == 0) return XRD_OK;
+  rays::PixP p{};
+  p.c = *cfg;
+  for (int f = 0; f < cfg->n_frames; ++f) {
+    if (!depth_imgs[f] || !rgb_imgs[f]) return XRD_E_NULL;
+    p.depth[f] = depth_imgs[f]; p.rgb[f] = rgb_imgs[f];
+  }
+  p.indices = indices; p.dirs = dirs; p.o_depth = depth; p.o_rgb = rgb; p.pose_ids = pose_ids;
+  p.ij = ij;
+  rays::k_pixels<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
+  XRD_LAUNCH_CHECK();
+  return XRD_OK;
+}
 
 extern "C" int xrd_rays_from_poses(int n_rays, const float* dirs_cam, const int64_t* pose_ids,
                                    const float* poses, int n_poses, float* rays_o, float* rays_d,

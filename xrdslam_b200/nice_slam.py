@@ -122,19 +122,23 @@ class NiceSLAM(Algorithm):
             n = int(np.maximum(self.config.mapping_sample // len(optimize_frames),
                                self.config.min_sample_pixels))
             Hedge = Wedge = 0
-        parts = self._sample_frames(optimize_frames, n, Hedge, Wedge)
-        rays_o = torch.cat([p[0].float() for p in parts])
-        rays_d = torch.cat([p[1].float() for p in parts])
-        gt_depth = torch.cat([p[2].float() for p in parts])
-        gt_color = torch.cat([p[3].float() for p in parts])
+        rays_o, rays_d, gt_depth, gt_color = self._sample_window(optimize_frames, n, Hedge, Wedge)
         with torch.no_grad():  # pre-filter depths beyond the bounding box exit
             det_o = rays_o.detach().unsqueeze(-1)
             det_d = rays_d.detach().unsqueeze(-1)
-            t = (self.bounding_box.unsqueeze(0).to(self.device) - det_o) / det_d
+            t = (self._bbox_dev() - det_o) / det_d
             t, _ = torch.min(torch.max(t, dim=2)[0], dim=1)
-            inside = t >= gt_depth.squeeze(-1)
-        return {'rays_o': rays_o[inside], 'rays_d': rays_d[inside], 'target_s': gt_color[inside],
-                'target_d': gt_depth[inside], 'stage': self.stage, 'is_mapping': is_mapping}
+            keep = (t >= gt_depth.squeeze(-1)).nonzero().squeeze(1)  # one host sync
+        sel = lambda x: x.index_select(0, keep)
+        return {'rays_o': sel(rays_o), 'rays_d': sel(rays_d), 'target_s': sel(gt_color),
+                'target_d': sel(gt_depth), 'stage': self.stage, 'is_mapping': is_mapping}
+
+    def _bbox_dev(self):
+        b = self.__dict__.get('_bbox_dev_t')
+        if b is None:
+            b = self.bounding_box.unsqueeze(0).to(self.device)
+            self.__dict__['_bbox_dev_t'] = b
+        return b
 
     # nice_slam.py:204-216
     def set_stage(self, is_mapping, step, n_iters, coarse=False):

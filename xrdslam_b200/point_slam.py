@@ -159,21 +159,25 @@ class PointSLAM(Algorithm):
             Hedge = Wedge = 0
         if not is_mapping and cfg.tracking_sample_with_color_grad:
             raise NotImplementedError('tracking_sample_with_color_grad')
-        parts = self._sample_frames(optimize_frames, n, Hedge, Wedge, depth_filter=True,
-                                    return_index=True)
-        rays_o = torch.cat([p[0].float() for p in parts])
-        rays_d = torch.cat([p[1].float() for p in parts])
-        gt_depth = torch.cat([p[2].float() for p in parts])
-        gt_color = torch.cat([p[3].float() for p in parts])
+        rays_o, rays_d, gt_depth, gt_color, i, j = self._sample_window(
+            optimize_frames, n, Hedge, Wedge, return_index=True)
         r_query = None
         if cfg.use_dynamic_radius:
-            r_query = torch.cat([self.dynamic_r_query_allkeyframe[str(int(f.fid))][p[5], p[4]]
-                                 for f, p in zip(optimize_frames, parts)])
-        with torch.no_grad():  # outlier filter (Q9: batch-global median / max)
-            inside = gt_depth <= torch.minimum(10 * gt_depth.median(), 1.2 * torch.max(gt_depth))
-        return {'rays_o': rays_o[inside], 'rays_d': rays_d[inside], 'target_s': gt_color[inside],
-                'target_d': gt_depth[inside],
-                'batch_dynamic_r': r_query[inside] if r_query is not None else None,
+            maps = torch.stack([self.dynamic_r_query_allkeyframe[str(int(f.fid))]
+                                for f in optimize_frames])  # [F,H,W]
+            fidx = torch.arange(len(optimize_frames), device=self.device).repeat_interleave(n)
+            r_query = maps[fidx, j, i]
+        with torch.no_grad():
+            d = gt_depth.squeeze(-1)
+            valid = d > 0  # per-frame depth_filter=True of get_samples (common.py:214-221)
+            dv = d[valid]
+            # outlier filter on the depth-filtered batch (Q9: batch-global median / max)
+            keep = (valid & (d <= torch.minimum(10 * dv.median(), 1.2 * torch.max(dv)))
+                    ).nonzero().squeeze(1)
+        sel = lambda x: x.index_select(0, keep)
+        return {'rays_o': sel(rays_o), 'rays_d': sel(rays_d), 'target_s': sel(gt_color),
+                'target_d': sel(gt_depth),
+                'batch_dynamic_r': sel(r_query) if r_query is not None else None,
                 'stage': self.stage, 'is_mapping': is_mapping}
 
     def set_stage(self, is_mapping, step, n_iters):

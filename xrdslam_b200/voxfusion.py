@@ -59,11 +59,8 @@ class VoxFusion(Algorithm):
     # voxfusion.py:55-94
     def get_model_input(self, optimize_frames, is_mapping):
         n = self.config.mapping_sample if is_mapping else self.config.tracking_sample
-        parts = self._sample_frames(optimize_frames, n)
-        return {'rays_o': torch.cat([p[0].float() for p in parts]),
-                'rays_d': torch.cat([p[1].float() for p in parts]),
-                'target_s': torch.cat([p[3].float() for p in parts]),
-                'target_d': torch.cat([p[2].float() for p in parts])}
+        rays_o, rays_d, gt_depth, gt_color = self._sample_window(optimize_frames, n)
+        return {'rays_o': rays_o, 'rays_d': rays_d, 'target_s': gt_color, 'target_d': gt_depth}
 
     # voxfusion.py:96-106
     def create_voxels(self, frame):
