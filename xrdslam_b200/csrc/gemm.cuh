@@ -2,7 +2,8 @@
 // wide per-point MLPs whose layers are real GEMMs (Point-SLAM colour decoder: 128-wide trunk
 // over R*5 points and the per-neighbour MLP over 8x as many columns):
 //   C[m][n] = epi( sum_k A(m,k) * B[k][n] ),   A(m,k) = transA ? A[k*lda+m] : A[m*lda+k]
-//   epi(v)  = act(v + bias[m]);  act_out[m][n] = epi(v) (optional);  + addend[m][n] (optional);
+//   epi(v)  = act(v + bias[m]);  zeroed where relu_mask[m][n] <= 0 (optional: backward of a
+//             relu layer);  act_out[m][n] = epi(v) (optional);  + addend[m][n] (optional);
 //             accumulate: C += that.
 // 64 x 128 tile, BK = 16, 256 threads, 4 x 8 register tile per thread, fp32 FMA (exact-order
 // independent of the tile position, so results do not depend on how points are batched).
@@ -23,6 +24,7 @@ struct GemmArgs {
   const float* addend; int ldadd;
   float* act_out; int ldact;
   int accumulate;
+  const float* relu_mask; int ldmask;  // optional: result zeroed where relu_mask[m][n] <= 0
 };
 
 __device__ __forceinline__ float act_apply(float v, int act) {
@@ -106,6 +108,7 @@ static __global__ void __launch_bounds__(256) k_gemm(const GemmArgs G) {
       const int gn = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
       if (gn >= G.N) continue;
       float v = act_apply(acc[i][j] + bias, G.act);
+      if (G.relu_mask && !(G.relu_mask[(size_t)gm * G.ldmask + gn] > 0.f)) v = 0.f;
       if (G.act_out) G.act_out[(size_t)gm * G.ldact + gn] = v;
       if (G.addend) v += G.addend[(size_t)gm * G.ldadd + gn];
       float* c = G.C + (size_t)gm * G.ldc + gn;
@@ -241,6 +244,7 @@ static __global__ void __launch_bounds__(256, 2) k_gemm_tc(const GemmArgs G) {
           const int gn = n0 + warp * 16 + nt * 8 + 2 * t + j;
           if (gn >= G.N) continue;
           float v = act_apply(acc[mt][nt][2 * h + j] + bias, G.act);
+          if (G.relu_mask && !(G.relu_mask[(size_t)gm * G.ldmask + gn] > 0.f)) v = 0.f;
           if (G.act_out) G.act_out[(size_t)gm * G.ldact + gn] = v;
           if (G.addend) v += G.addend[(size_t)gm * G.ldadd + gn];
           float* c = G.C + (size_t)gm * G.ldc + gn;
@@ -250,8 +254,8 @@ static __global__ void __launch_bounds__(256, 2) k_gemm_tc(const GemmArgs G) {
   }
 }
 
-// 0 = fp32 SIMT, 1 = 3xTF32 tensor cores (default), 2 = plain TF32 tensor cores
-static int g_gemm_mode = 1;
+// 0 = fp32 SIMT, 1 = 3xTF32 tensor cores (default), 2 = plain TF32 tensor cores (cabi.cu)
+extern int g_gemm_mode;
 
 static inline cudaError_t launch_gemm(const GemmArgs& G, cudaStream_t stream) {
   if (G.M <= 0 || G.N <= 0) return cudaSuccess;

@@ -610,12 +610,6 @@ int color_backward(ColorP C, const PWs& L, char* ws, int P, const XrdPointColorD
 }
 }  // namespace
 
-extern "C" int xrd_debug_gemm_mode(int mode) {
-  if (mode < 0 || mode > 2) return XRD_E_SHAPE;
-  xrd::g_gemm_mode = mode;
-  return XRD_OK;
-}
-
 extern "C" size_t xrd_pointslam_workspace_bytes(int n_rays, int n_surface, int stage, int with_grads) {
   return pws(n_rays, n_surface, stage, with_grads).total;
 }

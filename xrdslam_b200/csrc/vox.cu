@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include "dw.cuh"
+#include "gemm.cuh"
 
 namespace xrd {
 namespace vox {
@@ -297,12 +298,6 @@ __global__ void __launch_bounds__(128) k_march_sample(const MarchParams P) {
 }
 
 // ----------------------------------------------------------- per point ---
-// transposed weights (forward) live in the workspace: [in][out] rows, float4-aligned
-struct WT {
-  const float *w0t, *w1t, *wst, *wc0t, *wc1t;  // [16][128] [128][128] [128][132] [144][128] [128][4]
-};
-constexpr int LDS_ = 132;  // sdf_out transposed: cols 0..127 = feat, col 128 = sdf
-
 struct PointParams {
   int P, Pp, R;
   const int *pt_ray, *pt_k;
@@ -311,7 +306,6 @@ struct PointParams {
   const float* centres; const int* vertex_idx; const float* emb;
   float voxel_size;
   XrdVoxDecoder dec;
-  WT wt;
   float* acts;        // rows of Pp: x16 | h1 128 | h2 128 | feat 128 | c1 128
   float* sdf; float* rgb;  // [P], [3][P]
   // backward
@@ -321,38 +315,24 @@ struct PointParams {
   float* dp;          // [3][P]
   int need_dp;
 };
-__host__ __device__ inline int ra_x() { return 0; }
-__host__ __device__ inline int ra_h1() { return EMB; }
-__host__ __device__ inline int ra_h2() { return EMB + W; }
-__host__ __device__ inline int ra_feat() { return EMB + 2 * W; }
-__host__ __device__ inline int ra_c1() { return EMB + 3 * W; }
+// activation rows: h1 | h2 | feat | x   (feat and x adjacent: the colour net's 144-wide input
+// cat[feat, x] is one GEMM operand) | c1
+__host__ __device__ inline int ra_h1() { return 0; }
+__host__ __device__ inline int ra_h2() { return W; }
+__host__ __device__ inline int ra_feat() { return 2 * W; }
+__host__ __device__ inline int ra_x() { return 3 * W; }
+__host__ __device__ inline int ra_c1() { return 3 * W + EMB; }
 __host__ __device__ inline int ra_rows() { return EMB + 4 * W; }
+// gradient rows: do 4 | dc1 128 | dso 129 (dsdf, dfeat) | dxc 16 (right after dfeat: the
+// 144-row output of wc0^T dc1) | d2 128 | d1 128 | dx 16
 __host__ __device__ inline int rg_do() { return 0; }
 __host__ __device__ inline int rg_dc1() { return 4; }
 __host__ __device__ inline int rg_dso() { return 4 + W; }        // row 0 = dsdf, 1..128 = dfeat
-__host__ __device__ inline int rg_d2() { return 4 + W + 129; }
-__host__ __device__ inline int rg_d1() { return 4 + 2 * W + 129; }
-__host__ __device__ inline int rg_rows() { return 4 + 3 * W + 129; }
-
-template <int NO>
-__device__ __forceinline__ void fman(float (&acc)[NO], float x, const float* __restrict__ row) {
-  const float4* w = reinterpret_cast<const float4*>(row);
-#pragma unroll
-  for (int j4 = 0; j4 < NO / 4; ++j4) {
-    const float4 v = __ldg(&w[j4]);
-    acc[4 * j4 + 0] = fmaf(x, v.x, acc[4 * j4 + 0]);
-    acc[4 * j4 + 1] = fmaf(x, v.y, acc[4 * j4 + 1]);
-    acc[4 * j4 + 2] = fmaf(x, v.z, acc[4 * j4 + 2]);
-    acc[4 * j4 + 3] = fmaf(x, v.w, acc[4 * j4 + 3]);
-  }
-}
-// acc[NO] += sum_{r<n} col[r*T] * M[r*ld + 0..NO)   (M in global memory, L1-resident broadcast)
-template <int NO>
-__device__ __noinline__ void dense(float (&acc)[NO], const float* __restrict__ M, int ld,
-                                   const float* __restrict__ col, int n) {
-#pragma unroll 4
-  for (int r = 0; r < n; ++r) fman<NO>(acc, col[r * T], M + (size_t)r * ld);
-}
+__host__ __device__ inline int rg_dxc() { return 4 + W + 129; }
+__host__ __device__ inline int rg_d2() { return 4 + W + 129 + EMB; }
+__host__ __device__ inline int rg_d1() { return 4 + 2 * W + 129 + EMB; }
+__host__ __device__ inline int rg_dx() { return 4 + 3 * W + 129 + EMB; }
+__host__ __device__ inline int rg_rows() { return 4 + 3 * W + 129 + 2 * EMB; }
 
 struct Corner {
   int vid[8];
@@ -379,220 +359,84 @@ __device__ __forceinline__ void corners(const PointParams& P, int r, int k, floa
   }
 }
 
-__global__ void __launch_bounds__(T) k_point_fwd(const PointParams P) {
-  extern __shared__ __align__(16) float smem[];
-  float* xs = smem + threadIdx.x;            // [16][T]
-  float* as = smem + EMB * T + threadIdx.x;  // [128][T]
-  float* bs = as + W * T;                    // [128][T]
-  for (int p = blockIdx.x * T + threadIdx.x; p < P.P; p += gridDim.x * T) {
-    const int r = P.pt_ray[p], k = P.pt_k[p];
-    float xyz[3];
-    Corner c;
-    corners(P, r, k, xyz, c);
-    float x[EMB];
+// ---- GEMM decoder path: gather / head / scatter kernels around gemm.cuh -------------------
+// x = trilinear embedding of the sample point -> activation rows ra_x
+__global__ void __launch_bounds__(T) k_vox_gather(const PointParams P) {
+  const int p = blockIdx.x * T + threadIdx.x;
+  if (p >= P.P) return;
+  float xyz[3];
+  Corner c;
+  corners(P, P.pt_ray[p], P.pt_k[p], xyz, c);
+  float x[EMB];
 #pragma unroll
-    for (int q = 0; q < EMB; ++q) x[q] = 0.f;
+  for (int q = 0; q < EMB; ++q) x[q] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4* e = reinterpret_cast<const float4*>(P.emb + (size_t)c.vid[i] * EMB);
+  for (int i = 0; i < 8; ++i) {
+    const float4* e = reinterpret_cast<const float4*>(P.emb + (size_t)c.vid[i] * EMB);
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const float4 v = __ldg(&e[q4]);
+      x[4 * q4 + 0] = fmaf(c.w[i], v.x, x[4 * q4 + 0]);
+      x[4 * q4 + 1] = fmaf(c.w[i], v.y, x[4 * q4 + 1]);
+      x[4 * q4 + 2] = fmaf(c.w[i], v.z, x[4 * q4 + 2]);
+      x[4 * q4 + 3] = fmaf(c.w[i], v.w, x[4 * q4 + 3]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < EMB; ++q) P.acts[(size_t)(ra_x() + q) * P.Pp + p] = x[q];
+}
+
+// d(colour logits) = d_rgb * c (1 - c) -> rows rg_do (+ a zero 4th row); dsdf -> row rg_dso
+__global__ void __launch_bounds__(256) k_vox_dout(const PointParams P) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P.P) return;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const float c = P.rgb[(size_t)q * P.P + p];
+    P.grads[(size_t)(rg_do() + q) * P.Pp + p] = P.d_rgb[(size_t)q * P.P + p] * c * (1.f - c);
+  }
+  P.grads[(size_t)(rg_do() + 3) * P.Pp + p] = 0.f;
+  P.grads[(size_t)rg_dso() * P.Pp + p] = P.d_sdf[p];
+}
+
+// dx (rows rg_dx) -> embedding scatter + d loss / d xyz
+__global__ void __launch_bounds__(T) k_vox_scatter(const PointParams P) {
+  const int p = blockIdx.x * T + threadIdx.x;
+  if (p >= P.P) return;
+  float dx[EMB];
+#pragma unroll
+  for (int q = 0; q < EMB; ++q) dx[q] = P.grads[(size_t)(rg_dx() + q) * P.Pp + p];
+  float xyz[3];
+  Corner c;
+  corners(P, P.pt_ray[p], P.pt_k[p], xyz, c);
+  float gp[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const size_t off = (size_t)c.vid[i] * EMB;
+    if (P.d_emb)
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4)
+        red_add_v4(P.d_emb + off + 4 * q4, c.w[i] * dx[4 * q4], c.w[i] * dx[4 * q4 + 1],
+                   c.w[i] * dx[4 * q4 + 2], c.w[i] * dx[4 * q4 + 3]);
+    if (P.need_dp) {
+      float s = 0.f;
+      const float4* e = reinterpret_cast<const float4*>(P.emb + off);
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
         const float4 v = __ldg(&e[q4]);
-        x[4 * q4 + 0] = fmaf(c.w[i], v.x, x[4 * q4 + 0]);
-        x[4 * q4 + 1] = fmaf(c.w[i], v.y, x[4 * q4 + 1]);
-        x[4 * q4 + 2] = fmaf(c.w[i], v.z, x[4 * q4 + 2]);
-        x[4 * q4 + 3] = fmaf(c.w[i], v.w, x[4 * q4 + 3]);
+        s += v.x * dx[4 * q4] + v.y * dx[4 * q4 + 1] + v.z * dx[4 * q4 + 2] + v.w * dx[4 * q4 + 3];
       }
+      const int qx = i >> 2, qy = (i >> 1) & 1, qz = i & 1;
+      const float wx = qx ? c.p[0] : 1.f - c.p[0], wy = qy ? c.p[1] : 1.f - c.p[1],
+                  wz = qz ? c.p[2] : 1.f - c.p[2];
+      gp[0] += (qx ? 1.f : -1.f) * wy * wz * s;
+      gp[1] += (qy ? 1.f : -1.f) * wx * wz * s;
+      gp[2] += (qz ? 1.f : -1.f) * wx * wy * s;
     }
-#pragma unroll
-    for (int q = 0; q < EMB; ++q) {
-      xs[q * T] = x[q];
-      if (P.acts) P.acts[(size_t)(ra_x() + q) * P.Pp + p] = x[q];
-    }
-    float acc[32];
-    // h1 = relu(W0 x + b0)  -> as
-#pragma unroll 1
-    for (int ch = 0; ch < W; ch += 32) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = P.dec.b0[ch + j];
-      dense<32>(acc, P.wt.w0t + ch, W, xs, EMB);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float v = fmaxf(acc[j], 0.f);
-        as[(ch + j) * T] = v;
-        if (P.acts) P.acts[(size_t)(ra_h1() + ch + j) * P.Pp + p] = v;
-      }
-    }
-    // h2 = relu(W1 h1 + b1) -> bs
-#pragma unroll 1
-    for (int ch = 0; ch < W; ch += 32) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = P.dec.b1[ch + j];
-      dense<32>(acc, P.wt.w1t + ch, W, as, W);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float v = fmaxf(acc[j], 0.f);
-        bs[(ch + j) * T] = v;
-        if (P.acts) P.acts[(size_t)(ra_h2() + ch + j) * P.Pp + p] = v;
-      }
-    }
-    // sdf_out: feat (cols 0..127 of wst) -> as ; sdf = col 128
-    float sdf = P.dec.bs[0];
-    for (int i = 0; i < W; ++i) sdf = fmaf(bs[i * T], __ldg(P.wt.wst + (size_t)i * LDS_ + W), sdf);
-#pragma unroll 1
-    for (int ch = 0; ch < W; ch += 32) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = P.dec.bs[1 + ch + j];
-      dense<32>(acc, P.wt.wst + ch, LDS_, bs, W);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        as[(ch + j) * T] = acc[j];
-        if (P.acts) P.acts[(size_t)(ra_feat() + ch + j) * P.Pp + p] = acc[j];
-      }
-    }
-    // c1 = relu(Wc0 [feat, x] + bc0) -> bs
-#pragma unroll 1
-    for (int ch = 0; ch < W; ch += 32) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = P.dec.bc0[ch + j];
-      dense<32>(acc, P.wt.wc0t + ch, W, as, W);
-      dense<32>(acc, P.wt.wc0t + (size_t)W * W + ch, W, xs, EMB);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float v = fmaxf(acc[j], 0.f);
-        bs[(ch + j) * T] = v;
-        if (P.acts) P.acts[(size_t)(ra_c1() + ch + j) * P.Pp + p] = v;
-      }
-    }
-    float o3[4] = {P.dec.bc1[0], P.dec.bc1[1], P.dec.bc1[2], 0.f};
-    for (int i = 0; i < W; ++i) {
-      const float4 w = __ldg(reinterpret_cast<const float4*>(P.wt.wc1t + (size_t)i * 4));
-      const float v = bs[i * T];
-      o3[0] = fmaf(v, w.x, o3[0]); o3[1] = fmaf(v, w.y, o3[1]); o3[2] = fmaf(v, w.z, o3[2]);
-    }
-    P.sdf[p] = sdf;
-#pragma unroll
-    for (int q = 0; q < 3; ++q) P.rgb[(size_t)q * P.P + p] = sigmoidf_acc(o3[q]);
   }
-}
-
-__global__ void __launch_bounds__(T) k_point_bwd(const PointParams P) {
-  extern __shared__ __align__(16) float smem[];
-  float* as = smem + threadIdx.x;  // [128][T]
-  float* bs = as + W * T;          // [128][T]
-  for (int p = blockIdx.x * T + threadIdx.x; p < P.P; p += gridDim.x * T) {
-    const int r = P.pt_ray[p], k = P.pt_k[p];
-    auto act = [&](int row) { return P.acts[(size_t)row * P.Pp + p]; };
-    auto gout = [&](int row, float v) { P.grads[(size_t)row * P.Pp + p] = v; };
-    // colour head: rgb = sigmoid(o)
-    float dov[3];
+  if (P.need_dp)
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const float c = P.rgb[(size_t)q * P.P + p];
-      dov[q] = P.d_rgb[(size_t)q * P.P + p] * c * (1.f - c);
-      gout(rg_do() + q, dov[q]);
-    }
-    gout(rg_do() + 3, 0.f);
-    for (int i = 0; i < W; ++i) {
-      float g = dov[0] * __ldg(P.dec.wc1 + i) + dov[1] * __ldg(P.dec.wc1 + W + i) +
-                dov[2] * __ldg(P.dec.wc1 + 2 * W + i);
-      g = act(ra_c1() + i) > 0.f ? g : 0.f;
-      as[i * T] = g;
-      gout(rg_dc1() + i, g);
-    }
-    float acc[32];
-    float dxc[EMB];
-    // d[feat, x] = Wc0^T dprec1 : feat part -> bs, x part -> registers
-#pragma unroll 1
-    for (int ch = 0; ch < W; ch += 32) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-      dense<32>(acc, P.dec.wc0 + ch, W + EMB, as, W);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) { bs[(ch + j) * T] = acc[j]; gout(rg_dso() + 1 + ch + j, acc[j]); }
-    }
-#pragma unroll
-    for (int j = 0; j < EMB; ++j) dxc[j] = 0.f;
-    dense<EMB>(dxc, P.dec.wc0 + W, W + EMB, as, W);
-    const float dsdf = P.d_sdf[p];
-    gout(rg_dso(), dsdf);
-    // dh2 = Ws^T [dsdf, dfeat] masked -> as
-#pragma unroll 1
-    for (int ch = 0; ch < W; ch += 32) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = dsdf * __ldg(P.dec.ws + ch + j);
-      dense<32>(acc, P.dec.ws + W + ch, W, bs, W);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float g = act(ra_h2() + ch + j) > 0.f ? acc[j] : 0.f;
-        as[(ch + j) * T] = g;
-        gout(rg_d2() + ch + j, g);
-      }
-    }
-    // dh1 = W1^T dpre2 masked -> bs
-#pragma unroll 1
-    for (int ch = 0; ch < W; ch += 32) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-      dense<32>(acc, P.dec.w1 + ch, W, as, W);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float g = act(ra_h1() + ch + j) > 0.f ? acc[j] : 0.f;
-        bs[(ch + j) * T] = g;
-        gout(rg_d1() + ch + j, g);
-      }
-    }
-    // dx = W0^T dpre1 + colour-path part
-    float dx[EMB];
-#pragma unroll
-    for (int j = 0; j < EMB; ++j) dx[j] = dxc[j];
-    dense<EMB>(dx, P.dec.w0, EMB, bs, W);
-    // embedding scatter + d loss / d xyz
-    float xyz[3];
-    Corner c;
-    corners(P, r, k, xyz, c);
-    float gp[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const size_t off = (size_t)c.vid[i] * EMB;
-      if (P.d_emb)
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4)
-          red_add_v4(P.d_emb + off + 4 * q4, c.w[i] * dx[4 * q4], c.w[i] * dx[4 * q4 + 1],
-                     c.w[i] * dx[4 * q4 + 2], c.w[i] * dx[4 * q4 + 3]);
-      if (P.need_dp) {
-        float s = 0.f;
-        const float4* e = reinterpret_cast<const float4*>(P.emb + off);
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const float4 v = __ldg(&e[q4]);
-          s += v.x * dx[4 * q4] + v.y * dx[4 * q4 + 1] + v.z * dx[4 * q4 + 2] + v.w * dx[4 * q4 + 3];
-        }
-        const int qx = i >> 2, qy = (i >> 1) & 1, qz = i & 1;
-        const float wx = qx ? c.p[0] : 1.f - c.p[0], wy = qy ? c.p[1] : 1.f - c.p[1],
-                    wz = qz ? c.p[2] : 1.f - c.p[2];
-        gp[0] += (qx ? 1.f : -1.f) * wy * wz * s;
-        gp[1] += (qy ? 1.f : -1.f) * wx * wz * s;
-        gp[2] += (qz ? 1.f : -1.f) * wx * wy * s;
-      }
-    }
-    if (P.need_dp)
-#pragma unroll
-      for (int d = 0; d < 3; ++d) P.dp[(size_t)d * P.P + p] = gp[d] / P.voxel_size;
-  }
-}
-
-__global__ void k_transpose_weights(XrdVoxDecoder d, float* w0t, float* w1t, float* wst,
-                                    float* wc0t, float* wc1t) {
-  const int n = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
-  for (int q = t0; q < EMB * W; q += n) { const int i = q / W, j = q % W; w0t[q] = d.w0[j * EMB + i]; }
-  for (int q = t0; q < W * W; q += n) { const int i = q / W, j = q % W; w1t[q] = d.w1[j * W + i]; }
-  for (int q = t0; q < W * LDS_; q += n) {
-    const int i = q / LDS_, j = q % LDS_;  // col j: feat j (torch row j+1) for j < 128, sdf (row 0) at 128
-    wst[q] = j < W ? d.ws[(j + 1) * W + i] : (j == W ? d.ws[i] : 0.f);
-  }
-  for (int q = t0; q < (W + EMB) * W; q += n) { const int i = q / W, j = q % W; wc0t[q] = d.wc0[j * (W + EMB) + i]; }
-  for (int q = t0; q < W * 4; q += n) { const int i = q / 4, k = q % 4; wc1t[q] = k < 3 ? d.wc1[k * W + i] : 0.f; }
+    for (int d = 0; d < 3; ++d) P.dp[(size_t)d * P.P + p] = gp[d] / P.voxel_size;
 }
 
 __global__ void __launch_bounds__(128) k_points(int R, const int* count, const int* base,
@@ -860,7 +704,7 @@ extern "C" int xrd_voxfusion_march(const XrdRays* rays, const XrdVoxMap* map,
 
 namespace {
 struct VWs {
-  size_t hdr, pt_ray, pt_k, wt, sdf, rgb, d_sdf, d_rgb, dp, acts, grads, total;
+  size_t hdr, pt_ray, pt_k, sdf, rgb, d_sdf, d_rgb, dp, acts, grads, total;
 };
 VWs vws(int R, int Pn, int with_grads) {
   VWs L;
@@ -869,12 +713,11 @@ VWs vws(int R, int Pn, int with_grads) {
   auto take = [&](size_t b) { size_t o = q; q += align_up(b, 256); return o; };
   L.hdr = take(256);
   L.pt_ray = take(P * 4); L.pt_k = take(P * 4);
-  L.wt = take(sizeof(float) * (EMB * W + W * W + W * LDS_ + (W + EMB) * W + W * 4));
   L.sdf = take(P * 4); L.rgb = take(3 * P * 4);
-  L.d_sdf = L.d_rgb = L.dp = L.acts = L.grads = 0;
+  L.d_sdf = L.d_rgb = L.dp = L.grads = 0;
+  L.acts = take((size_t)ra_rows() * Pp * 4);  // the GEMM decoder path keeps activations in HBM
   if (with_grads) {
     L.d_sdf = take(P * 4); L.d_rgb = take(3 * P * 4); L.dp = take(3 * P * 4);
-    L.acts = take((size_t)ra_rows() * Pp * 4);
     L.grads = take((size_t)rg_rows() * Pp * 4);
   }
   (void)R;
@@ -908,37 +751,39 @@ extern "C" int xrd_voxfusion_render(const XrdRays* rays, const XrdVoxMap* map,
   double* loss_acc = reinterpret_cast<double*>(ws + L.hdr + 64);
   int* pt_ray = reinterpret_cast<int*>(ws + L.pt_ray);
   int* pt_k = reinterpret_cast<int*>(ws + L.pt_k);
-  float* wt = reinterpret_cast<float*>(ws + L.wt);
   XRD_CUDA_TRY(cudaMemsetAsync(ws + L.hdr, 0, 256, stream));
   k_points<<<(R + 127) / 128, 128, 0, stream>>>(R, march->smp_count, march->smp_base, pt_ray, pt_k);
   XRD_LAUNCH_CHECK();
-  WT t;
-  t.w0t = wt; t.w1t = t.w0t + EMB * W; t.wst = t.w1t + W * W; t.wc0t = t.wst + W * LDS_;
-  t.wc1t = t.wc0t + (W + EMB) * W;
-  k_transpose_weights<<<64, 256, 0, stream>>>(*dec, (float*)t.w0t, (float*)t.w1t, (float*)t.wst,
-                                              (float*)t.wc0t, (float*)t.wc1t);
-  XRD_LAUNCH_CHECK();
-
   PointParams Q;
   Q.P = Pn; Q.Pp = Pp; Q.R = R; Q.pt_ray = pt_ray; Q.pt_k = pt_k;
   Q.rays_o = rays->rays_o; Q.rays_d = rays->rays_d;
   Q.smp_depth = march->smp_depth; Q.smp_idx = march->smp_idx; Q.scap = mcfg->max_samples;
   Q.centres = map->centres; Q.vertex_idx = map->vertex_idx; Q.emb = map->embeddings;
-  Q.voxel_size = cfg->voxel_size; Q.dec = *dec; Q.wt = t;
-  Q.acts = grads ? reinterpret_cast<float*>(ws + L.acts) : nullptr;
+  Q.voxel_size = cfg->voxel_size; Q.dec = *dec;
+  Q.acts = reinterpret_cast<float*>(ws + L.acts);
   Q.sdf = reinterpret_cast<float*>(ws + L.sdf); Q.rgb = reinterpret_cast<float*>(ws + L.rgb);
   Q.d_sdf = nullptr; Q.d_rgb = nullptr; Q.grads = nullptr; Q.d_emb = nullptr; Q.dp = nullptr;
   Q.need_dp = 0;
-  const int sms = num_sms();
-  const int tiles = (Pn + T - 1) / T;
-  const int gridx = tiles < sms ? tiles : sms;
-  const size_t smem_f = sizeof(float) * (size_t)(EMB + 2 * W) * T;
-  XRD_CUDA_TRY(cudaFuncSetAttribute(k_point_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+  // decoder (decoder_voxfusion.py:122-149) as GEMMs over [feature][point] rows
+  auto ar = [&](int row) { return Q.acts + (size_t)row * Pp; };
+#define XRD_GEMM(...)                                         \
+  do {                                                        \
+    GemmArgs g_ = __VA_ARGS__;                                \
+    XRD_CUDA_TRY(launch_gemm(g_, stream));                    \
+  } while (0)
   {
     KernelTimer kt(stream);
-    k_point_fwd<<<gridx, T, smem_f, stream>>>(Q);
+    k_vox_gather<<<(Pn + T - 1) / T, T, 0, stream>>>(Q);
   }
   XRD_LAUNCH_CHECK();
+  XRD_GEMM({W, Pn, EMB, dec->w0, EMB, 0, ar(ra_x()), Pp, ar(ra_h1()), Pp, dec->b0, ACT_RELU});
+  XRD_GEMM({W, Pn, W, dec->w1, W, 0, ar(ra_h1()), Pp, ar(ra_h2()), Pp, dec->b1, ACT_RELU});
+  // sdf_out: torch row 0 = sdf, rows 1..128 = feat
+  XRD_GEMM({W, Pn, W, dec->ws + W, W, 0, ar(ra_h2()), Pp, ar(ra_feat()), Pp, dec->bs + 1, ACT_NONE});
+  XRD_GEMM({1, Pn, W, dec->ws, W, 0, ar(ra_h2()), Pp, Q.sdf, Pn, dec->bs, ACT_NONE});
+  // colour: relu(wc0 [feat, x] + bc0) -> sigmoid(wc1 . + bc1)
+  XRD_GEMM({W, Pn, W + EMB, dec->wc0, W + EMB, 0, ar(ra_feat()), Pp, ar(ra_c1()), Pp, dec->bc0, ACT_RELU});
+  XRD_GEMM({3, Pn, W, dec->wc1, W, 0, ar(ra_c1()), Pp, Q.rgb, Pn, dec->bc1, ACT_SIGMOID});
 
   RayParams Y;
   Y.R = R; Y.scap = mcfg->max_samples; Y.S = cfg->s_max; Y.Rh = cfg->n_hit_rays; Y.P = Pn;
@@ -967,9 +812,36 @@ extern "C" int xrd_voxfusion_render(const XrdRays* rays, const XrdVoxMap* map,
   Q.d_emb = grads->d_embeddings;
   Q.dp = reinterpret_cast<float*>(ws + L.dp);
   Q.need_dp = (grads->d_rays_o || grads->d_rays_d) ? 1 : 0;
-  const size_t smem_b = sizeof(float) * (size_t)(2 * W) * T;
-  XRD_CUDA_TRY(cudaFuncSetAttribute(k_point_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-  k_point_bwd<<<gridx, T, smem_b, stream>>>(Q);
+  auto gr_ = [&](int row) { return Q.grads + (size_t)row * Pp; };
+  k_vox_dout<<<(Pn + 255) / 256, 256, 0, stream>>>(Q);
+  XRD_LAUNCH_CHECK();
+  {
+    GemmArgs g{};  // dc1 = relu'(c1) * (wc1^T do)
+    g.M = W; g.N = Pn; g.K = 3; g.A = dec->wc1; g.lda = W; g.transA = 1; g.B = gr_(rg_do()); g.ldb = Pp;
+    g.C = gr_(rg_dc1()); g.ldc = Pp; g.relu_mask = ar(ra_c1()); g.ldmask = Pp;
+    XRD_CUDA_TRY(launch_gemm(g, stream));
+    // d[feat, x] = wc0^T dc1  (144 rows: dfeat | dxc)
+    g = GemmArgs{};
+    g.M = W + EMB; g.N = Pn; g.K = W; g.A = dec->wc0; g.lda = W + EMB; g.transA = 1;
+    g.B = gr_(rg_dc1()); g.ldb = Pp; g.C = gr_(rg_dso() + 1); g.ldc = Pp;
+    XRD_CUDA_TRY(launch_gemm(g, stream));
+    // d2 = relu'(h2) * (ws^T [dsdf, dfeat])
+    g = GemmArgs{};
+    g.M = W; g.N = Pn; g.K = W + 1; g.A = dec->ws; g.lda = W; g.transA = 1; g.B = gr_(rg_dso());
+    g.ldb = Pp; g.C = gr_(rg_d2()); g.ldc = Pp; g.relu_mask = ar(ra_h2()); g.ldmask = Pp;
+    XRD_CUDA_TRY(launch_gemm(g, stream));
+    // d1 = relu'(h1) * (w1^T d2)
+    g = GemmArgs{};
+    g.M = W; g.N = Pn; g.K = W; g.A = dec->w1; g.lda = W; g.transA = 1; g.B = gr_(rg_d2()); g.ldb = Pp;
+    g.C = gr_(rg_d1()); g.ldc = Pp; g.relu_mask = ar(ra_h1()); g.ldmask = Pp;
+    XRD_CUDA_TRY(launch_gemm(g, stream));
+    // dx = w0^T d1 + dxc
+    g = GemmArgs{};
+    g.M = EMB; g.N = Pn; g.K = W; g.A = dec->w0; g.lda = EMB; g.transA = 1; g.B = gr_(rg_d1()); g.ldb = Pp;
+    g.C = gr_(rg_dx()); g.ldc = Pp; g.addend = gr_(rg_dxc()); g.ldadd = Pp;
+    XRD_CUDA_TRY(launch_gemm(g, stream));
+  }
+  k_vox_scatter<<<(Pn + T - 1) / T, T, 0, stream>>>(Q);
   XRD_LAUNCH_CHECK();
 
   if (grads->d_decoder) {
