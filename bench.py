@@ -202,9 +202,10 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- value: batches resident in HBM -----------------------
-    # N = 1: the mapping iteration is ONE CUDA graph (xrdslam_b200/coslam_graph.py) replayed
-    # from a device-resident batch; N > 1: sharded autograd path + NCCL all-reduce.
-    use_graph = world == 1 and algo._graph_ok(frames)
+    # the mapping iteration is a CUDA graph (xrdslam_b200/coslam_graph.py) replayed from a
+    # device-resident batch; N > 1: three captured segments around two NCCL all-reduces
+    # (loss-normaliser counts, then ONE flat bucket of all gradients + loss terms).
+    use_graph = algo._graph_ok(frames)
     sess = None
     batches = []
     if use_graph:
@@ -363,11 +364,13 @@ def run_ours(args):
                     'd2h_bytes_per_step': d2h,
                     'path': ('CoSLAM.mapping_session(frames).step(): host pinned ray bank, '
                              'random.sample, H2D, one CUDA graph (poses, rays, sample, fused '
-                             'fwd/loss/bwd, smoothness, pose grads, Adam), loss.item()')
+                             'fwd/loss/bwd, smoothness, pose grads, Adam)' +
+                             (' in 3 captured segments around 2 NCCL all-reduces' if world > 1 else '') +
+                             ', loss.item()')
                     if use_graph else
                     ('CoSLAM.get_loss (host pinned ray bank, random.sample, H2D) -> '
                      'loss.backward -> all-reduce -> Optimizers.optimizer_step_all -> loss.item()')},
-            'gpu_launches': K * (11 if use_graph else 9) + (K // 5 if use_graph else 0),
+            'gpu_launches': K * ((11 if world == 1 else 12) if use_graph else 9) + (K // 5 if use_graph else 0),
             'gpu_launches_note': ('per step (one graph): pose::k_fwd, rays::k_fwd, k_sample, '
                                   'k_fused<true>, k_finalize, k_smooth_fwd, k_smooth_bwd, '
                                   'k_smooth_finalize, rays::k_bwd, pose::k_bwd, k_adam (+ k_adam on '

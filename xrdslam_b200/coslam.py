@@ -231,9 +231,8 @@ class CoSLAM(Algorithm):
     # ---- CUDA-graph mapping (row f1) -------------------------------------------------
     def _graph_ok(self, optimize_frames):
         cfg = self.config
-        dp = getattr(self.model, 'dp', None)
         if not (cfg.graph_mapping and self.device.type == 'cuda' and cfg.separate_LR
-                and cfg.rot_rep == 'axis_angle') or (dp is not None and dp.world > 1):
+                and cfg.rot_rep == 'axis_angle'):
             return False
         n_kf = len(self.keyframe_graph)
         return n_kf == 0 or len(optimize_frames) == n_kf + 1  # ids index the window 1:1

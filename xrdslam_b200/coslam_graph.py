@@ -49,7 +49,6 @@ class MappingGraphSession:
         self.d_rays_o, self.d_rays_d = z(R, 3), z(R, 3)
         self.out = dict(rgb=z(R, 3), depth=z(R), disp=z(R), acc=z(R), var=z(R), z_vals=z(R, S),
                         raw=z(R, S, 4))
-        self.losses, self.smooth_loss = z(4), z(1)
         lib = _cabi.lib()
         self.ws = torch.empty(lib.xrd_coslam_workspace_bytes(R, S), dtype=torch.uint8, device=dev)
         self.ws_s = torch.empty(lib.xrd_coslam_smoothness_workspace_bytes(cfg.trainging_smooth_pts),
@@ -68,10 +67,27 @@ class MappingGraphSession:
             if not isinstance(opt, FusedAdam) or len(opt.param_groups) != 1:
                 raise RuntimeError('graph mapping needs FusedAdam model optimizers')
             self.opt_groups.append((opt, list(opt.param_groups[0]['params'])))
-        self.grads = {}
-        for _, params in self.opt_groups:
-            for p in params:
-                self.grads[p] = torch.zeros_like(p)
+        dp = getattr(model, 'dp', None)
+        self.dp = dp if (dp is not None and dp.world > 1) else None
+        self.world = self.dp.world if self.dp is not None else 1
+        self.rank = self.dp.rank if self.dp is not None else 0
+        # ONE flat bucket [table grad | decoder grads | per-iteration pose grads | 5 loss terms]:
+        # zeroed by one memset, all-reduced by one NCCL call when mapping rays are sharded
+        plist = [p for _, params in self.opt_groups for p in params]
+        sizes = [(p.numel() + 3) // 4 * 4 for p in plist]  # float4-aligned slots
+        n_pose = (n_poses * 3 + 3) // 4 * 4
+        total = sum(sizes) + 2 * n_pose + 8
+        self.flat = torch.zeros(total, **f32)
+        self.grads, off = {}, 0
+        for p, sz in zip(plist, sizes):
+            self.grads[p] = self.flat[off:off + p.numel()].view_as(p)
+            off += sz
+        self.d_rot_it = self.flat[off:off + n_poses * 3].view(n_poses, 3)
+        self.d_trans_it = self.flat[off + n_pose:off + n_pose + n_poses * 3].view(n_poses, 3)
+        off += 2 * n_pose
+        self.losses, self.smooth_loss = self.flat[off:off + 4], self.flat[off + 4:off + 5]
+        self.counts = torch.zeros(4, dtype=torch.int32, device=dev)
+        self._gen = torch.Generator().manual_seed(977) if self.world > 1 else None
         self.pose_state = None
         # Adam state must exist BEFORE capture: tensors created while capturing come from the
         # graph's private pool and their zero-fill would be replayed every iteration
@@ -82,7 +98,7 @@ class MappingGraphSession:
                     st['step'] = torch.tensor(0.0)
                     st['exp_avg'] = torch.zeros_like(p)
                     st['exp_avg_sq'] = torch.zeros_like(p)
-        self.graph = torch.cuda.CUDAGraph()
+        self.graphs = []
         self._capture()
 
     # ------------------------------------------------------------------ capture ---
@@ -102,13 +118,32 @@ class MappingGraphSession:
                 descs.append(a)
         return descs
 
-    def _sequence(self, stream, with_adam):
-        """The launches of one iteration on `stream` (eagerly for warm-up, then captured)."""
-        model, cfg, lib = self.model, self.model.config, _cabi.lib()
-        R, n = self.R, self.n_poses
+    def _step_structs(self, phase):
+        model, cfg = self.model, self.model.config
+        R = self.R
         S = cfg.training_n_sample_d + cfg.training_n_range_d
-        for g in self.grads.values():
-            g.zero_()
+        rays = XrdRays(R, ptr(self.rays_o), ptr(self.rays_d), ptr(self.ts), ptr(self.td))
+        grid = model._grid_struct(self.table.detach())
+        mlp = XrdCoslamMlp(*(ptr(t.detach()) for t in self.weights))
+        c = XrdCoslamCfg(
+            S, cfg.training_n_sample_d, cfg.training_n_range_d,
+            int(cfg.training_perturb > 0), cfg.training_trunc * cfg.data_sc_factor,
+            cfg.cam_depth_trunc, cfg.trainging_rgb_weight, cfg.trainging_depth_weight,
+            cfg.trainging_sdf_weight, cfg.trainging_fs_weight, ptr(model._lin_uniform),
+            ptr(model._lin_range), ptr(model._lin_nodepth), ptr(model._lin_full), 0,
+            cfg.rays_per_tile, cfg.precision, phase,
+            R * self.world if phase == 2 else 0, ptr(self.counts) if phase == 2 else None,
+            ptr(self.counts) if phase == 1 else None, self.dyn.data_ptr())
+        o = self.out
+        out = XrdCoslamOut(ptr(o['rgb']), ptr(o['depth']), ptr(o['disp']), ptr(o['acc']),
+                           ptr(o['var']), ptr(o['z_vals']), ptr(o['raw']), ptr(self.losses))
+        return rays, grid, mlp, c, out
+
+    def _part_a(self, stream):
+        """zero the bucket, unpack the rows, poses -> c2w -> rays (+ the sample phase when the
+        batch is sharded: z_vals and this rank's loss-normaliser counts)."""
+        lib, R, n = _cabi.lib(), self.R, self.n_poses
+        self.flat.zero_()
         self.dirs = self.rows[:, :3].contiguous()
         self.ts = self.rows[:, 3:6].contiguous()
         self.td = self.rows[:, 6].contiguous()
@@ -117,20 +152,17 @@ class MappingGraphSession:
         check('xrd_rays_from_poses',
               lib.xrd_rays_from_poses(R, ptr(self.dirs), ptr(self.ids), ptr(self.poses), n,
                                       ptr(self.rays_o), ptr(self.rays_d), stream))
-        rays = XrdRays(R, ptr(self.rays_o), ptr(self.rays_d), ptr(self.ts), ptr(self.td))
-        grid = model._grid_struct(self.table.detach())
-        w = [t.detach() for t in self.weights]
-        mlp = XrdCoslamMlp(*(ptr(t) for t in w))
-        c = XrdCoslamCfg(
-            S, cfg.training_n_sample_d, cfg.training_n_range_d,
-            int(cfg.training_perturb > 0), cfg.training_trunc * cfg.data_sc_factor,
-            cfg.cam_depth_trunc, cfg.trainging_rgb_weight, cfg.trainging_depth_weight,
-            cfg.trainging_sdf_weight, cfg.trainging_fs_weight, ptr(model._lin_uniform),
-            ptr(model._lin_range), ptr(model._lin_nodepth), ptr(model._lin_full), 0,
-            cfg.rays_per_tile, cfg.precision, 0, 0, None, None, self.dyn.data_ptr())
-        o = self.out
-        out = XrdCoslamOut(ptr(o['rgb']), ptr(o['depth']), ptr(o['disp']), ptr(o['acc']),
-                           ptr(o['var']), ptr(o['z_vals']), ptr(o['raw']), ptr(self.losses))
+        if self.world > 1:
+            rays, grid, mlp, c, out = self._step_structs(1)
+            check('xrd_coslam_step[sample]',
+                  lib.xrd_coslam_step(C.byref(rays), C.byref(grid), C.byref(mlp), C.byref(c), None,
+                                      C.byref(out), None, ptr(self.ws), self.ws.numel(), stream))
+
+    def _part_b(self, stream):
+        """fused forward / loss / backward (+ smoothness, pose-gradient reduction)."""
+        model, cfg, lib = self.model, self.model.config, _cabi.lib()
+        R, n = self.R, self.n_poses
+        rays, grid, mlp, c, out = self._step_structs(2 if self.world > 1 else 0)
         G = self.grads
         gs = XrdCoslamGrads(ptr(G[self.table]), *(ptr(G[t]) for t in self.weights),
                             ptr(self.d_rays_o) if self.ba else None,
@@ -140,9 +172,11 @@ class MappingGraphSession:
               lib.xrd_coslam_step(C.byref(rays), C.byref(grid), C.byref(mlp), C.byref(c), None,
                                   C.byref(out), C.byref(gs), ptr(self.ws), self.ws.numel(), stream))
         if not self.first:
+            # sharded: every rank evaluates the SAME lattice (shared generator) at weight / W,
+            # so the all-reduced sum is the single-GPU term
             check('xrd_coslam_smoothness_dev', lib.xrd_coslam_smoothness_dev(
                 C.byref(grid), cfg.trainging_smooth_pts, cfg.trainging_smooth_vox,
-                cfg.trainging_smooth_margin, cfg.trainging_smooth_weight,
+                cfg.trainging_smooth_margin, cfg.trainging_smooth_weight / self.world,
                 self.dyn.data_ptr() + 8, ptr(self.smooth_loss), ptr(G[self.table]), 1.0,
                 ptr(self.ws_s), self.ws_s.numel(), stream))
         if self.ba:
@@ -150,8 +184,12 @@ class MappingGraphSession:
                 R, ptr(self.dirs), ptr(self.ids), n, ptr(self.d_rays_o), ptr(self.d_rays_d),
                 ptr(self.d_poses), stream))
             check('xrd_pose_matrices_grads', lib.xrd_pose_matrices_grads(
-                n, ptr(self.rot), ptr(self.d_poses), ptr(self.fixed), ptr(self.d_rot),
-                ptr(self.d_trans), stream))
+                n, ptr(self.rot), ptr(self.d_poses), ptr(self.fixed), ptr(self.d_rot_it),
+                ptr(self.d_trans_it), stream))
+
+    def _part_c(self, stream, with_adam):
+        """Adam on table + decoder, pose-gradient accumulation (accum_step), total loss."""
+        lib = _cabi.lib()
         if with_adam:
             descs = self._adam_descs()
         else:  # warm-up: load the kernel on scratch tensors, leave the model untouched
@@ -164,18 +202,38 @@ class MappingGraphSession:
             descs = [a]
         arr = (XrdAdamTensor * len(descs))(*descs)
         check('xrd_adam_step', lib.xrd_adam_step(arr, len(descs), 0, stream))
-        self.loss_total = self.losses.sum() + (0 if self.first else self.smooth_loss[0])
+        if self.ba:
+            self.d_rot += self.d_rot_it
+            self.d_trans += self.d_trans_it
+        self.loss_total = self.flat[-8:-3].sum()
 
     def _capture(self):
         dev = self.dev
+        cur = lambda: torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
             # eager warm-up (lazy module loading, attribute calls), then capture
             self.rows[:, 2] = -1.0
             self.rows[:, 6] = 1.0
-            self._sequence(torch.cuda.current_stream(dev).cuda_stream, with_adam=False)
+            self._part_a(cur())
+            self._part_b(cur())
+            self._part_c(cur(), with_adam=False)
             torch.cuda.synchronize(dev)
-            with torch.cuda.graph(self.graph, capture_error_mode='relaxed'):
-                self._sequence(torch.cuda.current_stream(dev).cuda_stream, with_adam=True)
+            if self.world == 1:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode='relaxed'):
+                    self._part_a(cur())
+                    self._part_b(cur())
+                    self._part_c(cur(), with_adam=True)
+                self.graphs = [g]
+            else:  # NCCL all-reduces run between the three captured segments
+                pool = None
+                for part in (self._part_a, self._part_b,
+                             lambda st: self._part_c(st, with_adam=True)):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=pool, capture_error_mode='relaxed'):
+                        part(cur())
+                    pool = g.pool()
+                    self.graphs.append(g)
         self.d_rot.zero_()
         self.d_trans.zero_()
 
@@ -234,9 +292,10 @@ class MappingGraphSession:
         dyn_host = self._dyn_ring[k]
         d = dyn_host.numpy()
         model._step_count += 1
-        d[0:8].view(np.uint64)[0] = (cfg.seed << 32) + model._step_count
+        d[0:8].view(np.uint64)[0] = (cfg.seed << 32) + model._step_count + (self.rank << 24)
         if not self.first:
-            r6 = torch.cat([torch.rand(3), torch.rand((1, 1, 1, 3)).reshape(3)])
+            r6 = torch.cat([torch.rand(3, generator=self._gen),
+                            torch.rand((1, 1, 1, 3), generator=self._gen).reshape(3)])
             d[8:32].view(np.float32)[:] = r6.numpy()
         for gi, (opt, params) in enumerate(self.opt_groups):
             g = opt.param_groups[0]
@@ -249,7 +308,14 @@ class MappingGraphSession:
         if self._dyn_ev[k] is None:
             self._dyn_ev[k] = torch.cuda.Event()
         self._dyn_ev[k].record(torch.cuda.current_stream(self.dev))
-        self.graph.replay()
+        if self.world == 1:
+            self.graphs[0].replay()
+        else:
+            self.graphs[0].replay()
+            self.dp.all_reduce_sum(self.counts)   # batch-global loss normalisers (Q9)
+            self.graphs[1].replay()
+            self.dp.all_reduce_sum(self.flat)     # ONE collective: all gradients + loss terms
+            self.graphs[2].replay()
         if self.ba:
             self._pose_step(step)
         return self.loss_total
