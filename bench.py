@@ -322,24 +322,21 @@ def run_ours(args):
     # ---------------- tracking iterations (reported beside) ----------------
     trk = None
     if rank == 0:
-        n_it = 20
-        topt = algo.setup_optimizers(n_it, [cur], is_mapping=False)
+        # CoSLAM.optimize_update(..., is_mapping=False): one captured iteration per step,
+        # image upload at begin(), best-pose read-back at end() -- per tracked frame
+        n_it, n_frames = algo.config.tracking_n_iters, 20
         for i in range(3):
-            topt.zero_grad_all()
-            algo.get_loss([cur], False, i, n_it).backward()
-            topt.optimizer_step_all(step=i)
+            algo.optimize_update(n_it, [cur], False)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for i in range(n_it):
-            topt.zero_grad_all()
-            loss = algo.get_loss([cur], False, i, n_it)
-            loss.item()
-            loss.backward()
-            topt.optimizer_step_all(step=i)
+        for i in range(n_frames):
+            cand = algo.optimize_update(n_it, [cur], False)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        trk = {'tracking_iters_per_s': n_it / dt, 'tracking_rays': algo.config.tracking_sample,
-               'tracking_rays_per_s': n_it * algo.config.tracking_sample / dt}
+        trk = {'tracking_iters_per_s': n_frames * n_it / dt,
+               'tracking_frames_per_s': n_frames / dt, 'tracking_iters_per_frame': n_it,
+               'tracking_rays': algo.config.tracking_sample,
+               'tracking_rays_per_s': n_frames * n_it * algo.config.tracking_sample / dt}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:

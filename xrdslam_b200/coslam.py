@@ -252,7 +252,23 @@ class CoSLAM(Algorithm):
             cache[key] = MappingGraphSession(self, n_bank, n_cur, len(optimize_frames), first, ba)
         return cache[key]
 
+    def tracking_session(self):
+        from .coslam_graph import TrackingGraphSession
+        s = self.__dict__.get('_track_session')
+        if s is None:
+            s = self.__dict__['_track_session'] = TrackingGraphSession(self)
+        return s
+
     def optimize_update(self, n_iters, optimize_frames, is_mapping, coarse=False):
+        cfg = self.config
+        if not is_mapping and cfg.graph_mapping and self.device.type == 'cuda' and \
+                cfg.separate_LR and cfg.rot_rep == 'axis_angle':
+            with self.lock:
+                sess = self.tracking_session()
+                sess.begin(optimize_frames[-1])
+                for _ in range(n_iters):
+                    sess.step()
+                return sess.end(optimize_frames[-1])
         if not is_mapping or not self._graph_ok(optimize_frames):
             return super().optimize_update(n_iters, optimize_frames, is_mapping, coarse=coarse)
         with self.lock:

@@ -364,3 +364,164 @@ class MappingGraphSession:
                 if not fixed[i]:
                     f.pose.data_r.copy_(rot[i])
                     f.pose.data_t.copy_(trans[i])
+
+
+class TrackingGraphSession:
+    """Co-SLAM tracking iteration (pose-only optimisation of the current frame,
+    base_algorithm.py:255-273 with is_mapping=False) as one CUDA graph:
+
+        randint -> xrd_sample_pixels -> pose -> rays -> sample + fused fwd/loss/bwd (ray
+        gradients only) -> pose-gradient reduction -> Rodrigues backward -> keep the pose with
+        the smallest loss so far (the reference's candidate_c2w, picked on the host from
+        loss.cpu().item() every iteration) -> Adam on (axis-angle, t)
+
+    The frame's images are copied once into session-owned buffers at begin(); nothing
+    synchronises until end() reads the best pose back."""
+    def __init__(self, algo, external_indices=False):
+        self.algo, self.model = algo, algo.model
+        model, cfg, dev = algo.model, algo.model.config, algo.device
+        self.dev = dev
+        cam = algo.camera
+        self.R = R = algo.config.tracking_sample
+        S = cfg.training_n_sample_d + cfg.training_n_range_d
+        f32 = dict(dtype=torch.float32, device=dev)
+        z = lambda *s: torch.zeros(*s, **f32)
+        self.depth_img, self.rgb_img = z(cam.height, cam.width), z(cam.height, cam.width, 3)
+        self.idx = torch.zeros(R, dtype=torch.int64, device=dev)
+        self.external_indices = external_indices
+        self.dirs, self.td2, self.ts = z(R, 3), z(R, 1), z(R, 3)
+        self.ids = torch.zeros(R, dtype=torch.int64, device=dev)
+        self.rot, self.trans = z(1, 3), z(1, 3)
+        self.poses, self.d_poses = z(1, 4, 4), z(1, 4, 4)
+        self.d_rot, self.d_trans = z(1, 3), z(1, 3)
+        self.m_r, self.v_r, self.m_t, self.v_t = z(1, 3), z(1, 3), z(1, 3), z(1, 3)
+        self.best_loss = torch.full((1,), float('inf'), **f32)
+        self.best_rot, self.best_trans = z(1, 3), z(1, 3)
+        self.rays_o, self.rays_d = z(R, 3), z(R, 3)
+        self.d_rays_o, self.d_rays_d = z(R, 3), z(R, 3)
+        self.out = dict(rgb=z(R, 3), depth=z(R), disp=z(R), acc=z(R), var=z(R), z_vals=z(R, S),
+                        raw=z(R, S, 4))
+        self.losses = z(4)
+        self.ws = torch.empty(_cabi.lib().xrd_coslam_workspace_bytes(R, S), dtype=torch.uint8,
+                              device=dev)
+        # per-iteration scalars: [seed u64 | pad | (lr, bc1, bc2) rot | (lr, bc1, bc2) trans]
+        self.dyn = torch.zeros(64, dtype=torch.uint8, device=dev)
+        self._dyn_ring = [torch.zeros(64, dtype=torch.uint8).pin_memory() for _ in range(8)]
+        self._dyn_ev, self._dyn_k, self.t = [None] * 8, 0, 0
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.device(dev):
+            self.rgb_img.fill_(0.5)
+            self.depth_img.fill_(1.0)
+            self._sequence(torch.cuda.current_stream(dev).cuda_stream, warm=True)
+            torch.cuda.synchronize(dev)
+            with torch.cuda.graph(self.graph, capture_error_mode='relaxed'):
+                self._sequence(torch.cuda.current_stream(dev).cuda_stream, warm=False)
+
+    def _sequence(self, stream, warm):
+        a, model, cfg, lib = self.algo, self.model, self.model.config, _cabi.lib()
+        cam, R = a.camera, self.R
+        He, We = a.config.tracking_Hedge, a.config.tracking_Wedge
+        S = cfg.training_n_sample_d + cfg.training_n_range_d
+        if not self.external_indices:
+            torch.randint((cam.height - 2 * He) * (cam.width - 2 * We), (R,), device=self.dev,
+                          out=self.idx)
+        pc = _cabi.XrdPixelSampleCfg(1, R, cam.height, cam.width, He, cam.height - He, We,
+                                     cam.width - We, cam.fx, cam.fy, cam.cx, cam.cy)
+        dp = (C.c_void_p * 1)(ptr(self.depth_img))
+        cp = (C.c_void_p * 1)(ptr(self.rgb_img))
+        check('xrd_sample_pixels', lib.xrd_sample_pixels(
+            C.byref(pc), dp, cp, ptr(self.idx), ptr(self.dirs), ptr(self.td2), ptr(self.ts),
+            ptr(self.ids), None, stream))
+        check('xrd_pose_matrices',
+              lib.xrd_pose_matrices(1, ptr(self.rot), ptr(self.trans), ptr(self.poses), stream))
+        check('xrd_rays_from_poses',
+              lib.xrd_rays_from_poses(R, ptr(self.dirs), None, ptr(self.poses), 1,
+                                      ptr(self.rays_o), ptr(self.rays_d), stream))
+        rays = XrdRays(R, ptr(self.rays_o), ptr(self.rays_d), ptr(self.ts), ptr(self.td2))
+        grid = model._grid_struct(model.embed_fn.params.detach())
+        mlp = XrdCoslamMlp(*(ptr(t.detach()) for t in model._weights()))
+        c = XrdCoslamCfg(
+            S, cfg.training_n_sample_d, cfg.training_n_range_d,
+            int(cfg.training_perturb > 0), cfg.training_trunc * cfg.data_sc_factor,
+            cfg.cam_depth_trunc, cfg.trainging_rgb_weight, cfg.trainging_depth_weight,
+            cfg.trainging_sdf_weight, cfg.trainging_fs_weight, ptr(model._lin_uniform),
+            ptr(model._lin_range), ptr(model._lin_nodepth), ptr(model._lin_full), 0,
+            cfg.rays_per_tile, cfg.precision, 0, 0, None, None, self.dyn.data_ptr())
+        o = self.out
+        out = XrdCoslamOut(ptr(o['rgb']), ptr(o['depth']), ptr(o['disp']), ptr(o['acc']),
+                           ptr(o['var']), ptr(o['z_vals']), ptr(o['raw']), ptr(self.losses))
+        gs = XrdCoslamGrads(None, None, None, None, None, ptr(self.d_rays_o), ptr(self.d_rays_d),
+                            (C.c_float * 4)(1.0, 1.0, 1.0, 1.0))  # pose-only pass
+        check('xrd_coslam_step',
+              lib.xrd_coslam_step(C.byref(rays), C.byref(grid), C.byref(mlp), C.byref(c), None,
+                                  C.byref(out), C.byref(gs), ptr(self.ws), self.ws.numel(), stream))
+        check('xrd_rays_pose_grads', lib.xrd_rays_pose_grads(
+            R, ptr(self.dirs), None, 1, ptr(self.d_rays_o), ptr(self.d_rays_d), ptr(self.d_poses),
+            stream))
+        self.d_rot.zero_()
+        self.d_trans.zero_()
+        check('xrd_pose_matrices_grads', lib.xrd_pose_matrices_grads(
+            1, ptr(self.rot), ptr(self.d_poses), None, ptr(self.d_rot), ptr(self.d_trans), stream))
+        self.loss_total = self.losses.sum()
+        # candidate pose = the pose this loss was evaluated at (before the update)
+        better = self.loss_total < self.best_loss
+        self.best_rot.copy_(torch.where(better, self.rot, self.best_rot))
+        self.best_trans.copy_(torch.where(better, self.trans, self.best_trans))
+        self.best_loss.copy_(torch.where(better, self.loss_total, self.best_loss))
+        oc = a.config.optimizers
+        arr = (XrdAdamTensor * 2)()
+        for k, (x, name, p, g, m, v) in enumerate((
+                (arr[0], 'tracking_pose_r', self.rot, self.d_rot, self.m_r, self.v_r),
+                (arr[1], 'tracking_pose_t', self.trans, self.d_trans, self.m_t, self.v_t))):
+            oo = oc[name]['optimizer']
+            x.param, x.grad, x.exp_avg, x.exp_avg_sq = (t.data_ptr() for t in (p, g, m, v))
+            x.n, x.lr, x.beta1, x.beta2, x.eps = 3, 0.0 if warm else oo.lr, oo.betas[0], oo.betas[1], oo.eps
+            x.weight_decay = getattr(oo, 'weight_decay', 0)
+            x.bias_correction1 = x.bias_correction2 = 1.0
+            x.dyn = None if warm else self.dyn.data_ptr() + 16 + 12 * k
+        check('xrd_adam_step', lib.xrd_adam_step(arr, 2, 0, stream))
+
+    def begin(self, frame):
+        self.depth_img.copy_(self.algo._frame_tensor(frame, 'depth'))
+        self.rgb_img.copy_(self.algo._frame_tensor(frame, 'rgb'))
+        self.rot.copy_(frame.pose.data_r.detach().float().reshape(1, 3))
+        self.trans.copy_(frame.pose.data_t.detach().float().reshape(1, 3))
+        for t in (self.m_r, self.v_r, self.m_t, self.v_t):
+            t.zero_()
+        self.best_loss.fill_(float('inf'))
+        self.best_rot.copy_(self.rot)
+        self.best_trans.copy_(self.trans)
+        self.t = 0
+
+    def step(self):
+        model, cfg = self.model, self.model.config
+        k = self._dyn_k % 8
+        self._dyn_k += 1
+        if self._dyn_ev[k] is not None:
+            self._dyn_ev[k].synchronize()
+        d = self._dyn_ring[k].numpy()
+        model._step_count += 1
+        self.t += 1
+        d[0:8].view(np.uint64)[0] = (cfg.seed << 32) + model._step_count
+        oc = self.algo.config.optimizers
+        for j, name in enumerate(('tracking_pose_r', 'tracking_pose_t')):
+            oo = oc[name]['optimizer']
+            d[16 + 12 * j:28 + 12 * j].view(np.float32)[:] = (
+                oo.lr, 1.0 - oo.betas[0]**self.t, 1.0 - oo.betas[1]**self.t)
+        self.dyn.copy_(self._dyn_ring[k], non_blocking=True)
+        if self._dyn_ev[k] is None:
+            self._dyn_ev[k] = torch.cuda.Event()
+        self._dyn_ev[k].record(torch.cuda.current_stream(self.dev))
+        self.graph.replay()
+        return self.loss_total
+
+    def end(self, frame):
+        """-> candidate c2w [4,4] numpy (pose of the smallest loss); the frame keeps the
+        last-iteration pose like the reference."""
+        with torch.no_grad():
+            frame.pose.data_r.copy_(self.rot.cpu().reshape(3))
+            frame.pose.data_t.copy_(self.trans.cpu().reshape(3))
+            from .opt_pose import OptimizablePose
+            best = OptimizablePose(torch.cat([self.best_trans.cpu().reshape(3),
+                                              self.best_rot.cpu().reshape(3)]))
+            return best.matrix().detach().clone().numpy()
