@@ -351,6 +351,72 @@ __device__ __noinline__ float3 hash_backward_item(const Params& P, const Lv* __r
   return make_float3(dx[0], dx[1], dx[2]);
 }
 
+// NL (point, level) items per call: the 8 NL corner loads of all levels are issued before any
+// is consumed (the kernel runs at 7 warps/SM, so memory-level parallelism has to come from
+// within the thread), then the 8 NL scatters.  on[h]: item present (level exists and its
+// gradient is non-zero).  Levels are l0 + 4 h (fragment layout: lane t owns levels 4 nt + t).
+template <int NL>
+__device__ __noinline__ float3 hash_backward_multi(const Params& P, const Lv* __restrict__ lv,
+                                                   int l0, const bool (&on)[NL], float x0,
+                                                   float x1, float x2, const float (&g)[NL][2],
+                                                   bool need_dx, bool scatter) {
+  const float2* __restrict__ tab = reinterpret_cast<const float2*>(P.table);
+  const float x[3] = {x0, x1, x2};
+  float w[NL][3], sc[NL];
+  uint32_t idx[NL][8];
+#pragma unroll
+  for (int h = 0; h < NL; ++h) {
+    const Lv L = lv[on[h] ? l0 + 4 * h : 0];
+    sc[h] = L.scale;
+    uint32_t c[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) pos_fract(x[d], sc[h], w[h][d], c[d]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      idx[h][k] = grid_index(L, c[0] + (k & 1), c[1] + ((k >> 1) & 1), c[2] + ((k >> 2) & 1));
+  }
+  float dx[3] = {0.f, 0.f, 0.f};
+  if (need_dx) {
+    float t[NL][8];
+#pragma unroll
+    for (int h = 0; h < NL; ++h)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float2 v = on[h] ? __ldg(&tab[idx[h][k]]) : make_float2(0.f, 0.f);
+        t[h][k] = v.x * g[h][0] + v.y * g[h][1];
+      }
+#pragma unroll
+    for (int h = 0; h < NL; ++h) {
+      const float w0 = w[h][0], w1 = w[h][1], w2 = w[h][2];
+      const float* tt = t[h];
+      const float d0 = (1 - w1) * (1 - w2) * (tt[1] - tt[0]) + w1 * (1 - w2) * (tt[3] - tt[2]) +
+                       (1 - w1) * w2 * (tt[5] - tt[4]) + w1 * w2 * (tt[7] - tt[6]);
+      const float d1 = (1 - w0) * (1 - w2) * (tt[2] - tt[0]) + w0 * (1 - w2) * (tt[3] - tt[1]) +
+                       (1 - w0) * w2 * (tt[6] - tt[4]) + w0 * w2 * (tt[7] - tt[5]);
+      const float d2 = (1 - w0) * (1 - w1) * (tt[4] - tt[0]) + w0 * (1 - w1) * (tt[5] - tt[1]) +
+                       (1 - w0) * w1 * (tt[6] - tt[2]) + w0 * w1 * (tt[7] - tt[3]);
+      if (on[h]) {
+        dx[0] = fmaf(sc[h], d0, dx[0]);
+        dx[1] = fmaf(sc[h], d1, dx[1]);
+        dx[2] = fmaf(sc[h], d2, dx[2]);
+      }
+    }
+  }
+  if (scatter) {
+#pragma unroll
+    for (int h = 0; h < NL; ++h) {
+      if (!on[h]) continue;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float wk = ((k & 1) ? w[h][0] : 1.f - w[h][0]) * ((k & 2) ? w[h][1] : 1.f - w[h][1]) *
+                         ((k & 4) ? w[h][2] : 1.f - w[h][2]);
+        red_add_v2(P.d_table + 2 * (size_t)idx[h][k], wk * g[h][0], wk * g[h][1]);
+      }
+    }
+  }
+  return make_float3(dx[0], dx[1], dx[2]);
+}
+
 // ------------------------------------------------------- tensor-core GEMMs ---
 // mma.sync m16n8k8 tf32 (fp32 accumulate).  PREC3 = 3xTF32 error-compensated split:
 // x = big + small, d += a_s*b_b + a_b*b_s + a_b*b_b  -> fp32-level accuracy.
@@ -849,13 +915,19 @@ __global__ void __launch_bounds__(256) k_fused(const Params P) {
             const int row = warp * 32 + mt * 16 + g + 8 * h;
             if (row < npts) {
               const float x3[3] = {xnb[row * 3], xnb[row * 3 + 1], xnb[row * 3 + 2]};
+              {  // the 4 levels of this lane (t, 4 + t, 8 + t, 12 + t) in one call
+                bool on[4];
+                float gg[4][2];
+                bool any = false;
 #pragma unroll
-              for (int nt = 0; nt < 4; ++nt) {
-                const int l = 4 * nt + t;
-                const float g0 = c[mt][nt][2 * h], g1 = c[mt][nt][2 * h + 1];
-                if (l < P.g.n_levels && (g0 != 0.f || g1 != 0.f)) {
-                  const float3 d3 = hash_backward_item(P, s_lv, l, x3[0], x3[1], x3[2], g0, g1,
-                                                       need_dx, map_grads);
+                for (int nt = 0; nt < 4; ++nt) {
+                  gg[nt][0] = c[mt][nt][2 * h]; gg[nt][1] = c[mt][nt][2 * h + 1];
+                  on[nt] = (4 * nt + t) < P.g.n_levels && (gg[nt][0] != 0.f || gg[nt][1] != 0.f);
+                  any |= on[nt];
+                }
+                if (any) {
+                  const float3 d3 = hash_backward_multi<4>(P, s_lv, t, on, x3[0], x3[1], x3[2], gg,
+                                                           need_dx, map_grads);
                   hdx[mt][h][0] += d3.x; hdx[mt][h][1] += d3.y; hdx[mt][h][2] += d3.z;
                 }
               }
@@ -1069,8 +1141,16 @@ __global__ void __launch_bounds__(256) k_smooth_bwd(SmoothParams p) {
       }
     }
   }
+  // one double atomic per CTA (per warp it was ~15 k serialised atomics on one address)
+  __shared__ float s_part[8];
   part = warp_sum(part);
-  if ((threadIdx.x & 31) == 0 && part != 0.f) atomicAdd(p.loss_acc, (double)part);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+    for (int i = 0; i < 8; ++i) a += (double)s_part[i];
+    if (a != 0.0) atomicAdd(p.loss_acc, a);
+  }
 }
 
 __global__ void k_smooth_finalize(const double* acc, float* loss, float scale) {
