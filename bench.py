@@ -281,8 +281,8 @@ def run_ours(args):
                 'frac': achieved / peak,
                 'peak_source': 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback 6650',
                 # dram__bytes_read.sum + dram__bytes_write.sum of one 4096-ray launch
-                # (ncu --set full, profiles/r01_coslam_fused_v3_4096rays_ncu.txt)
-                'traffic': 13906176 + 683008 if R == 4096 else None, 'kernel_ms': k_ms,
+                # (ncu --set full, profiles/r01_coslam_fused_v4_4096rays_ncu.txt)
+                'traffic': 13928960 + 1280 if R == 4096 else None, 'kernel_ms': k_ms,
                 'algorithmic_bytes_per_launch': R * BYTES_PER_RAY,
                 'note': 'table (6.56 MB) is L2-resident: DRAM traffic is far below '
                         'the algorithmic bytes, see profiles/'}
