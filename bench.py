@@ -44,6 +44,9 @@ BYTES_PER_RAY = 88064  # 43 samples x (1024 B gather + 1024 B scatter
 SMOOTH_BYTES = 29791 * 2048  # smoothness lattice, per mapping iteration
 MAP_KF, MAP_CUR = 2048, 2048
 N_KEYFRAMES = 5
+WORKLOAD = ('co-slam hash-grid(16 lvl x 2 feat, 2^16) + OneBlob16, 640x480 synthetic room, '
+            f'mapping iteration, {MAP_KF} keyframe-bank + {MAP_CUR} current-frame rays per GPU, '
+            f'43 samples/ray, smoothness 31^3, {N_KEYFRAMES} keyframes')
 
 
 def parse():
@@ -350,11 +353,7 @@ def run_ours(args):
             'ms_per_step': ms_total / K, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'precision': 'fp32 gathers/compositing/loss; decoder GEMMs 3xTF32 forward, TF32 backward (fp32 accumulate)',
-                       'workload': 'co-slam hash-grid(16 lvl x 2 feat, 2^16) + OneBlob16, '
-                                   '640x480 synthetic room, mapping iteration, '
-                                   f'{MAP_KF} keyframe-bank + {MAP_CUR} current-frame rays per GPU, '
-                                   '43 samples/ray, smoothness 31^3, '
-                                   f'{N_KEYFRAMES} keyframes',
+                       'workload': WORKLOAD,
                        'rays_per_step_per_gpu': R, 'parallelism': f'dp{world}',
                        'l2': 'flushed between timed steps (256 MB write); ray batches differ every step'},
             'e2e': {'value': e2e_value, 'unit': 'rays/s', 'h2d_bytes_per_step': h2d,
@@ -464,9 +463,12 @@ def run_reference(args):
         'value': v, 'unit': 'rays/s', 'n_gpus': int(os.environ.get('WORLD_SIZE', '1')),
         'steps': K, 'warmup': W, 'ms_per_step': dt / K * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'co-slam mapping iteration, CPU oracle port '
-                               '(reference python cannot run on the box), '
-                               f'bounded sample {R} rays x 43 samples per step'},
+        # same workload as the B200 arm; each step is a bounded sample of it
+        'config': {'workload': WORKLOAD, 'rays_per_step_per_gpu': MAP_KF + MAP_CUR,
+                   'precision': 'fp32 (torch CPU)',
+                   'sample': f'{R} of the {MAP_KF + MAP_CUR} rays per step (same sampler, decoder, '
+                             'losses, smoothness, Adam); the reference\'s own python cannot run on '
+                             'the box (py3.12 + tinycudann absent): CPU oracle port, all host threads'},
         'cpu_baseline': {'value': v, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
                          'sample': f'{K} steps x {R} rays'},
         'e2e': {'value': v, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},

@@ -331,3 +331,54 @@ def test_remap_linear_bilinear_and_border():
     out = remap_linear(img, uv)
     # 1.03 -> 33/32: OpenCV's 1/32-pixel coordinate quantisation
     assert torch.allclose(out, torch.tensor([0., 3.5, 11., 5.5, 0., 5. + 1. / 32]))
+
+
+def test_pose_matrices_batched_equals_per_frame():
+    """opt_pose.pose_matrices (one batched evaluation for the window) == stacking
+    OptimizablePose.matrix() per frame, values and gradients, both rotation reps, including
+    the identity-rotation branch and a detached (fixed) frame."""
+    from xrdslam_b200.opt_pose import OptimizablePose, pose_matrices
+    from xrdslam_b200.transforms import quaternion_to_matrix
+    g = torch.Generator().manual_seed(0)
+    for rep in ('axis_angle', 'quat'):
+        ps = []
+        for k in range(5):
+            M = torch.eye(4)
+            if k != 2:  # frame 2 keeps the identity rotation
+                q = torch.randn(4, generator=g)
+                M[:3, :3] = quaternion_to_matrix(q / q.norm())
+            M[:3, 3] = torch.randn(3, generator=g)
+            ps.append(OptimizablePose.from_matrix(M, rot_rep=rep))
+        A = torch.stack([p.matrix() for p in ps])
+        B = pose_matrices(ps, [True, False, False, False, False])
+        assert torch.allclose(A, B, atol=1e-7)
+        W = torch.randn(5, 4, 4, generator=g)
+        params = [q for p in ps[1:] for q in p.parameters()]
+        ga = torch.autograd.grad((A * W).sum(), params)
+        gb = torch.autograd.grad((B * W).sum(), params)
+        for a, b in zip(ga, gb):
+            assert torch.allclose(a, b, atol=1e-6)
+        # the fixed frame receives no gradient through the batched form
+        g0 = torch.autograd.grad((pose_matrices(ps, [True] + [False] * 4) * W).sum(),
+                                 list(ps[0].parameters()), allow_unused=True)
+        assert all(x is None or x.abs().sum() == 0 for x in g0)
+
+
+def test_dynamic_radius_sobel_matches_scipy():
+    """point_slam.sobel_magnitude restates skimage.filters.sobel_h/_v on rgb2gray
+    (scipy.ndimage.convolve, mode='reflect'); the radius map follows interp1d's knots."""
+    from scipy import ndimage as ndi
+    from xrdslam_b200.point_slam import sobel_magnitude
+    rng = np.random.default_rng(0)
+    rgb = rng.random((37, 53, 3)).astype(np.float32)
+    gray = rgb.astype(np.float64) @ np.array([0.2125, 0.7154, 0.0721])
+    H = np.array([[1, 2, 1], [0, 0, 0], [-1, -2, -1]]) / 4.0
+    mag = np.sqrt(ndi.convolve(gray, H)**2 + ndi.convolve(gray, H.T)**2)
+    assert np.abs(sobel_magnitude(torch.from_numpy(rgb)).numpy() - mag).max() < 1e-12
+    from scipy.interpolate import interp1d
+    thr, rmax, rmin = 0.15, 0.08, 0.02
+    m = np.clip(mag, 0.0, thr)
+    ref = interp1d([0, 0.01, thr], [rmax, rmax, rmin])(m)
+    mt = torch.from_numpy(m)
+    mine = torch.where(mt <= 0.01, torch.full_like(mt, rmax), rmax + (mt - 0.01) * (rmin - rmax) / (thr - 0.01))
+    assert np.abs(mine.numpy() - ref).max() < 1e-12

@@ -89,13 +89,6 @@ class Algorithm():
             frame.__dict__[key] = t
         return t
 
-    def _sample_frames(self, frames, n, Hedge=0, Wedge=0, **kw):
-        """get_samples per frame (shared by nice / vox / point get_model_input)."""
-        from .common import get_samples
-        return [get_samples(self.camera, n, f.get_pose(), self._frame_tensor(f, 'depth'),
-                            self._frame_tensor(f, 'rgb'), device=self.device, Hedge=Hedge,
-                            Wedge=Wedge, **kw) for f in frames]
-
     def _sample_window(self, frames, n, Hedge=0, Wedge=0, return_index=False):
         """All frames of the window at once: one batched pose evaluation, one H2D, three
         launches (csrc/rays.cu) -- instead of ~150 ATen launches and a host Rodrigues /

@@ -248,6 +248,9 @@ class CoSLAM(Algorithm):
         ba = self.bundle_adjust and len(optimize_frames) > 1
         key = (n_bank, n_cur, len(optimize_frames), first, ba)
         cache = self.__dict__.setdefault('_graph_sessions', {})
+        if key in cache and (cache[key].stale() or
+                             cache[key].opt_groups[0][0] is not self.model_optimizers.optimizers['embed_fn']):
+            del cache[key]  # optimiser state / parameters were replaced: re-capture
         if key not in cache:
             cache[key] = MappingGraphSession(self, n_bank, n_cur, len(optimize_frames), first, ba)
         return cache[key]

@@ -98,6 +98,8 @@ class MappingGraphSession:
                     st['step'] = torch.tensor(0.0)
                     st['exp_avg'] = torch.zeros_like(p)
                     st['exp_avg_sq'] = torch.zeros_like(p)
+        self._captured = {p: (p.data_ptr(), opt.state[p]['exp_avg'].data_ptr())
+                          for opt, params in self.opt_groups for p in params}
         self.graphs = []
         self._capture()
 
@@ -238,6 +240,17 @@ class MappingGraphSession:
         self.d_trans.zero_()
 
     # ------------------------------------------------------------------ running ---
+    def stale(self):
+        """True when a captured pointer no longer belongs to the live model / optimiser state
+        (optimiser state replaced, parameter re-allocated): the session must be rebuilt."""
+        for opt, params in self.opt_groups:
+            for p in params:
+                st = opt.state.get(p)
+                if not st or st['exp_avg'].data_ptr() != self._captured[p][1] or \
+                        p.data_ptr() != self._captured[p][0]:
+                    return True
+        return False
+
     def begin(self, optimize_frames):
         """Upload the window's poses; (re)start the pose optimiser (fresh Adam state per
         mapping call, like the reference's setup_optimizers)."""

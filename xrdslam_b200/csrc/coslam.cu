@@ -302,55 +302,8 @@ __device__ __forceinline__ void encode_point(const Params& P, const Lv* __restri
   blob_forward(xn, rec);
 }
 
-// one (point, level) item of the hash backward: scatter (g0,g1), optional d/dx.
-// Deliberately not inlined: 16 call sites per warp tile, and instruction-cache
-// footprint is what bounds this kernel (see profiles/).
-__device__ __noinline__ float3 hash_backward_item(const Params& P, const Lv* __restrict__ lv,
-                                                  int l, float x0, float x1,
-                                                  float x2, float g0, float g1, bool need_dx,
-                                                  bool scatter) {
-  const float2* __restrict__ tab = reinterpret_cast<const float2*>(P.table);
-  float w[3];
-  uint32_t c[3];
-  float dx[3] = {0.f, 0.f, 0.f};
-  const Lv L = lv[l];
-  const float sc = L.scale;
-  pos_fract(x0, sc, w[0], c[0]);
-  pos_fract(x1, sc, w[1], c[1]);
-  pos_fract(x2, sc, w[2], c[2]);
-  uint32_t idx[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k)
-    idx[k] = grid_index(L, c[0] + (k & 1), c[1] + ((k >> 1) & 1), c[2] + ((k >> 2) & 1));
-  if (need_dx) {
-    float t[8];  // <table entry, dfeat>
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float2 v = __ldg(&tab[idx[k]]);
-      t[k] = v.x * g0 + v.y * g1;
-    }
-    const float w0 = w[0], w1 = w[1], w2 = w[2];
-    float d0 = (1 - w1) * (1 - w2) * (t[1] - t[0]) + w1 * (1 - w2) * (t[3] - t[2]) +
-               (1 - w1) * w2 * (t[5] - t[4]) + w1 * w2 * (t[7] - t[6]);
-    float d1 = (1 - w0) * (1 - w2) * (t[2] - t[0]) + w0 * (1 - w2) * (t[3] - t[1]) +
-               (1 - w0) * w2 * (t[6] - t[4]) + w0 * w2 * (t[7] - t[5]);
-    float d2 = (1 - w0) * (1 - w1) * (t[4] - t[0]) + w0 * (1 - w1) * (t[5] - t[1]) +
-               (1 - w0) * w1 * (t[6] - t[2]) + w0 * w1 * (t[7] - t[3]);
-    dx[0] = fmaf(sc, d0, dx[0]);
-    dx[1] = fmaf(sc, d1, dx[1]);
-    dx[2] = fmaf(sc, d2, dx[2]);
-  }
-  if (scatter) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float wk = ((k & 1) ? w[0] : 1.f - w[0]) * ((k & 2) ? w[1] : 1.f - w[1]) *
-                 ((k & 4) ? w[2] : 1.f - w[2]);
-      red_add_v2(P.d_table + 2 * (size_t)idx[k], wk * g0, wk * g1);
-    }
-  }
-  return make_float3(dx[0], dx[1], dx[2]);
-}
-
+// NL (point, level) items of the hash backward per call (scatter (g0,g1), optional d/dx).
+// Deliberately not inlined: instruction-cache footprint matters for this kernel (profiles/).
 // NL (point, level) items per call: the 8 NL corner loads of all levels are issued before any
 // is consumed (the kernel runs at 7 warps/SM, so memory-level parallelism has to come from
 // within the thread), then the 8 NL scatters.  on[h]: item present (level exists and its
