@@ -384,3 +384,29 @@ def test_dynamic_radius_sobel_matches_scipy():
     mt = torch.from_numpy(m)
     mine = torch.where(mt <= 0.01, torch.full_like(mt, rmax), rmax + (mt - 0.01) * (rmin - rmax) / (thr - 0.01))
     assert np.abs(mine.numpy() - ref).max() < 1e-12
+
+
+def test_keyframe_selection_overlap_on_host():
+    """common.py:343-426: keyframes that see the current frame's back-projected samples are
+    kept, a keyframe looking the other way is dropped (host tensors: the torch branch of
+    rays_from_poses)."""
+    from xrdslam_b200.frame import Frame
+    from xrdslam_b200.keyframe_selection import keyframe_selection_overlap
+    from xrdslam_b200.synthetic import CENTRE, look_at, make_camera, render_frame
+    torch.manual_seed(0)
+    np.random.seed(0)
+    cam = make_camera(160, 120)
+    eye = CENTRE + np.array([0.5, 0.0, 0.1])
+    tgt = CENTRE + np.array([-1.5, 0.3, -0.2])
+    poses = [look_at(eye, tgt),                                   # current view
+             look_at(eye + np.array([0.1, 0.05, 0.0]), tgt),      # nearly the same view
+             look_at(eye, eye + (eye - tgt)),                     # looks the opposite way
+             look_at(eye + np.array([0.0, -0.2, 0.05]), tgt)]     # overlapping view
+    frames = []
+    for k, p in enumerate(poses):
+        rgb, depth = render_frame(cam, p, seed=k)
+        frames.append(Frame(k, rgb, depth, init_pose=p, rot_rep='quat'))
+    sel = keyframe_selection_overlap(cam, frames[0], frames[1:], k=3, device='cpu')
+    ids = sorted(f.fid for f in sel)
+    assert ids == [1, 3], ids
+    assert len(keyframe_selection_overlap(cam, frames[0], frames[1:], k=1, device='cpu')) == 1
