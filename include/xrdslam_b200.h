@@ -591,7 +591,8 @@ typedef struct {
   XrdPointColorDecoderGrads* color; /* colour-decoder gradients or NULL (decoder fixed)     */
 } XrdPointGrads;
 
-/* Measurement / parity hook: arithmetic of the wide-MLP GEMMs (Point-SLAM colour stage):
+/* Measurement / parity hook: arithmetic of the wide-MLP GEMMs (Point-SLAM colour stage and
+ * the Vox-Fusion decoder):
  * 0 = fp32 SIMT, 1 = 3xTF32 tensor cores (default, fp32-level accuracy), 2 = plain TF32. */
 int xrd_debug_gemm_mode(int mode);
 
