@@ -505,7 +505,9 @@ int xrd_voxfusion_render(const XrdRays* rays, const XrdVoxMap* map, const XrdVox
  *                            (5 surface samples), :248-309 eval_points, POINT.forward
  *                            slam/model_components/decoder_pointslam.py:595-655 stage
  *                            'geometry' (MLP_geometry :162-273: inverse-distance kNN feature
- *                            interpolation + 5x32 Fourier MLP), raw2outputs_nerf_color2
+ *                            interpolation + 5x32 Fourier MLP) and stage 'color' (adds
+ *                            MLP_color :408-542 with the per-neighbour MLP_col_neighbor
+ *                            :276-292), raw2outputs_nerf_color2
  *                            slam/model_components/utils.py:247-295, get_loss_dict
  *                            conv_onet_pointslam.py:144-195 and autograd's backward.
  */
