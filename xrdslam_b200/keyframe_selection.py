@@ -56,7 +56,7 @@ def frustum_mask(camera, c2w, pts, depth, edge=0, near_cam=None):
     uv, z = _project(camera, c2w, pts)
     d = remap_linear(depth, uv)
     H, W = depth.shape
-    mask = (uv[:, 0] < W - edge) & (uv[:, 0] > edge) & (uv[:, 1] < H - edge) & (uv[:, 1] > edge)
+    mask = camera.inside(uv[:, 0], uv[:, 1], edge)
     d = torch.where(d == 0, d.max(), d)  # rays with depth == 0 get the maximum depth
     mask = mask & (0 <= -z) & (-z <= d.double() + 0.5)
     if near_cam is not None:
@@ -81,8 +81,7 @@ def keyframe_selection_overlap(camera, cur_frame, keyframes_graph, k, N_samples=
     scored = []
     for kf in keyframes_graph:
         uv, z = _project(camera, kf.get_pose().to(device), pts)
-        m = (uv[:, 0] < W - edge) & (uv[:, 0] > edge) & (uv[:, 1] < H - edge) & \
-            (uv[:, 1] > edge) & (z < 0)
+        m = camera.inside(uv[:, 0], uv[:, 1], edge) & (z < 0)
         scored.append((kf, float(m.sum()) / max(1, uv.shape[0])))
     scored.sort(key=lambda e: e[1], reverse=True)
     sel = [kf for kf, p in scored if p > 0.0]
