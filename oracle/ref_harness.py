@@ -185,3 +185,53 @@ def ref_conv_onet2(**cfg_overrides):
     finally:
         m.ConvOnet2.load_pretrain = orig
     return model
+
+
+# ---- Vox-Fusion: the reference's SparseVoxel python (features, decoder, weights, losses) on
+# ---- CPU, fed with precomputed intersections / samples (its CUDA ops are pinned separately
+# ---- against oracle/_ref/grid.so on the GPU box)
+def ref_sparse_voxel_cpu(map_states, embeddings, marched):
+    """-> (model, module): a reference SparseVoxel whose map lives on the CPU and whose
+    ray_intersect / ray_sample return `marched` = (intersections dict [R,H], hits [R] bool,
+    samples dict [R',S])."""
+    install()
+    import torch
+    import slam.models.sparse_voxel as sv
+    from slam.model_components.decoder_voxfusion import Decoder
+    cfg = sv.SparseVoxelConfig()
+    model = sv.SparseVoxel.__new__(sv.SparseVoxel)
+    torch.nn.Module.__init__(model)
+    model.config = cfg
+    cfg.step_size = cfg.voxel_size * cfg.step_size
+    model.embeddings = torch.nn.Parameter(embeddings.clone())
+    model.decoder = Decoder(depth=cfg.depth, width=cfg.width, in_dim=cfg.embed_dim,
+                            embedder=cfg.embedder)
+    ms = dict(map_states)
+    ms['voxel_vertex_emb'] = model.embeddings
+    model.map_states = ms
+    inter, hits, samples = marched
+
+    def fake_intersect(rays_o, rays_d, centres, children, voxel_size, n_max, max_distance):
+        return {k: v.unsqueeze(0) for k, v in inter.items()}, hits.unsqueeze(0)
+
+    def fake_sample(intersections, step_size):
+        keys = ('sampled_point_depth', 'sampled_point_distance', 'sampled_point_voxel_idx')
+        return {k: samples[k].clone() for k in keys}  # what the reference's ray_sample returns
+    sv.ray_intersect, sv.ray_sample = fake_intersect, fake_sample
+    return model, sv
+
+
+import contextlib
+
+
+@contextlib.contextmanager
+def cuda_calls_are_noops():
+    """The reference hard-codes `.cuda()` in a few helpers (voxel_helpers_voxfusion.py:108-110):
+    on this GPU-less container they become identity for the duration of the block."""
+    import torch
+    orig_t, orig_p = torch.Tensor.cuda, torch.nn.Parameter.cuda if hasattr(torch.nn.Parameter, 'cuda') else None
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        yield
+    finally:
+        torch.Tensor.cuda = orig_t

@@ -16,8 +16,9 @@ Follows (reference @ f0366f20, paths relative to /root/reference):
 Pinned: octree + map states against the reference's own svo.Octree (oracle/_ref/svo.so, built
 from the reference sources by oracle/build_ref.py); on the GPU box the two kernels are
 additionally checked bit-for-bit against the reference's own `grid` CUDA extension
-(oracle/_ref/grid.so).  The torch part (features, decoder, weights, losses) is the reference's
-python restated line by line.
+(oracle/_ref/grid.so).  The torch part (features, decoder, weights, losses, gradients) is
+pinned against the reference's own SparseVoxel.render_rays + get_loss_dict run on CPU with
+these intersections / samples injected (tests/test_voxfusion_cpu.py, oracle/ref_harness.py).
 """
 from __future__ import annotations
 

@@ -67,3 +67,74 @@ def test_model_map_states_match_reference_formulas():
     have = {tuple(v) for v in torch.round(ms['voxel_center_xyz'][surf] / 0.2 - 0.5).int().tolist()}
     assert want <= have and len(have) == len(want)
     assert int(ms['voxel_vertex_idx'].max()) < m.config.num_embeddings
+
+
+def test_vox_oracle_torch_part_matches_reference_python():
+    """oracle/voxfusion.py's features / decoder / sdf2weights / losses against the reference's
+    own SparseVoxel.render_rays + get_loss_dict run on CPU (its two CUDA ops replaced by the
+    oracle's intersections and samples, which the GPU tests pin bit-for-bit against the
+    reference's compiled kernels)."""
+    import sys
+    sys.path.insert(0, ROOT)
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip('needs /root/reference')
+    from oracle.voxfusion import VoxOracle
+    ref_tree = ref_octree()
+    g = torch.Generator().manual_seed(3)
+    # a wall of voxels at z ~ 12.0 m (offset world), rays from above
+    xy = torch.rand(3000, 2, generator=g) * 2.0 + 11.0
+    pts = torch.cat([xy, torch.full((3000, 1), 12.05) + torch.rand(3000, 1, generator=g) * 0.3], 1)
+    ref_tree.insert(torch.div(pts, 0.2, rounding_mode='floor').int())
+    voxels, children, features = ref_tree.get_centres_and_children()
+    # node ids are process-global in the reference: make them local rows of the table
+    base = int(features[features >= 0].min()) if (features >= 0).any() else 0
+    ora = VoxOracle(seed=5)
+    feats_local = torch.where(features >= 0, features - base, features)
+    ora.set_map(voxels, children, feats_local)
+    with torch.no_grad():
+        ora.embeddings.mul_(30.0)
+    R = 96
+    ro = torch.cat([torch.rand(R, 2, generator=g) * 1.6 + 11.2, torch.full((R, 1), 10.5)], 1)
+    rd = torch.nn.functional.normalize(
+        torch.cat([torch.randn(R, 2, generator=g) * 0.15, torch.ones(R, 1)], 1), dim=-1)
+    rd[::13] = torch.tensor([0.0, 0.0, -1.0])  # rays that miss the map
+    marched = ora.march(ro, rd, lambda shape: torch.rand(shape, generator=g))
+    assert marched is not None
+    inter, hits, samples = marched
+    assert hits.any() and not hits.all()
+    td = torch.full((R, 1), 1.62) + torch.rand(R, 1, generator=g) * 0.2
+    td[5::11] = 0
+    ts = torch.rand(R, 3, generator=g)
+    # the reference model on the same map / decoder / embeddings
+    ms = {'voxel_vertex_idx': ora.vertex_idx, 'voxel_center_xyz': ora.centres,
+          'voxel_structure': ora.children}
+    full_inter = {k: torch.zeros((R,) + v.shape[1:], dtype=v.dtype) for k, v in inter.items()}
+    for k in full_inter:
+        full_inter[k][hits] = inter[k]
+    ref, sv = ref_harness.ref_sparse_voxel_cpu(ms, ora.embeddings.detach(), (full_inter, hits, samples))
+    rsd = ref.decoder.state_dict()
+    with torch.no_grad():
+        od = ora.decoder
+        od.pts_linears[0].weight.copy_(rsd['pts_linears.0.weight']); od.pts_linears[0].bias.copy_(rsd['pts_linears.0.bias'])
+        od.pts_linears[1].weight.copy_(rsd['pts_linears.1.weight']); od.pts_linears[1].bias.copy_(rsd['pts_linears.1.bias'])
+        od.sdf_out.weight.copy_(rsd['sdf_out.weight']); od.sdf_out.bias.copy_(rsd['sdf_out.bias'])
+        od.color_out[0].weight.copy_(rsd['color_out.0.weight']); od.color_out[0].bias.copy_(rsd['color_out.0.bias'])
+        od.color_out[2].weight.copy_(rsd['color_out.2.weight']); od.color_out[2].bias.copy_(rsd['color_out.2.bias'])
+    out_o, ld_o = ora.render(ro, rd, ts, td, marched)
+    with ref_harness.cuda_calls_are_noops():
+        out_r = ref.render_rays(ro.unsqueeze(0), rd.unsqueeze(0), target_d=td.unsqueeze(0))
+    ld_r = ref.get_loss_dict(out_r, {'target_d': td, 'target_s': ts}, True)
+    assert torch.equal(out_r['ray_mask'], out_o['ray_mask'])
+    assert (out_r['depth'] - out_o['depth']).abs().max() < 1e-6
+    assert (out_r['rgb'] - out_o['rgb']).abs().max() < 1e-6
+    assert (out_r['sdf'] - out_o['sdf']).abs().max() < 1e-6
+    for k in ld_r:
+        assert abs(float(ld_r[k]) - float(ld_o[k])) <= 1e-5 * max(1e-3, abs(float(ld_r[k]))), k
+    # gradients of the summed loss w.r.t. embeddings and decoder
+    sum(ld_o.values()).backward()
+    sum(ld_r.values()).backward()
+    ge_o, ge_r = ora.embeddings.grad, ref.embeddings.grad
+    assert (ge_o - ge_r).abs().max() <= 1e-5 * ge_r.abs().max()
+    assert (od.sdf_out.weight.grad - ref.decoder.sdf_out.weight.grad).abs().max() <= \
+        1e-5 * ref.decoder.sdf_out.weight.grad.abs().max()
