@@ -80,18 +80,19 @@ def test_vox_oracle_torch_part_matches_reference_python():
     if not ref_harness.available():
         pytest.skip('needs /root/reference')
     from oracle.voxfusion import VoxOracle
-    ref_tree = ref_octree()
+    from xrdslam_b200.camera import Camera
+    from xrdslam_b200.sparse_voxel import SparseVoxelConfig
     g = torch.Generator().manual_seed(3)
-    # a wall of voxels at z ~ 12.0 m (offset world), rays from above
+    # a wall of voxels at z ~ 12.0 m (offset world), rays from above.  The map comes from this
+    # package's octree (bit-exact vs the reference's svo above, with per-tree node ids: the
+    # reference's ids are offset by a process-global counter)
     xy = torch.rand(3000, 2, generator=g) * 2.0 + 11.0
     pts = torch.cat([xy, torch.full((3000, 1), 12.05) + torch.rand(3000, 1, generator=g) * 0.3], 1)
-    ref_tree.insert(torch.div(pts, 0.2, rounding_mode='floor').int())
-    voxels, children, features = ref_tree.get_centres_and_children()
-    # node ids are process-global in the reference: make them local rows of the table
-    base = int(features[features >= 0].min()) if (features >= 0).any() else 0
+    builder = SparseVoxelConfig().setup(camera=Camera(320, 320, 319.5, 239.5, 640, 480))
+    builder.insert_points(pts)
+    voxels, children, features = builder.export_octree()
     ora = VoxOracle(seed=5)
-    feats_local = torch.where(features >= 0, features - base, features)
-    ora.set_map(voxels, children, feats_local)
+    ora.set_map(voxels, children, features)
     with torch.no_grad():
         ora.embeddings.mul_(30.0)
     R = 96
