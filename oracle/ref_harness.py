@@ -226,12 +226,26 @@ import contextlib
 
 @contextlib.contextmanager
 def cuda_calls_are_noops():
-    """The reference hard-codes `.cuda()` in a few helpers (voxel_helpers_voxfusion.py:108-110):
-    on this GPU-less container they become identity for the duration of the block."""
+    """The reference hard-codes `.cuda()` / `.to('cuda:N')` in a few helpers
+    (voxel_helpers_voxfusion.py:108-110, decoder_nice.py:388-405): on this GPU-less container
+    they become identity for the duration of the block."""
     import torch
-    orig_t, orig_p = torch.Tensor.cuda, torch.nn.Parameter.cuda if hasattr(torch.nn.Parameter, 'cuda') else None
+    orig_cuda, orig_to = torch.Tensor.cuda, torch.Tensor.to
+
+    def to(self, *a, **k):
+        # decoder_nice.py:388 builds device = f'cuda:{p.get_device()}' ('cuda:-1' on the host)
+        if a and isinstance(a[0], str) and a[0].startswith('cuda'):
+            a = a[1:]
+            if not a and not k:
+                return self
+        if isinstance(k.get('device'), str) and k['device'].startswith('cuda'):
+            k = {kk: v for kk, v in k.items() if kk != 'device'}
+            if not a and not k:
+                return self
+        return orig_to(self, *a, **k)
     torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.Tensor.to = to
     try:
         yield
     finally:
-        torch.Tensor.cuda = orig_t
+        torch.Tensor.cuda, torch.Tensor.to = orig_cuda, orig_to

@@ -241,6 +241,21 @@ def test_nice_oracle_matches_reference_class_live():
         ld_o = ora.loss_dict(out_o, ts, td, m, 'color')
         for k in ld_r:
             assert float(ld_r[k].detach()) == float(ld_o[k].detach()), (m, k)
+    # stages middle / fine are CUDA-only in the reference (Q5: device = f'cuda:{p.get_device()}');
+    # with that string neutralised the reference's own class runs them on the host
+    with ref_harness.cuda_calls_are_noops():
+        for stage in ('middle', 'fine'):
+            inp_s = dict(inp, stage=stage)
+            out_r = ref(inp_s)
+            out_o = ora.render(rays_o, rays_d, td, stage)
+            for k in ('depth', 'uncertainty'):
+                assert torch.equal(out_r[k], out_o[k]), (stage, k)
+            for m in (True, False):
+                ld_r = ref.get_loss_dict(out_r, inp_s, m, stage)
+                ld_o = ora.loss_dict(out_o, ts, td, m, stage)
+                assert set(ld_r) == set(ld_o)
+                for k in ld_r:
+                    assert float(ld_r[k].detach()) == float(ld_o[k].detach()), (stage, m, k)
     # the reference's grid-shape hazard at the default office0 bound
     ref2 = ref_harness.ref_conv_onet(np.array([[-5.5, 5.9], [-6.7, 5.4], [-4.7, 5.3]]))
     assert tuple(ref2.grid_c['grid_middle'].shape) == (1, 32, 31, 37, 35)
