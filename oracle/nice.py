@@ -13,10 +13,11 @@ Follows (reference @ f0366f20, paths relative to /root/reference):
   slam/common/common.py:16-31        normalize_3d_coordinate
   slam/model_components/utils.py:189-244  raw2outputs_nerf_color (occupancy)
   slam/models/conv_onet.py:145-185   get_loss_dict
-Pinned against the reference's own ConvOnet (stage 'color', the one stage that runs on CPU,
-SURVEY Q5) by tests/test_oracle_cpu.py::test_nice_oracle_matches_reference_class_live and the
-committed vectors tests/golden/nice_*.npz.  Stages middle / fine only differ in NICE.forward's
-dispatch (decoder_nice.py:396-414), restated here.
+Pinned bit-identically against the reference's own ConvOnet, all three stages, by
+tests/test_oracle_cpu.py::test_nice_oracle_matches_reference_class_live (stage 'color' runs on
+the host as is; for 'middle' / 'fine' the hard-coded 'cuda:N' device string of
+decoder_nice.py:388, SURVEY Q5, is neutralised by oracle/ref_harness.cuda_calls_are_noops) and
+by the committed vectors tests/golden/nice_*.npz.
 
 Grids are held in the reference layout [1, C, Z, Y, X]; F.grid_sample is torch's own.
 """
