@@ -425,3 +425,36 @@ def test_keyframe_selection_overlap_on_host():
     ids = sorted(f.fid for f in sel)
     assert ids == [1, 3], ids
     assert len(keyframe_selection_overlap(cam, frames[0], frames[1:], k=1, device='cpu')) == 1
+
+
+@pytest.mark.needs_reference
+def test_host_frontend_bit_identical_to_reference_functions():
+    """common.get_samples / get_rays / get_camera_rays (host tensors) against the reference's
+    own slam.common.common / slam.utils.utils functions under the same torch seed: identical
+    pixel draws, rays, depth / colour gathers and index outputs (rows A1-A5)."""
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip('needs /root/reference')
+    ref_harness.install()
+    import slam.common.common as rc
+    import slam.utils.utils as ru
+    from slam.common.camera import Camera as RCam
+    import xrdslam_b200.common as mc
+    from xrdslam_b200.synthetic import make_sequence
+    cam, poses, fr = make_sequence(1, width=160, height=120)
+    rcam = RCam(cam.fx, cam.fy, cam.cx, cam.cy, cam.width, cam.height)
+    c2w = torch.from_numpy(poses[0])
+    rgb, depth = fr[0]
+    for kw in (dict(Hedge=0, Wedge=0), dict(Hedge=7, Wedge=11),
+               dict(Hedge=3, Wedge=5, depth_filter=True, return_index=True)):
+        torch.manual_seed(5)
+        a = rc.get_samples(rcam, 333, c2w, depth, rgb, device='cpu', **kw)
+        torch.manual_seed(5)
+        b = mc.get_samples(cam, 333, c2w, depth, rgb, device='cpu', **kw)
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            assert x.dtype == y.dtype and torch.equal(x, y), kw
+    for x, y in zip(rc.get_rays(rcam, c2w, 'cpu'), mc.get_rays(cam, c2w, 'cpu')):
+        assert torch.equal(x, y)
+    assert torch.equal(torch.as_tensor(ru.get_camera_rays(120, 160, cam.fx, cam.fy, cam.cx, cam.cy)),
+                       mc.get_camera_rays(120, 160, cam.fx, cam.fy, cam.cx, cam.cy))
