@@ -458,3 +458,35 @@ def test_host_frontend_bit_identical_to_reference_functions():
         assert torch.equal(x, y)
     assert torch.equal(torch.as_tensor(ru.get_camera_rays(120, 160, cam.fx, cam.fy, cam.cx, cam.cy)),
                        mc.get_camera_rays(120, 160, cam.fx, cam.fy, cam.cx, cam.cy))
+
+
+@pytest.mark.needs_reference
+def test_optimizers_match_reference_engine_incl_accum_step():
+    """xrdslam_b200.optimizers.Optimizers (zero_grad_all / optimizer_step_all, accum_step = 5,
+    weight decay, custom betas) against the reference's own slam.engine.optimizers on host
+    parameters: bit-identical after 12 steps (rows B2 / B3, Q11)."""
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip('needs /root/reference')
+    ref_harness.install()
+    import slam.engine.optimizers as ro
+    import xrdslam_b200.optimizers as mo
+
+    def run(mod):
+        A = mod.AdamOptimizerConfig
+        torch.manual_seed(0)
+        p = {'a': [torch.nn.Parameter(torch.randn(5))], 'pose': [torch.nn.Parameter(torch.randn(3))]}
+        cfg = {'a': {'optimizer': A(lr=1e-2, weight_decay=1e-6, betas=(0.9, 0.99)), 'scheduler': None},
+               'pose': {'optimizer': A(lr=1e-3, accum_step=5), 'scheduler': None}}
+        opt = mod.Optimizers(cfg, p)
+        g = torch.Generator().manual_seed(1)
+        for step in range(12):
+            opt.zero_grad_all()
+            for k in p:
+                gr = torch.randn(p[k][0].shape, generator=g)
+                p[k][0].grad = gr if p[k][0].grad is None else p[k][0].grad + gr
+            opt.optimizer_step_all(step=step)
+        return {k: v[0].detach().clone() for k, v in p.items()}
+    a, b = run(ro), run(mo)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
