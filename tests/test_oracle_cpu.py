@@ -490,3 +490,38 @@ def test_optimizers_match_reference_engine_incl_accum_step():
     a, b = run(ro), run(mo)
     for k in a:
         assert torch.equal(a[k], b[k]), k
+
+
+@pytest.mark.needs_reference
+def test_keyframe_selection_overlap_matches_reference_function():
+    """Same seeds -> the same keyframes in the same order as the reference's own
+    slam.common.common.keyframe_selection_overlap (host tensors)."""
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip('needs /root/reference')
+    ref_harness.install()
+    import slam.common.common as rc
+    from slam.common.camera import Camera as RCam
+    from xrdslam_b200.frame import Frame
+    from xrdslam_b200.keyframe_selection import keyframe_selection_overlap
+    from xrdslam_b200.synthetic import CENTRE, look_at, make_camera, render_frame
+    cam = make_camera(160, 120)
+    rcam = RCam(cam.fx, cam.fy, cam.cx, cam.cy, cam.width, cam.height)
+    eye = CENTRE + np.array([0.5, 0.0, 0.1])
+    tgt = CENTRE + np.array([-1.5, 0.3, -0.2])
+    rng = np.random.default_rng(0)
+    poses = [look_at(eye, tgt)] + [look_at(eye + rng.normal(size=3) * 0.3, tgt + rng.normal(size=3) * 0.8)
+                                   for _ in range(7)] + [look_at(eye, eye + (eye - tgt))]
+    frames = []
+    for k, p in enumerate(poses):
+        rgb, depth = render_frame(cam, p, seed=k)
+        frames.append(Frame(k, rgb, depth, init_pose=p, rot_rep='quat'))
+    for k in (2, 4, 8):
+        torch.manual_seed(3)
+        np.random.seed(3)
+        a = rc.keyframe_selection_overlap(rcam, frames[0], frames[1:], k, device='cpu')
+        torch.manual_seed(3)
+        np.random.seed(3)
+        b = keyframe_selection_overlap(cam, frames[0], frames[1:], k, device='cpu')
+        assert [f.fid for f in a] == [f.fid for f in b], k
+    assert 8 not in [f.fid for f in b]  # the frame looking the other way has no overlap
