@@ -257,9 +257,11 @@ class CoSLAM(Algorithm):
 
     def tracking_session(self):
         from .coslam_graph import TrackingGraphSession
+        key = (self.config.tracking_sample, self.config.tracking_Hedge, self.config.tracking_Wedge)
         s = self.__dict__.get('_track_session')
-        if s is None:
+        if s is None or s.key != key:  # the sample count / crop are baked into the graph
             s = self.__dict__['_track_session'] = TrackingGraphSession(self)
+            s.key = key
         return s
 
     def optimize_update(self, n_iters, optimize_frames, is_mapping, coarse=False):
