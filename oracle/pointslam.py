@@ -25,8 +25,7 @@ import torch.nn.functional as F
 FLT_MAX = float(np.finfo(np.float32).max)
 
 
-def exact_knn(cloud, q, k=8):
-    """Exact k-NN (squared L2, float32, ((dx^2 + dy^2) + dz^2)), ties by lower id."""
+def _exact_knn_sort(cloud, q, k):
     d = (cloud[None, :, :] - q[:, None, :])
     D = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
     N = cloud.shape[0]
@@ -37,6 +36,36 @@ def exact_knn(cloud, q, k=8):
     vals, idx = vals[:, :k], idx[:, :k]
     idx = torch.where(idx < N, idx, torch.full_like(idx, -1))
     return vals, idx
+
+
+def exact_knn(cloud, q, k=8, chunk=1024):
+    """Exact k-NN (squared L2, float32, ((dx^2 + dy^2) + dz^2)), ties by lower id.
+    Large problems run in query chunks with top-(k+1) selection; the selected k are then
+    ordered by (distance, id) and any row whose k-th and (k+1)-th distances tie falls back to
+    the full stable sort -- the result is the stable sort's for every row."""
+    N = cloud.shape[0]
+    if N <= 4 * k or q.shape[0] * N <= (1 << 22):
+        return _exact_knn_sort(cloud, q, k)
+    vals_all, idx_all = [], []
+    for s in range(0, q.shape[0], chunk):
+        qc = q[s:s + chunk]
+        d = (cloud[None, :, :] - qc[:, None, :])
+        D = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+        v, i = torch.topk(D, k + 1, dim=1, largest=False)
+        # order the candidates by (distance, id): two stable sorts
+        o = torch.argsort(i, dim=1, stable=True)
+        v, i = torch.gather(v, 1, o), torch.gather(i, 1, o)
+        o = torch.argsort(v, dim=1, stable=True)
+        v, i = torch.gather(v, 1, o), torch.gather(i, 1, o)
+        tie = v[:, k] == v[:, k - 1]
+        v, i = v[:, :k].clone(), i[:, :k].clone()
+        for r in torch.nonzero(tie).flatten().tolist():
+            vr, ir = _exact_knn_sort(cloud, qc[r:r + 1], k)
+            v[r], i[r] = vr[0], ir[0]
+        # equal distances inside the top k: the stable sort lists the lower id first -- done
+        vals_all.append(v)
+        idx_all.append(i)
+    return torch.cat(vals_all), torch.cat(idx_all)
 
 
 class GeoDecoder(nn.Module):

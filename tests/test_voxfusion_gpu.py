@@ -205,3 +205,117 @@ def test_no_hit_returns_none(cuda_dev):
     rd = torch.tensor([[0.0, 0.0, 1.0]], device=dev).expand(16, 3).contiguous()
     out = model(dict(rays_o=ro, rays_d=rd, target_s=ts[:16].to(dev), target_d=td[:16].to(dev)))
     assert out is None  # reference: render_rays prints "no hit" and returns None
+
+
+def _march_through_reference_grid(grid, ora, rays_o, rays_d, noise_fn, dev):
+    """VoxOracle.march with BOTH native stages executed by the reference's own compiled CUDA
+    extension (oracle/_ref/grid.so: svo_intersect + inverse_cdf_sampling), glued exactly as
+    voxel_helpers_voxfusion.py:237-255,399-481 glue them.  The CPU restatement divides
+    exactly where the reference kernels use __fdividef; chained through grid.so the oracle
+    sees the reference's own bits."""
+    from oracle.voxfusion import MAX_DEPTH, ray_intersect
+
+    def gpu_intersect(ro, rd, cen, ch, vs, n_max):
+        i, a, b = grid.svo_intersect(ro[None].to(dev).contiguous(), rd[None].to(dev).contiguous(),
+                                     cen[None].to(dev).contiguous(), ch[None].to(dev).contiguous(),
+                                     vs, n_max)
+        return i[0].cpu(), a[0].cpu(), b[0].cpu()
+    inter, hits = ray_intersect(rays_o, rays_d, ora.centres, ora.children, ora.voxel_size,
+                                intersect_fn=gpu_intersect)
+    inter = {k: v[hits] for k, v in inter.items()}
+    dists = (inter['max_depth'] - inter['min_depth']).masked_fill(
+        inter['intersected_voxel_idx'].eq(-1), 0)
+    probs = dists / dists.sum(dim=-1, keepdim=True)
+    steps = dists.sum(-1) / ora.step_size
+    pts_idx = inter['intersected_voxel_idx']
+    G, N, P = 200, pts_idx.size(0), pts_idx.size(1)
+    Hh = int(np.ceil(N / G)) * G
+    pad = lambda t: torch.cat([t, t[:1].expand(Hh - N, *t.shape[1:])], 0) if Hh > N else t
+    pi, mn, mx, pr, stp = map(pad, (pts_idx, inter['min_depth'], inter['max_depth'], probs, steps))
+    K = Hh // G
+    max_steps = int(steps.ceil().long().max()) + P
+    noise = noise_fn((G, K, max_steps))
+    d = lambda t: t.to(dev).contiguous()
+    r_idx, r_depth, r_dist = grid.inverse_cdf_sampling(
+        d(pi.reshape(G, K, P)), d(mn.reshape(G, K, P)), d(mx.reshape(G, K, P)), d(noise),
+        d(pr.reshape(G, K, P)), d(stp.reshape(G, K)), -1)
+    s_idx = r_idx.reshape(Hh, -1)[:N].cpu()
+    s_depth = r_depth.reshape(Hh, -1)[:N].cpu()
+    s_dist = r_dist.reshape(Hh, -1)[:N].cpu()
+    max_len = int(s_idx.ne(-1).sum(-1).max())
+    s_idx, s_depth, s_dist = s_idx[:, :max_len], s_depth[:, :max_len], s_dist[:, :max_len]
+    s_dist = s_dist.clamp(min=0.0)
+    s_depth = s_depth.masked_fill(s_idx.eq(-1), MAX_DEPTH)
+    s_dist = s_dist.masked_fill(s_idx.eq(-1), 0.0)
+    samples = {'sampled_point_depth': s_depth, 'sampled_point_distance': s_dist,
+               'sampled_point_voxel_idx': s_idx, 'probs': probs, 'steps': steps, 'K': K}
+    return inter, hits, samples
+
+
+@pytest.mark.parametrize('R', [300, 5 * 1024])
+def test_full_step_vs_oracle_chained_through_reference_grid(cuda_dev, R):
+    """Full step (march + sample + decode + composite + loss + backward) with the oracle fed
+    the reference extension's own intersections / samples: sample->voxel ids and depths
+    BIT-EXACT, gradients rel-l2 <= 5e-4.  R = 5 x 1024 is the default mapping batch
+    (5 keyframes x 1024 rays, slam/configs/input_config.py vox-fusion entry)."""
+    from oracle.voxfusion import VoxOracle
+    grid = ref_grid()
+    model, rays_o, rays_d, ts, td = scene(cuda_dev, R=R, seed=4)
+    dev = cuda_dev
+    ora = VoxOracle()
+    with torch.no_grad():
+        g = torch.Generator().manual_seed(9)
+        model.embeddings.copy_(torch.randn(model.embeddings.shape, generator=g) * 0.3)
+        ora.embeddings.copy_(model.embeddings.cpu())
+        ora.decoder.load_state_dict(model.decoder.state_dict())
+    voxels, children, features = model.export_octree()
+    ora.set_map(voxels, children, features)
+    gen = torch.Generator().manual_seed(5)
+    noise_rank = torch.rand(rays_o.shape[0], model.config.max_samples_per_ray,
+                            generator=gen).clamp(0.001, 0.999)
+
+    def noise_fn(shape):
+        G, K, ms = shape
+        out = torch.full((G * K, ms), 0.5)
+        n = min(G * K, noise_rank.shape[0])
+        out[:n] = noise_rank[:n, :ms]
+        return out.reshape(G, K, ms)
+    ro_o = rays_o.clone().requires_grad_(True)
+    rd_o = rays_d.clone().requires_grad_(True)
+    marched = _march_through_reference_grid(grid, ora, ro_o.detach(), rd_o.detach(), noise_fn, dev)
+    out_o, ld_o = ora.render(ro_o, rd_o, ts, td, marched)
+    sum(ld_o.values()).backward()
+    hits = marched[1]
+    rank = torch.cumsum(hits.long(), 0) - 1
+    noise = torch.full((rays_o.shape[0], model.config.max_samples_per_ray), 0.5)
+    noise[hits] = noise_rank[rank[hits]]
+    ro = rays_o.to(dev).requires_grad_(True)
+    rd = rays_d.to(dev).requires_grad_(True)
+    inp = dict(rays_o=ro, rays_d=rd, target_s=ts.to(dev), target_d=td.to(dev), noise=noise.to(dev))
+    out = model(inp)
+    ld = model.get_loss_dict(out, inp, True, 0)
+    sum(ld.values()).backward()
+    torch.cuda.synchronize()
+    m = model.last_march
+    assert m['overflow'] == 0
+    assert torch.equal(out['ray_mask'].cpu(), hits)
+    smp = marched[2]
+    S = smp['sampled_point_voxel_idx'].shape[1]
+    assert m['s_max'] == S and m['n_hit_rays'] == int(hits.sum())
+    got_idx = m['smp_idx'].cpu()[hits][:, :S]
+    assert torch.equal(got_idx, smp['sampled_point_voxel_idx'])               # bit-exact
+    valid = got_idx >= 0
+    assert torch.equal(m['smp_depth'].cpu()[hits][:, :S][valid],
+                       smp['sampled_point_depth'][valid])                     # bit-exact
+    assert max_abs(out['depth'], out_o['depth']) < 5e-5
+    assert max_abs(out['rgb'], out_o['rgb']) < 5e-5
+    for k in ld_o:
+        a, b = float(ld[k].detach()), float(ld_o[k].detach())
+        assert abs(a - b) <= 1e-4 * max(abs(b), 1e-6), (k, a, b)
+    TOL = 5e-4
+    assert rel_err(model.embeddings.grad, ora.embeddings.grad) < TOL
+    sd_o = dict(ora.decoder.named_parameters())
+    for n, p in model.decoder.named_parameters():
+        assert rel_err(p.grad, sd_o[n].grad) < TOL, n
+    assert rel_err(ro.grad, ro_o.grad) < TOL
+    assert rel_err(rd.grad, rd_o.grad) < TOL

@@ -143,11 +143,51 @@ class Algorithm():
         with self.lock:
             self.keyframe_graph.append(keyframe)
 
+    # accessors the pipeline processes call through the Manager proxy
+    # (base_algorithm.py:116-158; slam/pipeline/{tracker,mapper,xrdslam}.py)
+    def get_estimate_c2w_list(self):
+        with self.lock:
+            return self.estimate_c2w_list
+
+    def get_gt_c2w_list(self):
+        with self.lock:
+            return self.gt_c2w_list
+
+    def get_gt_c2w_list_ori(self):
+        with self.lock:
+            return self.gt_c2w_list_ori
+
+    def is_separate_LR(self):
+        with self.lock:
+            return self.config.separate_LR
+
+    def get_rot_rep(self):
+        with self.lock:
+            return self.config.rot_rep
+
     def is_initialized(self):
-        return self.initialized
+        with self.lock:
+            return self.initialized
 
     def set_initialized(self):
-        self.initialized = True
+        with self.lock:
+            self.initialized = True
+
+    def is_finished(self):
+        with self.lock:
+            return self.finished
+
+    def set_finished(self):
+        with self.lock:
+            self.finished = True
+
+    @staticmethod
+    def release_frame_tensors(frame):
+        """Drop the device-resident copies of a frame's images (_frame_tensor).  Called for
+        frames that leave the optimisation window without becoming keyframes; keyframe
+        containers that keep their images decide for themselves."""
+        for k in ('_dev_depth', '_dev_rgb', '_ray_table'):
+            frame.__dict__.pop(k, None)
 
     # ---- optimisation -----------------------------------------------------
     def setup_optimizers(self, n_iters, optimize_frames, is_mapping=True,
@@ -183,6 +223,12 @@ class Algorithm():
         if self.is_initialized():
             return self.optimize_update(self.config.tracking_n_iters,
                                         [cur_frame], is_mapping=False)
+
+    def finish_frame(self, frame):
+        """The pipeline is done with `frame` (tracked, and mapped if it was a map frame):
+        free its device images unless a keyframe container still needs them."""
+        if not any(frame is kf for kf in self.keyframe_graph):
+            self.release_frame_tensors(frame)
 
     def do_mapping(self, cur_frame):
         n_iters = (self.config.mapping_n_iters if self.is_initialized() else

@@ -18,6 +18,39 @@ from torch.nn import Parameter
 Outputs = Dict[str, Union[torch.Tensor, List]]
 
 
+def upstream_scale(g_losses: torch.Tensor, n_live: int = None) -> torch.Tensor:
+    """Device scalar that the in-kernel gradients are multiplied with in ``backward``.
+
+    The fused steps compute d(sum of the weighted loss terms)/d(parameters) during forward.
+    Autograd's upstream gradient ``g_losses`` (one entry per loss term) is 1 under the plugin
+    contract ``loss = reduce(add, loss_dict.values()); loss.backward()``
+    (slam/algorithms/base_algorithm.py:263-266); a caller that scales the TOTAL loss
+    (``(c * loss).backward()``, gradient-accumulation scaling) sends c for every term and gets
+    c * gradient.  Unequal per-term scales cannot be honoured from the summed gradient: the
+    scalar becomes NaN so the mistake is loud (Co-SLAM's ``strict_loss_grad`` re-runs the
+    fused pass with the per-term scales instead).  ``n_live``: only the first n_live terms
+    entered the in-kernel gradient (NICE / Point-SLAM leave the colour term out of some
+    stages; its upstream gradient is then 0 and is ignored).  No host synchronisation."""
+    g = g_losses.detach().reshape(-1).float()
+    if n_live is not None:
+        g = g[:n_live]
+    same = (g == g[0]).all()
+    return torch.where(same, g[0], torch.full_like(g[0], float('nan')))
+
+
+def scale_grads(grads, s):
+    """In-place ``t *= s`` for every tensor in a (nested) list; None passes through."""
+    out = []
+    for t in grads:
+        if t is None:
+            out.append(None)
+        elif isinstance(t, (list, tuple)):
+            out.append(scale_grads(t, s))
+        else:
+            out.append(t.mul_(s.to(t.dtype)))
+    return out
+
+
 @dataclass
 class InstantiateConfig:
     """A config knows the class it configures: ``cfg.setup(**kw)`` builds ``_target(cfg, **kw)``."""

@@ -25,7 +25,7 @@ from torch.nn import Parameter
 from . import _cabi
 from ._cabi import (XrdNiceCfg, XrdNiceDecoder, XrdNiceDecoderGrads, XrdNiceGrads,
                     XrdNiceGrid, XrdNiceOut, XrdRays, check, ptr)
-from .base_model import Model, ModelConfig
+from .base_model import Model, ModelConfig, scale_grads, upstream_scale
 
 STAGES = {'middle': 0, 'fine': 1, 'color': 2}
 
@@ -137,6 +137,9 @@ class _NiceStep(torch.autograd.Function):
         outs, grads = model._launch(stage, is_mapping, rays_o, rays_d, target_s, target_d,
                                     with_grads, need_rays, need_grid, need_col)
         ctx.grads = grads
+        cfg = model.config  # the colour term is live exactly when get_loss_dict returns it
+        ctx.n_live = 2 if ((not is_mapping and cfg.tracking_use_color_in_tracking) or
+                           (is_mapping and stage == 'color')) else 1
         ret = (outs['losses'], outs['rgb'], outs['depth'], outs['uncertainty'])
         ctx.mark_non_differentiable(*ret[1:])
         return ret
@@ -146,8 +149,9 @@ class _NiceStep(torch.autograd.Function):
         g = ctx.grads
         if g is None:
             raise RuntimeError('backward through a forward-only NICE pass')
-        return (None, None, None, None, None, g['d_rays_o'], g['d_rays_d'], g['d_grid'][0],
-                g['d_grid'][1], g['d_grid'][2], *g['d_color'])
+        ro, rd, dg, dc = scale_grads([g['d_rays_o'], g['d_rays_d'], list(g['d_grid']),
+                                      list(g['d_color'])], upstream_scale(g_losses, ctx.n_live))
+        return (None, None, None, None, None, ro, rd, dg[0], dg[1], dg[2], *dc)
 
 
 class ConvOnet(Model):

@@ -21,7 +21,7 @@ from . import _cabi
 from ._cabi import (XrdNiceDecoder, XrdPointCfg, XrdPointColorDecoder,
                     XrdPointColorDecoderGrads, XrdPointFeats, XrdPointGrads, XrdPointOut,
                     XrdRays, check, ptr)
-from .base_model import Model, ModelConfig
+from .base_model import Model, ModelConfig, scale_grads, upstream_scale
 from .conv_onet import MLP as _GeoMLP
 from .conv_onet import _dec_struct
 from .neural_point_cloud import NeuralPointCloud
@@ -153,6 +153,8 @@ class _PointStep(torch.autograd.Function):
             need_col_feats=color and need[11], need_cdec=color and any(need[12:]))
         ctx.grads = grads
         ctx.n_c = len(cparams)
+        ctx.n_live = 2 if ((is_mapping and color) or
+                           (not is_mapping and model.config.tracking_use_color_in_tracking)) else 1
         ret = (outs['losses'], outs['rgb'], outs['depth'], outs['uncertainty'],
                outs['valid_ray_mask'])
         ctx.mark_non_differentiable(*ret[1:])
@@ -162,8 +164,9 @@ class _PointStep(torch.autograd.Function):
     def backward(ctx, g_losses, *_):
         g = ctx.grads
         dc = g['d_cdec'] if g['d_cdec'] is not None else [None] * ctx.n_c
-        return (None, None, None, None, None, None, None, None, g['d_rays_o'], g['d_rays_d'],
-                g['d_geo_feats'], g['d_col_feats'], *dc)
+        ro, rd, gf, cf, dc = scale_grads([g['d_rays_o'], g['d_rays_d'], g['d_geo_feats'],
+                                          g['d_col_feats'], list(dc)], upstream_scale(g_losses, ctx.n_live))
+        return (None, None, None, None, None, None, None, None, ro, rd, gf, cf, *dc)
 
 
 class ConvOnet2(Model):

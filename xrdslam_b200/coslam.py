@@ -166,7 +166,10 @@ class CoSLAM(Algorithm):
                 self.rays = self.rays.pin_memory()
             keyframe.rgb = None
             keyframe.depth = None
-            keyframe.__dict__.pop('_ray_table', None)
+            # the full-resolution copies made for sampling / tracking are dropped with the
+            # images (the reference keeps only the ray bank, coslam.py:133-137)
+            for k in ('_ray_table', '_dev_depth', '_dev_rgb'):
+                keyframe.__dict__.pop(k, None)
             self.keyframe_graph.append(keyframe)
 
     def sample_global_rays(self, bs):
@@ -193,6 +196,13 @@ class CoSLAM(Algorithm):
                 torch.empty(n, 7), torch.empty(n, dtype=torch.int64))
             pose_list, detach = [], []
             if n_kf > 0:
+                if len(optimize_frames) != n_kf + 1:
+                    # bank ids index the whole keyframe graph; the reference's
+                    # poses_all[ids_all] (coslam.py:208) raises the same way when the
+                    # window is a subset (keyframe_selection_method != 'all')
+                    raise IndexError(
+                        f'co-slam mapping window has {len(optimize_frames) - 1} keyframes but '
+                        f'the ray bank indexes {n_kf}: use keyframe_selection_method="all"')
                 idxs = self._sample_ids(n_kf * self.num_rays_to_save, n_bank)
                 torch.index_select(self.rays, 0, idxs, out=rows[:n_bank])
                 torch.div(idxs, self.num_rays_to_save, rounding_mode='floor',
@@ -247,10 +257,16 @@ class CoSLAM(Algorithm):
             self.config.mapping_sample // n_kf, self.config.min_sample_pixels))
         ba = self.bundle_adjust and len(optimize_frames) > 1
         key = (n_bank, n_cur, len(optimize_frames), first, ba)
+        # ONE live session: under keyframe_selection 'all' the window grows with every keyframe,
+        # so the shape key changes for good -- the previous session (flat gradient bucket the
+        # size of the hash table, raw outputs, workspace, the graph's private pool) is released
+        # before the new one is captured instead of piling up over a sequence.
         cache = self.__dict__.setdefault('_graph_sessions', {})
+        for k in [k for k in cache if k != key]:
+            cache.pop(k).release()
         if key in cache and (cache[key].stale() or
                              cache[key].opt_groups[0][0] is not self.model_optimizers.optimizers['embed_fn']):
-            del cache[key]  # optimiser state / parameters were replaced: re-capture
+            cache.pop(key).release()  # optimiser state / parameters were replaced: re-capture
         if key not in cache:
             cache[key] = MappingGraphSession(self, n_bank, n_cur, len(optimize_frames), first, ba)
         return cache[key]

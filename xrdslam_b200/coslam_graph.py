@@ -87,7 +87,12 @@ class MappingGraphSession:
         off += 2 * n_pose
         self.losses, self.smooth_loss = self.flat[off:off + 4], self.flat[off + 4:off + 5]
         self.counts = torch.zeros(4, dtype=torch.int32, device=dev)
-        self._gen = torch.Generator().manual_seed(977) if self.world > 1 else None
+        # sharded mapping: every rank must draw the SAME smoothness lattice -> a generator with
+        # a fixed seed, owned by the algorithm so that it keeps advancing across sessions
+        # (a per-session generator would replay the same offsets after every re-capture)
+        if self.world > 1 and getattr(algo, '_smooth_gen', None) is None:
+            algo._smooth_gen = torch.Generator().manual_seed(977)
+        self._gen = algo._smooth_gen if self.world > 1 else None
         self.pose_state = None
         # Adam state must exist BEFORE capture: tensors created while capturing come from the
         # graph's private pool and their zero-fill would be replayed every iteration
@@ -238,6 +243,13 @@ class MappingGraphSession:
                     self.graphs.append(g)
         self.d_rot.zero_()
         self.d_trans.zero_()
+
+    def release(self):
+        """Drop the captured graphs and every device buffer of this session."""
+        self.graphs = []
+        for k in ('flat', 'grads', 'out', 'ws', 'ws_s', 'rows', 'ids', 'rays_o', 'rays_d',
+                  'd_rays_o', 'd_rays_d', 'dirs', 'ts', 'td'):
+            self.__dict__.pop(k, None)
 
     # ------------------------------------------------------------------ running ---
     def stale(self):

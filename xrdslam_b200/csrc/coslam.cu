@@ -244,24 +244,32 @@ __device__ __forceinline__ void blob_forward(const float xn[3], float* __restric
   }
 }
 
-// dx[d] += sum_b dblob[d*16+b] * d out_b / dx  (dblob read through the functor)
+// d/dx of dimension d's 16 OneBlob outputs, contracted with dblob (read through the functor)
+template <typename F>
+__device__ __forceinline__ float blob_backward_dim(float x, int d, F dblob) {
+  float acc = 0.f;
+#pragma unroll
+  for (int s = -1; s <= 1; ++s) {
+    const float u = (x - (float)s) * (float)kBins;
+    const float fl = floorf(u);
+    if (fl < -1.f || fl > (float)kBins) continue;
+    const int b0 = (int)fl;
+    const float f = u - fl;
+    const float p0 = qpdf(-f), p1 = qpdf(1.f - f);  // d cdf(-f)/dx = -16 p0, d cdf(1-f)/dx = -16 p1
+    if (b0 - 1 >= 0 && b0 - 1 < kBins) acc -= dblob(d * kBins + b0 - 1) * p0;
+    if (b0 >= 0 && b0 < kBins) acc += dblob(d * kBins + b0) * (p0 - p1);
+    if (b0 + 1 >= 0 && b0 + 1 < kBins) acc += dblob(d * kBins + b0 + 1) * p1;
+  }
+  return acc * (float)kBins;
+}
+
+// dx[d] += sum_b dblob[d*16+b] * d out_b / dx
 template <typename F>
 __device__ __forceinline__ void blob_backward(const float xn[3], F dblob, float dx[3]) {
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    float acc = 0.f;
-#pragma unroll
-    for (int s = -1; s <= 1; ++s) {
-      const float u = (xn[d] - (float)s) * (float)kBins;
-      const float fl = floorf(u);
-      if (fl < -1.f || fl > (float)kBins) continue;
-      const int b0 = (int)fl;
-      const float f = u - fl;
-      const float p0 = qpdf(-f), p1 = qpdf(1.f - f);  // d cdf(-f)/dx = -16 p0, d cdf(1-f)/dx = -16 p1
-      if (b0 - 1 >= 0 && b0 - 1 < kBins) acc -= dblob(d * kBins + b0 - 1) * p0;
-      if (b0 >= 0 && b0 < kBins) acc += dblob(d * kBins + b0) * (p0 - p1);
-      if (b0 + 1 >= 0 && b0 + 1 < kBins) acc += dblob(d * kBins + b0 + 1) * p1;
-    }
+    // (fmaf(acc, 16, dx) as one rounding: keeps the v4 kernel's bits)
+    float acc = blob_backward_dim(xn[d], d, dblob) * (1.0f / (float)kBins);
     dx[d] = fmaf(acc, (float)kBins, dx[d]);
   }
 }
@@ -973,6 +981,607 @@ __global__ void __launch_bounds__(256) k_fused(const Params P) {
   }
 }
 
+
+// ----------------------------------------------------------- fused, grouped ---
+// v5: the same record-based algorithm, re-organised for latency hiding.  One persistent CTA
+// per SM holds NGROUPS independent groups of 6 warps; a group owns GP record slots and pulls
+// units of NR rays from a global queue, so at any time one group is in its gather phase
+// (L1/L2 latency), another in the tensor-core phases and a third in the scatter phase: the
+// phases that were serialised behind __syncthreads() in k_fused now overlap on the SM.
+// Two threads share one sample point in the gather phases (8 levels each), one warp owns one
+// 16-row MMA tile; all intra-group synchronisation is a named barrier (bar.sync grp+1, 192).
+constexpr int GT = 192;      // threads per group
+constexpr int GW = 6;        // warps per group = m-tiles of 16 points per unit
+constexpr int GP = 96;       // record slots per group
+constexpr int NGROUPS = 3;
+constexpr int G_SLOTS = 7;   // 42 weight-gradient tiles / 6 warps
+
+__device__ __forceinline__ void group_sync(int grp) {
+  asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(GT) : "memory");
+}
+
+// hash levels half, half+2, ... and the OneBlob dims of this half (0: x,y  1: z)
+__device__ __forceinline__ void encode_half(const Params& P, const Lv* __restrict__ lv,
+                                            const float xn[3], float* __restrict__ rec, int half) {
+  const float2* __restrict__ tab = reinterpret_cast<const float2*>(P.table);
+#pragma unroll 2
+  for (int i = 0; i < kL / 2; ++i) {
+    const int l = half + 2 * i;
+    if (l >= P.g.n_levels) {
+      *reinterpret_cast<float2*>(rec + R_FEAT + 2 * l) = make_float2(0.f, 0.f);
+      continue;
+    }
+    float w[3];
+    uint32_t c[3];
+    const Lv L = lv[l];
+    pos_fract(xn[0], L.scale, w[0], c[0]);
+    pos_fract(xn[1], L.scale, w[1], c[1]);
+    pos_fract(xn[2], L.scale, w[2], c[2]);
+    float2 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      uint32_t idx = grid_index(L, c[0] + (k & 1), c[1] + ((k >> 1) & 1), c[2] + ((k >> 2) & 1));
+      v[k] = __ldg(&tab[idx]);
+    }
+    float f0 = 0.f, f1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float wk = ((k & 1) ? w[0] : 1.f - w[0]) * ((k & 2) ? w[1] : 1.f - w[1]) *
+                 ((k & 4) ? w[2] : 1.f - w[2]);
+      f0 = fmaf(wk, v[k].x, f0);
+      f1 = fmaf(wk, v[k].y, f1);
+    }
+    *reinterpret_cast<float2*>(rec + R_FEAT + 2 * l) = make_float2(f0, f1);
+  }
+  const int d_lo = half ? 2 : 0, d_hi = half ? 3 : 2;
+  for (int d = d_lo; d < d_hi; ++d) {
+    float* o = rec + R_BLOB + d * kBins;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(o + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int s = -1; s <= 1; ++s) {
+      const float u = (xn[d] - (float)s) * (float)kBins;
+      const float fl = floorf(u);
+      if (fl < -1.f || fl > (float)kBins) continue;
+      const int b0 = (int)fl;
+      const float f = u - fl;
+      const float c0 = qcdf(-f), c1 = qcdf(1.f - f);
+      if (b0 - 1 >= 0 && b0 - 1 < kBins) o[b0 - 1] += c0;
+      if (b0 >= 0 && b0 < kBins) o[b0] += c1 - c0;
+      if (b0 + 1 >= 0 && b0 + 1 < kBins) o[b0 + 1] += 1.f - c1;
+    }
+  }
+}
+
+// one 16-row m-tile: C[nt] += A * B   (A rows = wrec[row*REC + aoff + k])
+template <int KS, int NT, bool TRANS, bool PREC3>
+__device__ __forceinline__ void warp_gemm1(const float* __restrict__ wrec, int aoff,
+                                           const float* __restrict__ w, int ld, int koff,
+                                           int noff, float (&c)[NT][4]) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll 1
+  for (int ks = 0; ks < KS; ++ks) {
+    FragA<PREC3> a;
+    {
+      const float* r0 = wrec + g * REC + aoff + ks * 8 + t;
+      const float v[4] = {r0[0], r0[8 * REC], r0[4], r0[8 * REC + 4]};
+      a.set(v);
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      FragB<PREC3> b;
+      const int k0 = koff + ks * 8 + t, n0 = noff + nt * 8 + g;
+      if (TRANS) b.set(w[n0 * ld + k0], w[n0 * ld + k0 + 4]);
+      else b.set(w[k0 * ld + n0], w[(k0 + 4) * ld + n0]);
+      mma<PREC3>(c[nt], a, b);
+    }
+  }
+}
+template <int NT>
+__device__ __forceinline__ void zero_c1(float (&c)[NT][4]) {
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[nt][i] = 0.f;
+}
+template <int NT, bool RELU>
+__device__ __forceinline__ void store_c1(float* __restrict__ wrec, int coff, const float (&c)[NT][4]) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    float v0 = c[nt][0], v1 = c[nt][1], v2 = c[nt][2], v3 = c[nt][3];
+    if (RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+    float* r0 = wrec + g * REC + coff + nt * 8 + 2 * t;
+    *reinterpret_cast<float2*>(r0) = make_float2(v0, v1);
+    *reinterpret_cast<float2*>(r0 + 8 * REC) = make_float2(v2, v3);
+  }
+}
+
+template <bool BWD, bool PREC3, bool BPREC3>
+__global__ void __launch_bounds__(GT * NGROUPS, 1) k_fused_g(const Params P, int* __restrict__ queue) {
+  extern __shared__ __align__(16) float smem[];
+  float* sw = smem;  // SW_TOTAL
+  const int tid = threadIdx.x;
+  const int grp = tid / GT, gt = tid - grp * GT;
+  const int gw = gt >> 5, lane = gt & 31;
+  const int g = lane >> 2, t = lane & 3;
+  float* recs = sw + SW_TOTAL + grp * (GP * REC);
+  float* misc = sw + SW_TOTAL + NGROUPS * (GP * REC) + grp * (GP * 6);
+  float* zbuf = misc;          // GP z values
+  float* sgb = misc + GP;      // GP sigma(sdf/trunc)
+  float* ub = misc + 2 * GP;   // GP unnormalised weights
+  float* xnb = misc + 3 * GP;  // GP*3 normalised coordinates
+  const int S = P.S;
+
+  __shared__ Lv s_lv[kL];
+  __shared__ int s_unit[NGROUPS];
+  load_levels(s_lv, P.g);
+  for (int q = tid; q < SW_TOTAL; q += blockDim.x) sw[q] = 0.f;
+  for (int q = gt; q < GP * REC; q += GT) recs[q] = 0.f;
+  __syncthreads();
+  for (int q = tid; q < 80 * 32; q += blockDim.x) {
+    int i = q / 32, j = q % 32;
+    sw[SW0 + i * LD0 + j] = P.w_sdf0[j * 80 + i];
+  }
+  for (int q = tid; q < 32 * 16; q += blockDim.x) {
+    int i = q / 16, jp = q % 16;  // jp: geo0..14 -> torch out 1..15, jp 15 -> out 0 (sdf)
+    int jt = (jp + 1) & 15;
+    sw[SW1 + i * LD1 + jp] = P.w_sdf1[jt * 32 + i];
+  }
+  for (int q = tid; q < 63 * 32; q += blockDim.x) {
+    int i = q / 32, j = q % 32;
+    sw[SWC0 + i * LDC0 + j] = P.w_col0[j * 63 + i];
+  }
+  for (int q = tid; q < 32 * 3; q += blockDim.x) {
+    int i = q / 3, k = q % 3;
+    sw[SWC1 + i * LDC1 + k] = P.w_col1[k * 32 + i];
+  }
+
+  float fs_w = 0.f, sdf_w = 0.f, inv_nvalid = 0.f;
+  if (BWD) {
+    const float n_fs = (float)P.counts[0], n_sdf = (float)P.counts[1];
+    const float n = (float)(P.counts[0] + P.counts[1]);
+    fs_w = 1.0f - n_fs / n;
+    sdf_w = 1.0f - n_sdf / n;
+    inv_nvalid = 1.0f / (float)P.counts[2];
+  }
+  double l_rgb = 0.0, l_depth = 0.0, l_sdf = 0.0, l_fs = 0.0;
+  float dwacc[G_SLOTS][4];
+#pragma unroll
+  for (int j = 0; j < G_SLOTS; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dwacc[j][i] = 0.f;
+  __syncthreads();
+
+  const int p = gt >> 1, half = gt & 1;       // gather phases: two threads per point
+  float* rec = recs + p * REC;
+  float* wrec = recs + (gw * 16) * REC;       // MMA phases: this warp's 16 records
+  const bool need_dx = BWD && ((P.d_rays_o != nullptr) || (P.d_rays_d != nullptr));
+  const bool map_grads = BWD && (P.d_table != nullptr);
+  int prev_npts = 0;
+
+  for (;;) {
+    if (gt == 0) s_unit[grp] = atomicAdd(queue, 1);
+    group_sync(grp);  // also: every reader of the previous unit's records is done
+    const int unit = s_unit[grp];
+    if (unit >= P.n_tiles) break;
+    const int r0 = unit * P.NR;
+    const int nr = min(P.NR, P.R - r0);
+    const int npts = nr * S;
+    const bool active = p < npts;
+    const bool warp_active = gw * 16 < npts;
+    const int rl = active ? p / S : 0;
+    const int k = active ? p - rl * S : 0;
+    const int r = r0 + rl;
+    float xn[3] = {0.f, 0.f, 0.f};
+    float zv = 0.f;
+    // ---------------- phase 1: forward -------------------------------------
+    if (active) {
+      zv = P.z_vals[(size_t)r * S + k];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        float pt = __fadd_rn(P.rays_o[r * 3 + d], __fmul_rn(P.rays_d[r * 3 + d], zv));
+        xn[d] = normalise(pt, P.g.bmin[d], P.g.bmax[d]);
+      }
+      if (half == 0) {
+        zbuf[p] = zv;
+        xnb[p * 3] = xn[0]; xnb[p * 3 + 1] = xn[1]; xnb[p * 3 + 2] = xn[2];
+      }
+      encode_half(P, s_lv, xn, rec, half);
+    } else if (p < prev_npts) {
+      // rows left dirty by a larger unit must read as zero in every GEMM
+      float* z0 = rec + half * (REC / 2);
+#pragma unroll 1
+      for (int q = 0; q < REC / 2; q += 2) *reinterpret_cast<float2*>(z0 + q) = make_float2(0.f, 0.f);
+    }
+    prev_npts = npts;
+    __syncwarp();
+    if (warp_active) {
+      {  // h1 = relu(x W0^T)
+        float c[4][4];
+        zero_c1<4>(c);
+        warp_gemm1<10, 4, false, PREC3>(wrec, R_FEAT, sw + SW0, LD0, 0, 0, c);
+        store_c1<4, true>(wrec, R_H1, c);
+      }
+      __syncwarp();
+      {  // [geo, sdf] = h1 W1^T
+        float c[2][4];
+        zero_c1<2>(c);
+        warp_gemm1<4, 2, false, PREC3>(wrec, R_H1, sw + SW1, LD1, 0, 0, c);
+        store_c1<2, false>(wrec, R_GEO, c);
+      }
+      __syncwarp();
+      {  // c1 = relu([blob, geo, (sdf: zero weight row)] Wc0^T)
+        float c[4][4];
+        zero_c1<4>(c);
+        warp_gemm1<8, 4, false, PREC3>(wrec, R_BLOB, sw + SWC0, LDC0, 0, 0, c);
+        store_c1<4, true>(wrec, R_C1, c);
+      }
+      __syncwarp();
+      {  // rgb logits = c1 Wc1^T (cols 0..2 of an 8-wide tile)
+        float c[1][4];
+        zero_c1<1>(c);
+        warp_gemm1<4, 1, false, PREC3>(wrec, R_C1, sw + SWC1, LDC1, 0, 0, c);
+        float* q0 = wrec + g * REC + R_RAW;
+        if (t == 0) {
+          q0[0] = c[0][0]; q0[1] = c[0][1];
+          q0[8 * REC] = c[0][2]; q0[8 * REC + 1] = c[0][3];
+        } else if (t == 1) {
+          q0[2] = c[0][0];
+          q0[8 * REC + 2] = c[0][2];
+        }
+      }
+      __syncwarp();
+    }
+    if (active && half == 0) {
+      rec[R_RAW + 3] = rec[R_SDF];
+      if (P.raw) {
+        float4 rw = *reinterpret_cast<const float4*>(rec + R_RAW);
+        *reinterpret_cast<float4*>(P.raw + ((size_t)r * S + k) * 4) = rw;
+      }
+    }
+    group_sync(grp);
+    // ---------------- phase 2: per-ray composite, loss, d loss / d raw ----
+    for (int q = gw; q < nr; q += GW) {
+      const int rr = r0 + q;
+      const float* zr = zbuf + q * S;
+      float* sg_r = sgb + q * S;
+      float* u_r = ub + q * S;
+      float* rq = recs + (size_t)(q * S) * REC;
+      const float tr = P.trunc;
+      int first = 0x7fffffff;
+      for (int kk = lane; kk < S; kk += 32) {
+        float* rp = rq + kk * REC + R_RAW;
+        const float s = rp[3];
+        const float sg = sigmoidf_acc(s / tr);
+        sg_r[kk] = sg;
+        u_r[kk] = sg * sigmoidf_acc((-s) / tr);
+        rp[0] = sigmoidf_acc(rp[0]);
+        rp[1] = sigmoidf_acc(rp[1]);
+        rp[2] = sigmoidf_acc(rp[2]);
+        if (kk < S - 1 && rq[(kk + 1) * REC + R_RAW + 3] * s < 0.f) first = min(first, kk);
+      }
+      first = warp_min_i(first);
+      if (first == 0x7fffffff) first = 0;
+      __syncwarp();
+      const float zlim = zr[first] + P.trunc;
+      float usum = 0.f;
+      for (int kk = lane; kk < S; kk += 32) {
+        const float u = (zr[kk] < zlim) ? u_r[kk] : 0.f;
+        u_r[kk] = u;
+        usum += u;
+      }
+      usum = warp_sum(usum);
+      const float W = usum + 1e-8f;
+      float o_r = 0.f, o_g = 0.f, o_b = 0.f, o_d = 0.f, o_acc = 0.f;
+      for (int kk = lane; kk < S; kk += 32) {
+        const float* rp = rq + kk * REC + R_RAW;
+        const float w = u_r[kk] / W;
+        o_r = fmaf(w, rp[0], o_r);
+        o_g = fmaf(w, rp[1], o_g);
+        o_b = fmaf(w, rp[2], o_b);
+        o_d = fmaf(w, zr[kk], o_d);
+        o_acc += w;
+      }
+      o_r = warp_sum(o_r); o_g = warp_sum(o_g); o_b = warp_sum(o_b);
+      o_d = warp_sum(o_d); o_acc = warp_sum(o_acc);
+      if (P.depth_var) {
+        float v = 0.f;
+        for (int kk = lane; kk < S; kk += 32) {
+          const float dz = zr[kk] - o_d;
+          v = fmaf(u_r[kk] / W, dz * dz, v);
+        }
+        v = warp_sum(v);
+        if (lane == 0) P.depth_var[rr] = v;
+      }
+      if (lane == 0) {
+        if (P.rgb) { P.rgb[rr * 3] = o_r; P.rgb[rr * 3 + 1] = o_g; P.rgb[rr * 3 + 2] = o_b; }
+        if (P.depth) P.depth[rr] = o_d;
+        if (P.acc) P.acc[rr] = o_acc;
+        if (P.disp) P.disp[rr] = 1.0f / fmaxf(1e-10f, o_d / o_acc);
+      }
+      if (BWD) {
+        const float td = P.target_d[rr];
+        const float tr_ = P.target_s[rr * 3], tg_ = P.target_s[rr * 3 + 1],
+                    tb_ = P.target_s[rr * 3 + 2];
+        const bool valid = (td > 0.f) && (td < P.depth_trunc);
+        const float RS = (float)P.Rg * (float)S;
+        const float c_rgb = P.ls[0] * P.w_rgb * 2.0f / (3.0f * (float)P.Rg);
+        const float g_r = c_rgb * (o_r - tr_), g_g = c_rgb * (o_g - tg_), g_b = c_rgb * (o_b - tb_);
+        const float g_d = valid ? P.ls[1] * P.w_depth * 2.0f * (o_d - td) * inv_nvalid : 0.f;
+        if (lane == 0) {
+          l_rgb += (double)((o_r - tr_) * (o_r - tr_) + (o_g - tg_) * (o_g - tg_) +
+                            (o_b - tb_) * (o_b - tb_));
+          if (valid) l_depth += (double)((o_d - td) * (o_d - td));
+        }
+        float qw = 0.f;
+        for (int kk = lane; kk < S; kk += 32) {
+          const float* rp = rq + kk * REC + R_RAW;
+          const float q_ = g_r * rp[0] + g_g * rp[1] + g_b * rp[2] + g_d * zr[kk];
+          qw = fmaf(q_, u_r[kk] / W, qw);
+        }
+        qw = warp_sum(qw);
+        float a_fs = 0.f, a_sdf = 0.f;
+        const float c_fs = P.ls[3] * P.w_fs * fs_w * 2.0f / RS;
+        const float c_sdf = P.ls[2] * P.w_sdf * sdf_w * 2.0f / RS;
+        for (int kk = lane; kk < S; kk += 32) {
+          float* rp = rq + kk * REC + R_RAW;
+          const float z = zr[kk];
+          const float s = rp[3];
+          const float sg = sg_r[kk];
+          const float u = u_r[kk];  // a * mask
+          const float w = u / W;
+          const float c0 = rp[0], c1 = rp[1], c2 = rp[2];
+          const float q_ = g_r * c0 + g_g * c1 + g_b * c2 + g_d * z;
+          float ds = (q_ - qw) / W * u * (1.f - 2.f * sg) / tr;
+          const bool front = z < __fsub_rn(td, P.trunc);
+          const bool back = z > __fadd_rn(td, P.trunc);
+          if (front) {
+            ds += c_fs * (s - 1.f);
+            a_fs += (s - 1.f) * (s - 1.f);
+          }
+          if (!front && !back && td > 0.f) {
+            float e = (z + s * P.trunc) - td;
+            ds += c_sdf * e * P.trunc;
+            a_sdf += e * e;
+          }
+          rp[0] = g_r * w * c0 * (1.f - c0);
+          rp[1] = g_g * w * c1 * (1.f - c1);
+          rp[2] = g_b * w * c2 * (1.f - c2);
+          rp[3] = ds;
+        }
+        a_fs = warp_sum(a_fs);
+        a_sdf = warp_sum(a_sdf);
+        if (lane == 0) { l_fs += (double)a_fs; l_sdf += (double)a_sdf; }
+      }
+    }
+    if (!BWD) continue;  // the barrier at the top of the loop orders the next unit
+    group_sync(grp);
+    // ---------------- phase 3: backward ----------------------------------
+    const int npts8 = (npts + 7) & ~7;
+    auto dw_phase = [&](int lo, int hi, int aoff, int boff, int n_tiles_n) {
+      if (!map_grads) return;
+#pragma unroll
+      for (int j = 0; j < G_SLOTS; ++j) {
+        const int id = gw + j * GW;
+        if (id >= lo && id < hi) {
+          const int loc = id - lo, mt = loc / n_tiles_n, nt = loc % n_tiles_n;
+          dw_tile<BPREC3>(recs, npts8, aoff + 16 * mt, boff + 8 * nt, dwacc[j]);
+        }
+      }
+    };
+    // d w_col1 += c1^T draw   (8-wide n tile over raw[4] + 4 floats of the next record: columns
+    dw_phase(0, 2, R_C1, R_RAW, 1);  //  3..7 are never written out; the last record's overrun
+    group_sync(grp);                 //  stays inside the group's misc block)
+    float draw3 = 0.f;
+    if (active) {
+      const float4 dr = *reinterpret_cast<const float4*>(rec + R_RAW);
+      draw3 = dr.w;
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) {
+        const int j = half * 16 + jj;
+        const float* w = sw + SWC1 + j * LDC1;
+        const float c1 = rec[R_C1 + j];
+        rec[R_C1 + j] = (c1 > 0.f) ? (dr.x * w[0] + dr.y * w[1] + dr.z * w[2]) : 0.f;
+      }
+    }
+    group_sync(grp);
+    // d w_col0 += [blob, geo, sdf]^T dc1pre   (row 63 is discarded at write-out)
+    dw_phase(2, 18, R_BLOB, R_C1, 4);
+    group_sync(grp);
+    if (warp_active) {
+      // dgeo = dc1pre Wc0[:, 48:64]  -> dH = [dgeo(15), dsdf]
+      float c[2][4];
+      zero_c1<2>(c);
+      warp_gemm1<4, 2, true, BPREC3>(wrec, R_C1, sw + SWC0, LDC0, 0, 48, c);
+      store_c1<2, false>(wrec, R_GEO, c);
+    }
+    __syncwarp();
+    if (active && half == 0) rec[R_SDF] = draw3;
+    group_sync(grp);
+    // d w_sdf1 += h1^T dH
+    dw_phase(18, 22, R_H1, R_GEO, 2);
+    group_sync(grp);
+    if (warp_active) {
+      // dh1pre = (h1 > 0) * (dH W1)
+      float c[4][4];
+      zero_c1<4>(c);
+      warp_gemm1<2, 4, true, BPREC3>(wrec, R_GEO, sw + SW1, LD1, 0, 0, c);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        float* q0 = wrec + g * REC + R_H1 + nt * 8 + 2 * t;
+        float2 h0 = *reinterpret_cast<float2*>(q0);
+        float2 h8 = *reinterpret_cast<float2*>(q0 + 8 * REC);
+        *reinterpret_cast<float2*>(q0) =
+            make_float2(h0.x > 0.f ? c[nt][0] : 0.f, h0.y > 0.f ? c[nt][1] : 0.f);
+        *reinterpret_cast<float2*>(q0 + 8 * REC) =
+            make_float2(h8.x > 0.f ? c[nt][2] : 0.f, h8.y > 0.f ? c[nt][3] : 0.f);
+      }
+    }
+    group_sync(grp);
+    // d w_sdf0 += x^T dh1pre
+    dw_phase(22, 42, R_FEAT, R_H1, 4);
+    // (readers of C1 / GEO slots are done: dW phases 2 and 3 finished before the last barrier)
+    if (warp_active) {
+      if (need_dx) {
+        // dblob = dc1pre Wc0[:, 0:48] + dh1pre W0[:, 32:80]  -> scratch (C1 slots 0..31, GEO 32..47)
+        float c[6][4];
+        zero_c1<6>(c);
+        warp_gemm1<4, 6, true, BPREC3>(wrec, R_C1, sw + SWC0, LDC0, 0, 0, c);
+        warp_gemm1<4, 6, true, BPREC3>(wrec, R_H1, sw + SW0, LD0, 0, 32, c);
+        __syncwarp();
+#pragma unroll
+        for (int nt = 0; nt < 6; ++nt) {
+          const int col = nt * 8 + 2 * t;
+          const int off = (col < 32) ? (R_C1 + col) : (R_GEO + col - 32);
+          float* q0 = wrec + g * REC + off;
+          *reinterpret_cast<float2*>(q0) = make_float2(c[nt][0], c[nt][1]);
+          *reinterpret_cast<float2*>(q0 + 8 * REC) = make_float2(c[nt][2], c[nt][3]);
+        }
+      }
+      float hdx[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+      if (map_grads || need_dx) {
+        // dfeat = dh1pre W0[:, 0:32]; lane (g,t) holds (f0,f1) of level 4*nt+t for rows g, g+8
+        float c[4][4];
+        zero_c1<4>(c);
+        warp_gemm1<4, 4, true, BPREC3>(wrec, R_H1, sw + SW0, LD0, 0, 0, c);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int row = gw * 16 + g + 8 * h;
+          if (row < npts) {
+            const float x0 = xnb[row * 3], x1 = xnb[row * 3 + 1], x2 = xnb[row * 3 + 2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {  // levels t + 8 j, t + 8 j + 4
+              bool on[2];
+              float gg[2][2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int nt = 2 * j + e;
+                gg[e][0] = c[nt][2 * h]; gg[e][1] = c[nt][2 * h + 1];
+                on[e] = (4 * nt + t) < P.g.n_levels && (gg[e][0] != 0.f || gg[e][1] != 0.f);
+              }
+              if (on[0] || on[1]) {
+                const float3 d3 = hash_backward_multi<2>(P, s_lv, t + 8 * j, on, x0, x1, x2, gg,
+                                                         need_dx, map_grads);
+                hdx[h][0] += d3.x; hdx[h][1] += d3.y; hdx[h][2] += d3.z;
+              }
+            }
+          }
+        }
+      }
+      if (need_dx) {
+        // reduce the hash-path dx over the 4 lanes (t) that share a row, park it in RAW[0..2]
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            float v = hdx[h][d];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if (t == 0) wrec[(g + 8 * h) * REC + R_RAW + d] = v;
+          }
+        __syncwarp();
+        // blob path + chain rule; half 0 owns x, y and half 1 owns z of the point
+        float dp0 = 0.f, dp1 = 0.f;
+        if (active) {
+          auto dblob = [&](int i) { return (i < 32) ? rec[R_C1 + i] : rec[R_GEO + i - 32]; };
+          if (half == 0) {
+            dp0 = (float)((double)(blob_backward_dim(xn[0], 0, dblob) + rec[R_RAW + 0]) * P.g.binv[0]);
+            dp1 = (float)((double)(blob_backward_dim(xn[1], 1, dblob) + rec[R_RAW + 1]) * P.g.binv[1]);
+          } else {
+            dp0 = (float)((double)(blob_backward_dim(xn[2], 2, dblob) + rec[R_RAW + 2]) * P.g.binv[2]);
+          }
+        }
+        __syncwarp();  // both halves have read the dblob scratch before C1[0..5] is reused
+        if (active) {
+          // park d loss / d pts and z * d loss / d pts in the (dead) C1 slots 0..5
+          if (half == 0) {
+            rec[R_C1 + 0] = dp0; rec[R_C1 + 3] = dp0 * zv;
+            rec[R_C1 + 1] = dp1; rec[R_C1 + 4] = dp1 * zv;
+          } else {
+            rec[R_C1 + 2] = dp0; rec[R_C1 + 5] = dp0 * zv;
+          }
+        }
+      }
+    }
+    if (need_dx) {
+      group_sync(grp);
+      for (int q = gw; q < nr; q += GW) {
+        float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int kk = lane; kk < S; kk += 32) {
+          const float* rp = recs + (size_t)(q * S + kk) * REC + R_C1;
+#pragma unroll
+          for (int d = 0; d < 6; ++d) a[d] += rp[d];
+        }
+#pragma unroll
+        for (int d = 0; d < 6; ++d) a[d] = warp_sum(a[d]);
+        if (lane == 0) {
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            if (P.d_rays_o) P.d_rays_o[(r0 + q) * 3 + d] = a[d];
+            if (P.d_rays_d) P.d_rays_d[(r0 + q) * 3 + d] = a[3 + d];
+          }
+        }
+      }
+    }
+  }
+
+  if (BWD) {
+    if (lane == 0) {
+      if (l_rgb != 0.0) atomicAdd(&P.loss_acc[0], l_rgb);
+      if (l_depth != 0.0) atomicAdd(&P.loss_acc[1], l_depth);
+      if (l_sdf != 0.0) atomicAdd(&P.loss_acc[2], l_sdf);
+      if (l_fs != 0.0) atomicAdd(&P.loss_acc[3], l_fs);
+    }
+    if (map_grads) {
+      // sum the weight-gradient tiles of the NGROUPS groups in shared memory (the record area is
+      // dead now), then one red.global per element and CTA
+      float* red = sw + SW_TOTAL;  // [42 tiles][4][32 lanes]
+      __syncthreads();
+      for (int gsel = 0; gsel < NGROUPS; ++gsel) {
+        if (grp == gsel) {
+#pragma unroll
+          for (int j = 0; j < G_SLOTS; ++j) {
+            const int id = gw + j * GW;
+            if (id >= DW_TILES) continue;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float* q0 = red + (id * 4 + i) * 32 + lane;
+              *q0 = (gsel == 0) ? dwacc[j][i] : (*q0 + dwacc[j][i]);
+            }
+          }
+        }
+        __syncthreads();
+      }
+      if (grp == 0) {
+#pragma unroll
+        for (int j = 0; j < G_SLOTS; ++j) {
+          const int id = gw + j * GW;
+          if (id >= DW_TILES) continue;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float v = red[(id * 4 + i) * 32 + lane];
+            const int rloc = g + ((i & 2) ? 8 : 0), cloc = 2 * t + (i & 1);
+            if (id < 2) {  // d w_col1 [3][32]
+              const int in = 16 * id + rloc, out = cloc;
+              if (out < 3) red_add(P.d_w_col1 + out * 32 + in, v);
+            } else if (id < 18) {  // d w_col0 [32][63]
+              const int loc = id - 2, in = 16 * (loc / 4) + rloc, out = 8 * (loc % 4) + cloc;
+              if (in < 63) red_add(P.d_w_col0 + out * 63 + in, v);
+            } else if (id < 22) {  // d w_sdf1 [16][32], stored column jp -> torch row (jp+1)&15
+              const int loc = id - 18, in = 16 * (loc / 2) + rloc, jp = 8 * (loc % 2) + cloc;
+              red_add(P.d_w_sdf1 + ((jp + 1) & 15) * 32 + in, v);
+            } else {  // d w_sdf0 [32][80]
+              const int loc = id - 22, in = 16 * (loc / 4) + rloc, out = 8 * (loc % 4) + cloc;
+              red_add(P.d_w_sdf0 + out * 80 + in, v);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 struct FinalizeParams {
   const double* loss_acc;
   const int* counts;
@@ -1249,6 +1858,42 @@ extern "C" int xrd_coslam_step(const XrdRays* rays, const XrdHashGrid* grid,
   } else {
     P.d_table = P.d_w_sdf0 = P.d_w_sdf1 = P.d_w_col0 = P.d_w_col1 = P.d_rays_o = P.d_rays_d = nullptr;
   }
+  const int sms = num_sms();
+  if (cfg->rays_per_tile == 0 && S <= GP) {
+    // grouped persistent kernel (k_fused_g): units of NR rays pulled from a queue
+    P.NR = GP / S;
+    P.n_tiles = (R + P.NR - 1) / P.NR;
+    int* queue = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + 128);  // zeroed above
+    const size_t smem_g = sizeof(float) * ((size_t)SW_TOTAL + (size_t)NGROUPS * GP * (REC + 6));
+    int gridx = (P.n_tiles + NGROUPS - 1) / NGROUPS;
+    if (gridx > sms) gridx = sms;
+#define XRD_LAUNCH_G(KERNEL)                                                                      \
+  do {                                                                                            \
+    XRD_CUDA_TRY(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                      (int)smem_g));                                              \
+    KernelTimer kt(stream);                                                                       \
+    KERNEL<<<gridx, GT * NGROUPS, smem_g, stream>>>(P, queue);                                    \
+  } while (0)
+    if (grads) {
+      switch (cfg->precision) {
+        case 0: XRD_LAUNCH_G((k_fused_g<true, true, true>)); break;
+        case 1: XRD_LAUNCH_G((k_fused_g<true, true, false>)); break;
+        case 2: XRD_LAUNCH_G((k_fused_g<true, false, false>)); break;
+        default: return XRD_E_SHAPE;
+      }
+      XRD_LAUNCH_CHECK();
+      FinalizeParams fp{loss_acc, P.counts, out->losses, P.Rg, S, cfg->w_rgb, cfg->w_depth, cfg->w_sdf, cfg->w_fs};
+      k_finalize<<<1, 32, 0, stream>>>(fp);
+      XRD_LAUNCH_CHECK();
+    } else {
+      if (cfg->precision <= 1) XRD_LAUNCH_G((k_fused_g<false, true, false>));
+      else XRD_LAUNCH_G((k_fused_g<false, false, false>));
+      XRD_LAUNCH_CHECK();
+    }
+#undef XRD_LAUNCH_G
+    return XRD_OK;
+  }
+  // tile kernel (k_fused): rays_per_tile > 0 selects its tile size, < 0 its default
   int NR = pick_rays_per_tile(S, cfg->rays_per_tile);
   if (NR < 1 || NR * S > 256) return XRD_E_SHAPE;
   int threads = (NR * S + 31) / 32 * 32;
@@ -1256,7 +1901,6 @@ extern "C" int xrd_coslam_step(const XrdRays* rays, const XrdHashGrid* grid,
   P.NR = NR;
   P.n_tiles = (R + NR - 1) / NR;
   const size_t smem = sizeof(float) * ((size_t)SW_TOTAL + (size_t)(threads + 8) * REC + 6 * (size_t)NR * S);
-  const int sms = num_sms();
   const int nwarps = threads / 32;
   const int slots = (DW_TILES + nwarps - 1) / nwarps;
 #define XRD_LAUNCH_FUSED(KERNEL)                                                                  \

@@ -21,16 +21,27 @@ struct P {
   float* d_poses;
 };
 
+// Row of the pose table a ray reads, or -1 when the id is out of range.  torch raises an
+// IndexError for `poses_all[ids_all]` there (coslam.py:208-216); an asynchronous kernel cannot,
+// so an out-of-range ray gets NaN rays (the loss turns NaN: loud) and contributes no gradient
+// -- never an out-of-bounds access.
 __device__ __forceinline__ int pose_row(const P& p, int r) {
   long long id = p.ids ? p.ids[r] : 0;
   if (id < 0) id += p.n_poses;  // python indexing: -1 = the current frame, appended last
-  return (int)id;
+  return (id < 0 || id >= p.n_poses) ? -1 : (int)id;
 }
 
 __global__ void __launch_bounds__(256) k_fwd(const P p) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= p.R) return;
-  const float* M = p.poses + (size_t)pose_row(p, r) * 16;
+  const int row = pose_row(p, r);
+  if (row < 0) {
+    const float nan = __int_as_float(0x7fc00000);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) p.rays_d[r * 3 + c] = p.rays_o[r * 3 + c] = nan;
+    return;
+  }
+  const float* M = p.poses + (size_t)row * 16;
   const float d0 = p.dirs[r * 3], d1 = p.dirs[r * 3 + 1], d2 = p.dirs[r * 3 + 2];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -51,8 +62,8 @@ __global__ void __launch_bounds__(256) k_bwd(const P p) {
   // whole warps iterate together (r0 is warp-uniform) so the shuffles below are convergent
   for (int r0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; r0 < p.R; r0 += gridDim.x * blockDim.x) {
     const int r = r0 + lane;
-    const bool live = r < p.R;
-    const int id = live ? pose_row(p, r) : -1;
+    const int id = (r < p.R) ? pose_row(p, r) : -1;
+    const bool live = id >= 0;  // out-of-range ids contribute nothing
     float v[12];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {

@@ -29,7 +29,7 @@ from torch.nn import Parameter
 from . import _cabi
 from ._cabi import (XrdCoslamCfg, XrdCoslamGrads, XrdCoslamMlp, XrdCoslamOut,
                     XrdHashGrid, XrdRays, check, ptr)
-from .base_model import Model, ModelConfig
+from .base_model import Model, ModelConfig, scale_grads, upstream_scale
 
 
 @dataclass
@@ -164,6 +164,13 @@ class _CoslamStep(torch.autograd.Function):
                     rays_o, rays_d, table, w0, w1, wc0, wc1, ts, td, noise,
                     with_grads=True, need_ray_grads=True,
                     loss_scale=[float(v) for v in g], seed=seed)
+        else:
+            # sync-free: total-loss scaling is honoured, unequal per-term scales poison
+            # the gradients with NaN (base_model.upstream_scale)
+            s = upstream_scale(g_losses)
+            keys = ('d_rays_o', 'd_rays_d', 'd_table', 'd_w_sdf0', 'd_w_sdf1', 'd_w_col0',
+                    'd_w_col1')
+            grads = dict(zip(keys, scale_grads([grads[k] for k in keys], s)))
         return (grads['d_rays_o'], grads['d_rays_d'], grads['d_table'],
                 grads['d_w_sdf0'], grads['d_w_sdf1'], grads['d_w_col0'],
                 grads['d_w_col1'], None, None, None, None)
@@ -472,5 +479,5 @@ class _SmoothFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        d = ctx.d_table
-        return (d * g if ctx.exact else d), None, None, None
+        d = ctx.d_table  # linear in the upstream gradient: exact for any g, no host sync
+        return (d * g if d is not None else None), None, None, None

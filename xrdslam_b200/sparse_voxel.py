@@ -23,7 +23,7 @@ from torch.nn import Parameter
 from . import _cabi
 from ._cabi import (XrdRays, XrdVoxDecoder, XrdVoxDecoderGrads, XrdVoxGrads, XrdVoxMap,
                     XrdVoxMarch, XrdVoxMarchCfg, XrdVoxOut, XrdVoxRenderCfg, check, ptr)
-from .base_model import Model, ModelConfig
+from .base_model import Model, ModelConfig, scale_grads, upstream_scale
 
 MAX_DEPTH = 10.0  # voxel_helpers_voxfusion.py:11
 
@@ -99,7 +99,9 @@ class _VoxStep(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_losses, *_):
         g = ctx.grads
-        return (None, None, None, None, g['d_rays_o'], g['d_rays_d'], g['d_emb'], *g['d_dec'])
+        ro, rd, emb, dec = scale_grads([g['d_rays_o'], g['d_rays_d'], g['d_emb'], list(g['d_dec'])],
+                                       upstream_scale(g_losses))
+        return (None, None, None, None, ro, rd, emb, *dec)
 
 
 class SparseVoxel(Model):
