@@ -1,7 +1,13 @@
 #!/usr/bin/env python
-"""Benchmark of the Co-SLAM render-and-optimise hot path on B200.
+"""Benchmark of the xrdslam render-and-optimise hot path on B200.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python bench.py [--config coslam|nice|vox|point] --gpus N --steps K --warmup W
+                    [--impl reference] [--scaling weak|strong]
+
+--config selects the BASELINE.json configuration: coslam = cfg 2 (the default: the
+configuration the headline metric is quoted on), vox = cfg 3, nice = cfg 4 (cfg 1 is its
+CPU-plumbing shape), point = cfg 5; the three non-default workloads live in
+bench_workloads.py.  Everything below describes the default.
 
 Workload (BASELINE.json configs[1]): co-slam hash grid + OneBlob, 640x480
 synthetic Replica-shaped RGB-D sequence.  One *step* = one mapping iteration of
@@ -44,6 +50,8 @@ BYTES_PER_RAY = 88064  # 43 samples x (1024 B gather + 1024 B scatter
 SMOOTH_BYTES = 29791 * 2048  # smoothness lattice, per mapping iteration
 MAP_KF, MAP_CUR = 2048, 2048
 N_KEYFRAMES = 5
+METRIC = ('rays/s (co-slam mapping iteration: sample+march+hash gather+decode+'
+          'composite+loss+backward+Adam, 640x480 synthetic RGB-D)')
 WORKLOAD = ('co-slam hash-grid(16 lvl x 2 feat, 2^16) + OneBlob16, 640x480 synthetic room, '
             f'mapping iteration, {MAP_KF} keyframe-bank + {MAP_CUR} current-frame rays per GPU, '
             f'43 samples/ray, smoothness 31^3, {N_KEYFRAMES} keyframes')
@@ -55,7 +63,11 @@ def parse():
     ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default='coslam', choices=['coslam', 'nice', 'vox', 'point'])
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='N > 1: weak = fixed rays per GPU, strong = the single-GPU batch split over N')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-torch-gpu-baseline', action='store_true')
     return ap.parse_args()
 
 
@@ -142,6 +154,17 @@ def build_algorithm(device, seed):
                 separate_LR=True, rot_rep='axis_angle')
     algo.set_initialized()
     return algo, kfs, cur
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one 4096-ray k_fused launch from the
+    committed `ncu --set full` capture of this round (profiles/r02_coslam_kfused_traffic.json,
+    written by scripts/ncu_summary.py); None when no capture of the current kernel exists."""
+    try:
+        d = json.load(open(os.path.join(ROOT, 'profiles', 'r02_coslam_kfused_traffic.json')))
+        return int(d['dram_bytes_read'] + d['dram_bytes_write'])
+    except Exception:
+        return None
 
 
 def flat_params(model):
@@ -285,7 +308,7 @@ def run_ours(args):
                 'peak_source': 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback 6650',
                 # dram__bytes_read.sum + dram__bytes_write.sum of one 4096-ray launch
                 # (ncu --set full, profiles/r01_coslam_fused_v4_4096rays_ncu.txt)
-                'traffic': 13928960 + 1280 if R == 4096 else None, 'kernel_ms': k_ms,
+                'traffic': ncu_traffic(), 'kernel_ms': k_ms,
                 'algorithmic_bytes_per_launch': R * BYTES_PER_RAY,
                 'note': 'table (6.56 MB) is L2-resident: DRAM traffic is far below '
                         'the algorithmic bytes, see profiles/'}
@@ -343,12 +366,14 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(sample_rays=1024, iters=3)
+        cpu = cpu_baseline(iters=2)
+    tgb = None
+    if rank == 0 and not args.no_torch_gpu_baseline:
+        tgb = torch_gpu_baseline(dev)
 
     if rank == 0:
         line = {
-            'metric': 'rays/s (co-slam mapping iteration: sample+march+hash gather+decode+'
-                      'composite+loss+backward+Adam, 640x480 synthetic RGB-D)',
+            'metric': METRIC,
             'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': ms_total / K, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -375,6 +400,7 @@ def run_ours(args):
                                   'k_smooth_fwd/bwd/finalize, rays::k_bwd, k_adam x2 (torch glue '
                                   'not counted)'),
             'clocks': clk, 'roofline': roofline, 'cpu_baseline': cpu,
+            'torch_gpu_baseline': tgb,
             'iters': {'mapping_iters_per_s': K / (ms_total * 1e-3),
                       **(trk or {})},
             'wall_s_value_leg': wall,
@@ -385,24 +411,39 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------ CPU baseline ---
-def cpu_step_factory(R):
-    """One Co-SLAM mapping iteration of the oracle port on CPU (fwd+bwd+Adam)."""
+def coslam_ref_step_factory(R_bank, R_cur, device='cpu'):
+    """One Co-SLAM mapping iteration of the oracle port (fwd + bwd + Adam) on `device`, on the
+    SAME workload as the B200 arm: the keyframe ray bank and the per-iteration sampler are
+    CoSLAM.get_model_input's own host path (random.sample rows of the bank + current-frame
+    pixels, per-ray pose gather), R_bank + R_cur rays, smoothness term, Adam on table +
+    decoder."""
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     from oracle.coslam import CoslamOracle
-    from helpers import BOUND, make_rays
+    from helpers import BOUND
+    dev = torch.device(device)
+    algo, kfs, cur = build_algorithm(torch.device('cpu'), seed=1234)  # host sampler only
+    frames = kfs + [cur]
+    algo.config.mapping_sample = R_bank
+    algo.config.min_sample_pixels = R_cur
     torch.manual_seed(0)
     ora = CoslamOracle(BOUND)
+    if dev.type == 'cuda':
+        ora.to(dev)
+        ora.bounding_box = ora.bounding_box.to(dev) if hasattr(ora, 'bounding_box') else None
     opt = torch.optim.Adam([
         {'params': [ora.embed_fn.params], 'lr': 1e-2, 'eps': 1e-15, 'betas': (0.9, 0.99)},
         {'params': [ora.sdf0.weight, ora.sdf1.weight, ora.col0.weight, ora.col1.weight],
          'lr': 1e-2, 'weight_decay': 1e-6, 'betas': (0.9, 0.99)}])
-    rays_o, rays_d, ts, td, _ = make_rays(R, seed=0)
 
     def step():
+        with torch.no_grad():
+            inp = algo.get_model_input(frames, True)  # host: rows, ids, poses -> rays
+        t = lambda k: inp[k].detach().to(dev)
+        R = inp['rays_o'].shape[0]
         opt.zero_grad(set_to_none=True)
-        noise = torch.rand(R, 43)
-        _, _, tot = ora.step(rays_o, rays_d, ts, td, noise, True, False,
-                             smooth_rand=torch.rand(2, 3))
+        noise = torch.rand(R, 43).to(dev)
+        _, _, tot = ora.step(t('rays_o'), t('rays_d'), t('target_s'), t('target_d'), noise, True,
+                             False, smooth_rand=torch.rand(2, 3).to(dev))
         tot.backward()
         opt.step()
         return float(tot.detach())
@@ -410,8 +451,8 @@ def cpu_step_factory(R):
 
 
 def pick_threads(step):
-    """The oracle port is many small torch ops: past a few dozen threads the
-    intra-op pool only adds contention.  Calibrate once on one step each."""
+    """The oracle ports are many small torch ops: past a few dozen threads the intra-op pool
+    only adds contention.  Calibrate once on one step each."""
     cores = os.cpu_count() or 1
     best, best_t = cores, None
     for n in sorted({min(cores, c) for c in (8, 16, 32, cores)}):
@@ -426,28 +467,56 @@ def pick_threads(step):
     return best
 
 
-def cpu_baseline(sample_rays=1024, iters=3):
-    step = cpu_step_factory(sample_rays)
+def cpu_baseline(iters=2):
+    """Bounded sample of the SAME workload: `iters` full 4096-ray iterations (~10-30 s)."""
+    step = coslam_ref_step_factory(MAP_KF, MAP_CUR)
     cores = pick_threads(step)
     t0 = time.perf_counter()
     for _ in range(iters):
         step()
     dt = time.perf_counter() - t0
-    return {'value': sample_rays * iters / dt, 'unit': 'rays/s', 'cores': cores,
+    R = MAP_KF + MAP_CUR
+    return {'value': R * iters / dt, 'unit': 'rays/s', 'cores': cores,
             'kind': 'port',
-            'sample': f'{iters} mapping iterations x {sample_rays} rays x 43 samples '
-                      '(oracle/coslam.py torch-CPU port incl. smoothness + Adam)',
+            'sample': f'{iters} mapping iterations x {R} rays x 43 samples, same sampler and '
+                      'batch as the B200 arm (oracle/coslam.py torch-CPU port incl. smoothness '
+                      '+ Adam)',
             'ms_per_iter': dt / iters * 1e3}
+
+
+def torch_gpu_baseline(dev, iters=10):
+    """The restated reference PyTorch path (oracle/coslam.py: restated-tcnn hash grid + OneBlob
+    in torch ops, autograd, torch Adam) run on the B200 itself -- BASELINE.md section 5's
+    'reference PyTorch path on the GPU', what north_star's >= 10x is quoted against."""
+    try:
+        step = coslam_ref_step_factory(MAP_KF, MAP_CUR, device=str(dev))
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        R = MAP_KF + MAP_CUR
+        return {'value': R * iters / dt, 'unit': 'rays/s', 'ms_per_iter': dt / iters * 1e3,
+                'kind': 'restated reference PyTorch path (oracle/coslam.py) on cuda, eager '
+                        'autograd + torch.optim.Adam, host ray bank -> H2D per iteration',
+                'iters': iters}
+    except Exception as e:  # noqa
+        return {'unavailable': repr(e)[:300]}
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    R = 1024
-    step = cpu_step_factory(R)
+    if args.config != 'coslam':
+        return run_reference_workload(args)
+    R = MAP_KF + MAP_CUR
+    step = coslam_ref_step_factory(MAP_KF, MAP_CUR)
     cores = pick_threads(step)
-    K = min(args.steps, 8)
+    K = min(args.steps, 10)
     W = min(args.warmup, 2)
     for _ in range(max(W, 1)):
         step()
@@ -458,15 +527,14 @@ def run_reference(args):
     v = R * K / dt
     line = {
         'impl': 'reference',
-        'metric': 'rays/s (co-slam mapping iteration: sample+march+hash gather+decode+'
-                  'composite+loss+backward+Adam, 640x480 synthetic RGB-D)',
+        'metric': METRIC,
         'value': v, 'unit': 'rays/s', 'n_gpus': int(os.environ.get('WORLD_SIZE', '1')),
         'steps': K, 'warmup': W, 'ms_per_step': dt / K * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        # same workload as the B200 arm; each step is a bounded sample of it
-        'config': {'workload': WORKLOAD, 'rays_per_step_per_gpu': MAP_KF + MAP_CUR,
+        # same workload, same batch, same sampler as the B200 arm; fewer steps
+        'config': {'workload': WORKLOAD, 'rays_per_step_per_gpu': R,
                    'precision': 'fp32 (torch CPU)',
-                   'sample': f'{R} of the {MAP_KF + MAP_CUR} rays per step (same sampler, decoder, '
+                   'sample': f'{K} full steps of {R} rays (same frames, ray bank, sampler, decoder, '
                              'losses, smoothness, Adam); the reference\'s own python cannot run on '
                              'the box (py3.12 + tinycudann absent): CPU oracle port, all host threads'},
         'cpu_baseline': {'value': v, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
@@ -476,9 +544,189 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ------------------------------------------------- nice / vox / point (cfg 3-5) ---
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        return {}
+
+
+def run_workload(args):
+    import torch.distributed as dist
+    from bench_workloads import WORKLOADS
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    from xrdslam_b200 import _cabi
+    lib = _cabi.lib()
+    _cabi.check('xrd_check_device', lib.xrd_check_device(local))
+    random.seed(1234 + rank)
+    np.random.seed(1234 + rank)
+    torch.manual_seed(1234 + rank)
+    wl = WORKLOADS[args.config](dev, rank, world)
+    wl.build()
+    K, W = args.steps, args.warmup
+    R = wl.rays_per_step()
+    n_sched = wl.n_iters_schedule
+    wl.begin(n_sched)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # the timed steps walk through the stage schedule exactly like one mapping call does
+    sched = [int(j * n_sched / K) for j in range(K)]
+    for i in range(W):
+        wl.step(sched[i % K])
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(K)]
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        flush.zero_()  # L2 flush between timed steps (outside the events)
+        ev[i][0].record()
+        wl.step(sched[i])
+        ev[i][1].record()
+    barrier()
+    wall = time.perf_counter() - t0
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    clk = clocks.stop() if rank == 0 else None
+    value = world * R * K / (ms_total * 1e-3)
+
+    # ---- dominant kernel, timed by the library with events around its launches
+    peaks = _peaks()
+    kms = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps_r = wl.roofline_steps() if hasattr(wl, 'roofline_steps') else list(range(8))
+    for i in steps_r:
+        flush.zero_()
+        e0.record(); e1.record()
+        lib.xrd_debug_kernel_events(e0.cuda_event, e1.cuda_event)
+        wl.step(i)
+        lib.xrd_debug_kernel_events(None, None)
+        torch.cuda.synchronize()
+        kms.append(e0.elapsed_time(e1))
+    k_ms = float(np.median(kms))
+    if args.config == 'vox':
+        n_pts = int(wl.algo.model.last_march.get('n_points', 0)) or None
+        roofline = wl.kernel_roofline(k_ms, float(peaks.get('bf16_tflops_sustained', 1400.0)),
+                                      n_pts or 1)
+    else:
+        roofline = wl.kernel_roofline(k_ms, float(peaks.get('hbm_gbs', 6650.0)))
+    roofline['peak_source'] = 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback'
+
+    # ---- e2e through the plugin call
+    Ke = max(10, min(K, n_sched))
+    wl.e2e(Ke)  # warm-up call (optimizer set-up paths, allocator)
+    barrier()
+    dt, h2d, d2h, _ = wl.e2e(Ke)
+    t = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * R * Ke / float(t.item())
+
+    trk = wl.tracking() if rank == 0 else None
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_workload(wl)
+    if rank == 0:
+        line = {
+            'metric': wl.metric, 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': K,
+            'warmup': W, 'ms_per_step': ms_total / K, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': wl.dtype, 'data': 'synthetic',
+            'config': {'workload': wl.workload, 'rays_per_step_per_gpu': R,
+                       'parallelism': f'dp{world}', 'precision': wl.precision,
+                       'l2': 'flushed between timed steps (256 MB write)', 'map': wl.map_info},
+            'e2e': {'value': e2e_value, 'unit': 'rays/s', 'h2d_bytes_per_step': h2d / Ke,
+                    'd2h_bytes_per_step': d2h / Ke + 8,
+                    'path': f'{type(wl.algo).__name__}.optimize_update({Ke}, window, is_mapping=True): '
+                            'current frame as host arrays (upload inside), per-iteration device '
+                            'sampling + fused step + autograd hand-off + Adam, one host read per '
+                            'iteration (ray filter count), final D2H read'},
+            'gpu_launches': None, 'clocks': clk, 'roofline': roofline, 'cpu_baseline': cpu,
+            'iters': {'mapping_iters_per_s': K / (ms_total * 1e-3), **(trk or {})},
+            'wall_s_value_leg': wall,
+        }
+        line['gpu_launches'] = count_launches(wl, min(K, 5))
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def count_launches(wl, n):
+    """Launches of OUR kernels (names in namespace xrd::) inside n steps, counted with the
+    torch profiler (CUPTI) outside every timed region."""
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(n):
+                wl.step(i)
+            torch.cuda.synchronize()
+        tot = sum(e.count for e in prof.key_averages() if 'xrd::' in e.key)
+        return int(round(tot / n)) if tot else None
+    except Exception:
+        return None
+
+
+def cpu_baseline_workload(wl, budget_s=20.0):
+    step, R, what = wl.cpu_step_factory()
+    cores = pick_threads(step)
+    t0 = time.perf_counter()
+    n = 0
+    while n < 1 or (time.perf_counter() - t0 < budget_s and n < 20):
+        step()
+        n += 1
+    dt = time.perf_counter() - t0
+    return {'value': R * n / dt, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
+            'sample': f'{n} mapping iterations x {R} rays, same frames / window / batch as the '
+                      f'B200 arm: {what}', 'ms_per_iter': dt / n * 1e3}
+
+
+def run_reference_workload(args):
+    from bench_workloads import WORKLOADS
+    dev = torch.device('cuda', 0) if torch.cuda.is_available() else torch.device('cpu')
+    wl = WORKLOADS[args.config](dev, 0, 1)
+    if args.config in ('vox', 'point'):
+        wl.build()  # the map (octree / point cloud) is built by the product's own maintenance code
+    step, R, what = wl.cpu_step_factory()
+    cores = pick_threads(step)
+    K = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step()
+    dt = time.perf_counter() - t0
+    v = R * K / dt
+    print(json.dumps({
+        'impl': 'reference', 'metric': wl.metric, 'value': v, 'unit': 'rays/s',
+        'n_gpus': int(os.environ.get('WORLD_SIZE', '1')), 'steps': K, 'warmup': 2,
+        'ms_per_step': dt / K * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': wl.workload, 'rays_per_step_per_gpu': R,
+                   'sample': f'{K} full steps: {what}'},
+        'cpu_baseline': {'value': v, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
+                         'sample': f'{K} steps x {R} rays'},
+        'e2e': {'value': v, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+
+
 if __name__ == '__main__':
     a = parse()
     if a.impl == 'reference':
         run_reference(a)
-    else:
+    elif a.config == 'coslam':
         run_ours(a)
+    else:
+        run_workload(a)

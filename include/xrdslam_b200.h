@@ -595,8 +595,18 @@ typedef struct {
 
 /* Measurement / parity hook: arithmetic of the wide-MLP GEMMs (Point-SLAM colour stage and
  * the Vox-Fusion decoder):
- * 0 = fp32 SIMT, 1 = 3xTF32 tensor cores (default, fp32-level accuracy), 2 = plain TF32. */
+ * 0 = fp32 SIMT, 1 = 3xTF32 tensor cores (default, fp32-level accuracy): tcgen05 / TMEM / TMA
+ * kernel where the shape qualifies, mma.sync otherwise, 2 = plain TF32 (mma.sync),
+ * 3 = 3xTF32 on mma.sync only.  Thread-local, like the error state. */
 int xrd_debug_gemm_mode(int mode);
+
+/* The wide-MLP GEMM itself (unit tests): C[m][n] = act(sum_k A(m,k) B[k][n] + bias[m]) with
+ * A(m,k) = transA ? A[k*lda+m] : A[m*lda+k]; act 0 none, 1 relu, 2 softplus(beta 100),
+ * 3 sigmoid; result zeroed where relu_mask[m][n] <= 0; + addend[m][n].  DEVICE pointers. */
+int xrd_debug_gemm(int M, int N, int K, const float* A, int lda, int transA, const float* B,
+                   int ldb, float* C, int ldc, const float* bias, int act,
+                   const float* relu_mask, int ldmask, const float* addend, int ldadd,
+                   void* stream);
 
 size_t xrd_pointslam_workspace_bytes(int n_rays, int n_surface, int stage, int with_grads);
 

@@ -267,6 +267,8 @@ SYMBOLS = {
     'xrd_pointslam_knn_query': (C.c_int, [C.POINTER(XrdPointIndex), vp, vp, C.c_int, C.c_int,
                                           vp, vp, vp, vp]),
     'xrd_debug_gemm_mode': (C.c_int, [C.c_int]),
+    'xrd_debug_gemm': (C.c_int, [C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, vp,
+                                 C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp]),
     'xrd_pointslam_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     'xrd_pointslam_step': (C.c_int, [
         C.POINTER(XrdRays), C.POINTER(XrdPointIndex), C.POINTER(XrdPointFeats),

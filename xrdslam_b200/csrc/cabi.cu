@@ -7,7 +7,7 @@
 
 namespace xrd {
 thread_local int g_last_cuda_error = 0;
-int g_gemm_mode = 1;  // gemm.cuh: arithmetic of the wide-MLP GEMMs
+thread_local int g_gemm_mode = 1;  // gemm.cuh: arithmetic of the wide-MLP GEMMs (per calling thread)
 thread_local cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
 
 int num_sms() {
@@ -29,7 +29,7 @@ extern "C" int xrd_abi_version(void) { return XRD_ABI_VERSION; }
 extern "C" int xrd_last_cuda_error(void) { return xrd::g_last_cuda_error; }
 
 extern "C" int xrd_debug_gemm_mode(int mode) {
-  if (mode < 0 || mode > 2) return XRD_E_SHAPE;
+  if (mode < 0 || mode > 3) return XRD_E_SHAPE;
   xrd::g_gemm_mode = mode;
   return XRD_OK;
 }

@@ -254,17 +254,22 @@ static __global__ void __launch_bounds__(256, 2) k_gemm_tc(const GemmArgs G) {
   }
 }
 
-// 0 = fp32 SIMT, 1 = 3xTF32 tensor cores (default), 2 = plain TF32 tensor cores (cabi.cu)
-extern int g_gemm_mode;
+// Arithmetic of the wide-MLP GEMMs (xrd_debug_gemm_mode, cabi.cu):
+//   0 = fp32 SIMT (k_gemm)
+//   1 = 3xTF32 tensor cores (default): tcgen05 / TMEM / TMA kernel (gemm_t5.cuh) for the shapes
+//       it takes, mma.sync k_gemm_tc<true> for the rest
+//   2 = plain TF32 mma.sync (k_gemm_tc<false>)
+//   3 = 3xTF32 mma.sync only (k_gemm_tc<true>; the pre-Blackwell path, kept for A/B runs)
+extern thread_local int g_gemm_mode;
 
-static inline cudaError_t launch_gemm(const GemmArgs& G, cudaStream_t stream) {
+static inline cudaError_t launch_gemm_legacy(const GemmArgs& G, cudaStream_t stream) {
   if (G.M <= 0 || G.N <= 0) return cudaSuccess;
   if (g_gemm_mode == 0 || G.K < 8) {
     dim3 grid((G.N + GBN - 1) / GBN, (G.M + GBM - 1) / GBM);
     k_gemm<<<grid, 256, 0, stream>>>(G);
   } else {
     dim3 grid((G.N + TBN - 1) / TBN, (G.M + TBM - 1) / TBM);
-    if (g_gemm_mode == 1) k_gemm_tc<true><<<grid, 256, 0, stream>>>(G);
+    if (g_gemm_mode != 2) k_gemm_tc<true><<<grid, 256, 0, stream>>>(G);
     else k_gemm_tc<false><<<grid, 256, 0, stream>>>(G);
   }
   return cudaGetLastError();

@@ -1,0 +1,421 @@
+// Blackwell-native GEMM for the wide per-point MLP layers (Vox-Fusion decoder 16-128-128-129 /
+// 144-128-3, Point-SLAM colour trunk 5 x 128): tcgen05.mma kind::tf32 with the accumulators in
+// TMEM, activation tiles fetched by TMA (cp.async.bulk.tensor), warp-specialised roles, 3xTF32
+// error compensation for fp32-level parity.
+//
+//   C[m][n] = epi( sum_k A(m,k) * B[k][n] )      (same contract as gemm.cuh: k_gemm / k_gemm_tc)
+//   MMA M = 128 output features (weights, zero padded), MMA N = 256 points per tile, K = 8/step.
+//
+// Shared-memory operand layouts are the "no swizzle" canonical UMMA layouts (core matrix = 8
+// rows x 16 bytes, cute/atom/mma_traits_sm100.hpp make_umma_desc):
+//   A (weights), K-major:  off(m,k) = (k/4)*2048 + m*16 + (k%4)*4       SBO = 128 B, LBO = 2048 B
+//      staged ONCE per CTA by all threads (handles transA / lda / padding) as  big = x with the
+//      13 low mantissa bits cleared and  small = x - big;  resident for every point tile.
+//   B (activations [K][N], points contiguous), MN-major, 128-byte swizzle: per stage 8 TMA boxes of
+//      (32 points, BK rows) land as 8 swizzle atoms (row = 128 B, 8-row groups 1024 B apart, the
+//      TMA and the UMMA descriptor apply the same address-bit XOR): LBO = BK*128 B between
+//      32-point groups, SBO = 1024 B between 8-row groups.  A splitter warp-group turns the landed
+//      tile into big / small in place (element-wise, so it never needs to know the swizzle).
+//   D: 128 lanes x 256 fp32 columns of TMEM, two accumulators (512 columns) so that the epilogue
+//      of tile i overlaps the MMAs of tile i+1.
+// Roles (384 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected
+// lane), warps 4-7 = epilogue (tcgen05.ld 32x32b, bias / activation / mask / addend, 128-byte
+// row stores), warps 8-11 = splitter.  All hand-offs are mbarriers; every wait is bounded (a
+// broken pipeline traps instead of hanging the GPU).
+#pragma once
+#include <cuda.h>
+
+#include "gemm.cuh"
+
+namespace xrd {
+namespace t5 {
+
+constexpr int BM = 128, BN = 256, BK = 16;
+constexpr int NTHREADS = 384;
+constexpr int B_STAGE_BYTES = BK * BN * 4;  // 16 KB
+constexpr uint32_t SPIN_LIMIT = 1u << 27;
+
+struct Params {
+  GemmArgs G;
+  int Kpad;      // K rounded up to BK
+  int n_tiles;   // ceil(N / BN)
+  int stages;    // 2 or 3 (shared-memory budget)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > SPIN_LIMIT) __trap();  // broken pipeline: fail loudly, never hang
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* holder, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(holder)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes (this warp's TMEM quadrant) x 32 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading / stride
+// byte offsets (16-byte units), Blackwell version field = 1, layout type (0 = no swizzle,
+// 2 = 128-byte swizzle) in bits [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(layout_type & 7) << 61;
+  return d;
+}
+// instruction descriptor: D = F32, A = B = TF32, A K-major, B MN-major, M = 128, N = 256
+__host__ __device__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
+         ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_big(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+static __global__ void __launch_bounds__(NTHREADS, 1)
+k_gemm_t5(const __grid_constant__ CUtensorMap tmap_b, const Params P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const GemmArgs& G = P.G;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Kpad = P.Kpad, S = P.stages;
+  const int a_bytes = BM * Kpad * 4;
+  float* a_big = reinterpret_cast<float*>(smem);
+  float* a_small = reinterpret_cast<float*>(smem + a_bytes);
+  uint8_t* b_base = smem + 2 * a_bytes;  // [S][big 16 KB | small 16 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)S * 2 * B_STAGE_BYTES);
+  uint64_t* full = bars;            // [S]  TMA bytes landed
+  uint64_t* split = bars + 4;       // [S]  big/small ready (128 splitter arrivals)
+  uint64_t* empty = bars + 8;       // [S]  MMAs that read the stage are complete
+  uint64_t* tfull = bars + 12;      // [2]  accumulator complete
+  uint64_t* tempty = bars + 14;     // [2]  accumulator drained (128 epilogue arrivals)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 16);
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(split + s, 128); mbar_init(empty + s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_holder, 512);
+  // ---- stage the weights once: A(m,k) -> canonical K-major core-matrix layout, big / small
+  for (int e = tid; e < BM * Kpad; e += NTHREADS) {
+    const int m = e % BM, k = e / BM;
+    float v = 0.f;
+    if (m < G.M && k < G.K) v = G.transA ? G.A[(size_t)k * G.lda + m] : G.A[(size_t)m * G.lda + k];
+    const float big = tf32_big(v);
+    const int off = (k >> 2) * (BM * 4) + m * 4 + (k & 3);
+    a_big[off] = big;
+    a_small[off] = v - big;
+  }
+  fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  const int n_kb = Kpad / BK;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < n_kb; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(empty + s, ph ^ 1);
+          mbar_expect_tx(full + s, B_STAGE_BYTES);
+          uint8_t* dst = b_base + (size_t)s * 2 * B_STAGE_BYTES;
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j)  // one 128-byte-swizzle atom (32 points x BK rows) each
+            tma_load_2d(dst + j * (BK * 128), &tmap_b, full + s, tile * BN + j * 32, kb * BK);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc();
+    int it = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++lt) {
+      const int acc = lt & 1;
+      mbar_wait(tempty + acc, ((lt >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+      for (int kb = 0; kb < n_kb; ++kb, ++it) {
+        const int s = it % S;
+        mbar_wait(split + s, (it / S) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t bb = smem_u32(b_base + (size_t)s * 2 * B_STAGE_BYTES);
+          const uint32_t bs = bb + B_STAGE_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            const int kc = (kb * (BK / 8) + ks) * 2;  // first of the two 16-byte K chunks
+            const uint64_t da_b = make_desc(smem_u32(a_big) + kc * (BM * 16), BM * 16, 128, 0);
+            const uint64_t da_s = make_desc(smem_u32(a_small) + kc * (BM * 16), BM * 16, 128, 0);
+            const uint64_t db_b = make_desc(bb + ks * 1024, BK * 128, 1024, 2);
+            const uint64_t db_s = make_desc(bs + ks * 1024, BK * 128, 1024, 2);
+            const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
+            umma_tf32(d_tmem, da_s, db_b, idesc, first);  // small terms first (3xTF32)
+            umma_tf32(d_tmem, da_b, db_s, idesc, 1u);
+            umma_tf32(d_tmem, da_b, db_b, idesc, 1u);
+          }
+          umma_commit(empty + s);                      // stage reusable once these MMAs retire
+          if (kb == n_kb - 1) umma_commit(tfull + acc);  // accumulator complete
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== splitter: landed fp32 tile -> big (in place) + small =====================
+    const int st = tid - 256;  // 0..127
+    int it = 0;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < n_kb; ++kb, ++it) {
+        const int s = it % S;
+        mbar_wait(full + s, (it / S) & 1);
+        float4* big = reinterpret_cast<float4*>(b_base + (size_t)s * 2 * B_STAGE_BYTES);
+        float4* sml = reinterpret_cast<float4*>(b_base + (size_t)s * 2 * B_STAGE_BYTES + B_STAGE_BYTES);
+#pragma unroll
+        for (int q = 0; q < B_STAGE_BYTES / 16 / 128; ++q) {
+          const int i = st + q * 128;
+          const float4 v = big[i];
+          const float4 b = make_float4(tf32_big(v.x), tf32_big(v.y), tf32_big(v.z), tf32_big(v.w));
+          big[i] = b;
+          sml[i] = make_float4(v.x - b.x, v.y - b.y, v.z - b.z, v.w - b.w);
+        }
+        fence_proxy_async();
+        mbar_arrive(split + s);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;              // TMEM lane quadrant of this warp
+    const int m = q * 32 + lane;         // output feature row
+    const bool row_ok = m < G.M;
+    const float bias = (row_ok && G.bias) ? G.bias[m] : 0.f;
+    const bool vec = ((G.ldc & 3) == 0) && ((((uintptr_t)G.C) & 15) == 0);
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++lt) {
+      const int acc = lt & 1;
+      mbar_wait(tfull + acc, (lt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * BN;
+      const int n0 = tile * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld32(t0 + c * 32, v);
+        const int nb = n0 + c * 32;
+        if (row_ok && nb < G.N) {
+        const int nv = min(32, G.N - nb);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j] + bias, G.act);
+        if (G.relu_mask) {
+          const float* mk = G.relu_mask + (size_t)m * G.ldmask + nb;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nv && !(mk[j] > 0.f)) v[j] = 0.f;
+        }
+        if (G.act_out) {
+          float* ao = G.act_out + (size_t)m * G.ldact + nb;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nv) ao[j] = v[j];
+        }
+        if (G.addend) {
+          const float* ad = G.addend + (size_t)m * G.ldadd + nb;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nv) v[j] += ad[j];
+        }
+        float* cp = G.C + (size_t)m * G.ldc + nb;
+        if (vec && nv == 32 && !G.accumulate) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nv) cp[j] = G.accumulate ? (cp[j] + v[j]) : v[j];
+        }
+        }
+        __syncwarp();  // tcgen05.ld is warp-collective: reconverge before the next chunk
+      }
+      tc_fence_before();
+      mbar_arrive(tempty + acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static inline EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// shapes this kernel takes (everything else stays on k_gemm_tc / k_gemm)
+static inline bool eligible(const GemmArgs& G) {
+  return G.M >= 64 && G.M <= BM && G.K >= 16 && G.K <= 144 && G.N >= 512 && (G.ldb & 3) == 0 &&
+         ((((uintptr_t)G.B) & 15) == 0) && encode_fn() != nullptr;
+}
+
+static inline cudaError_t launch(const GemmArgs& G, cudaStream_t stream) {
+  Params P;
+  P.G = G;
+  P.Kpad = (G.K + BK - 1) / BK * BK;
+  P.n_tiles = (G.N + BN - 1) / BN;
+  P.stages = P.Kpad > 128 ? 2 : 3;
+  // B [K][ldb] fp32 as a 2-D tensor (points innermost); box = (32 points = 128 B, BK rows) with the
+  // 128-byte swizzle; rows >= K and columns >= ldb read as zero (out-of-bounds fill)
+  CUtensorMap tm;
+  const cuuint64_t dims[2] = {(cuuint64_t)G.ldb, (cuuint64_t)G.K};
+  const cuuint64_t strides[1] = {(cuuint64_t)G.ldb * 4};  // bytes, dim 1
+  const cuuint32_t box[2] = {32, BK};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(G.B), dims, strides,
+                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+  const size_t smem = 2 * (size_t)BM * P.Kpad * 4 + (size_t)P.stages * 2 * B_STAGE_BYTES + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_t5, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  int grid = P.n_tiles < num_sms() ? P.n_tiles : num_sms();
+  k_gemm_t5<<<grid, NTHREADS, smem, stream>>>(tm, P);
+  return cudaGetLastError();
+}
+
+}  // namespace t5
+
+// rows [m0, m0 + mc) of a GEMM as a GEMM of its own
+static inline GemmArgs gemm_rows(const GemmArgs& G, int m0, int mc) {
+  GemmArgs H = G;
+  H.M = mc;
+  H.A = G.transA ? G.A + m0 : G.A + (size_t)m0 * G.lda;
+  H.C = G.C + (size_t)m0 * G.ldc;
+  if (G.bias) H.bias = G.bias + m0;
+  if (G.addend) H.addend = G.addend + (size_t)m0 * G.ldadd;
+  if (G.act_out) H.act_out = G.act_out + (size_t)m0 * G.ldact;
+  if (G.relu_mask) H.relu_mask = G.relu_mask + (size_t)m0 * G.ldmask;
+  return H;
+}
+
+static inline cudaError_t launch_gemm(const GemmArgs& G, cudaStream_t stream) {
+  if (G.M <= 0 || G.N <= 0) return cudaSuccess;
+  if (g_gemm_mode == 1) {
+    if (t5::eligible(G)) return t5::launch(G, stream);
+    if (G.M > t5::BM) {  // e.g. 144 = 128 (tcgen05) + 16 (mma.sync)
+      GemmArgs top = gemm_rows(G, 0, t5::BM);
+      if (t5::eligible(top)) {
+        cudaError_t e = t5::launch(top, stream);
+        if (e != cudaSuccess) return e;
+        return launch_gemm_legacy(gemm_rows(G, t5::BM, G.M - t5::BM), stream);
+      }
+    }
+  }
+  return launch_gemm_legacy(G, stream);
+}
+
+}  // namespace xrd

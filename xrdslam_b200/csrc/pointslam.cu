@@ -15,7 +15,7 @@
 
 #define XRD_NICE_KERNELS_ONLY
 #include "nice.cu"
-#include "gemm.cuh"
+#include "gemm_t5.cuh"
 
 namespace xrd {
 namespace point {

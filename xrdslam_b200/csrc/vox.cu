@@ -14,7 +14,7 @@
 
 #include "common.cuh"
 #include "dw.cuh"
-#include "gemm.cuh"
+#include "gemm_t5.cuh"
 
 namespace xrd {
 namespace vox {
@@ -875,5 +875,23 @@ extern "C" int xrd_voxfusion_render(const XrdRays* rays, const XrdVoxMap* map,
                                                  grads->d_rays_o, grads->d_rays_d);
     XRD_LAUNCH_CHECK();
   }
+  return XRD_OK;
+}
+
+
+// Direct entry to the wide-MLP GEMM (gemm.cuh / gemm_t5.cuh) for the unit tests:
+//   C[m][n] = act( sum_k A(m,k) B[k][n] + bias[m] ), optional relu mask / addend, under the
+//   calling thread's xrd_debug_gemm_mode.  All pointers DEVICE.
+extern "C" int xrd_debug_gemm(int M, int N, int K, const float* A, int lda, int transA, const float* B,
+                              int ldb, float* C, int ldc, const float* bias, int act,
+                              const float* relu_mask, int ldmask, const float* addend, int ldadd,
+                              void* stream) {
+  if (!A || !B || !C) return XRD_E_NULL;
+  if (M <= 0 || N <= 0 || K <= 0) return XRD_E_SHAPE;
+  xrd::GemmArgs g{};
+  g.M = M; g.N = N; g.K = K; g.A = A; g.lda = lda; g.transA = transA; g.B = B; g.ldb = ldb;
+  g.C = C; g.ldc = ldc; g.bias = bias; g.act = act; g.relu_mask = relu_mask; g.ldmask = ldmask;
+  g.addend = addend; g.ldadd = ldadd;
+  XRD_CUDA_TRY(xrd::launch_gemm(g, (cudaStream_t)stream));
   return XRD_OK;
 }
