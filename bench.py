@@ -178,6 +178,49 @@ def allreduce_grads(dp):
     dp.all_reduce_grads()
 
 
+def dp_preflight(model, dp, dev, R=1024):
+    """Sharded == single-GPU check on the live process group (what tests/test_dp_gpu.py
+    asserts on a 2-GPU box): every rank renders the SAME seeded batch once whole and once as
+    its shard + all-reduce; the summed gradients must match the whole-batch gradients."""
+    g = torch.Generator().manual_seed(77)
+    rays_o = (torch.rand(R, 3, generator=g) - 0.5)
+    rays_d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    td = torch.rand(R, 1, generator=g) * 3 + 0.3
+    ts = torch.rand(R, 3, generator=g)
+    noise = torch.rand(R, 43, generator=g)
+    full = dict(rays_o=rays_o.to(dev), rays_d=rays_d.to(dev), target_s=ts.to(dev),
+                target_d=td.to(dev), first=True, noise=noise.to(dev))
+    params = dp.params
+    saved = [p.detach().clone() for p in params]
+    gp = torch.Generator().manual_seed(5)
+    with torch.no_grad():  # a non-trivial table, identical on every rank
+        params[0].copy_(((torch.rand(params[0].shape, generator=gp) * 2 - 1) * 0.1).to(dev))
+    model.dp = None
+    for p in params:
+        p.grad = None
+    ld = model.get_loss_dict(model(full), full, True, 0)
+    sum(ld.values()).backward()
+    ref = [p.grad.detach().clone() for p in params]
+    for p in params:
+        p.grad = None
+    model.dp = dp
+    sl = dp.shard(R)
+    part = {k: (v[sl] if torch.is_tensor(v) else v) for k, v in full.items()}
+    ld = model.get_loss_dict(model(part), part, True, 0)
+    sum(ld.values()).backward()
+    dp.all_reduce_grads()
+    rel = max(float((p.grad - r).norm() / (r.norm() + 1e-30)) for p, r in zip(params, ref))
+    t = torch.tensor([rel], device=dev, dtype=torch.float64)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    with torch.no_grad():
+        for p, s_ in zip(params, saved):
+            p.copy_(s_)
+            p.grad = None
+    rel = float(t.item())
+    return {'ok': bool(rel < 1e-4), 'grad_rel_l2_max_over_ranks': rel, 'rays': R,
+            'world': dp.world}
+
+
 def run_ours(args):
     import torch.distributed as dist
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -195,11 +238,17 @@ def run_ours(args):
     model = algo.model
     frames = kfs + [cur]
     K, W = args.steps, args.warmup
-    R = MAP_KF + MAP_CUR
+    # weak scaling: every rank renders the full single-GPU batch; strong: that batch is split
+    strong = args.scaling == 'strong' and world > 1
+    map_kf = MAP_KF // world if strong else MAP_KF
+    map_cur = MAP_CUR // world if strong else MAP_CUR
+    algo.config.mapping_sample = map_kf
+    R = map_kf + map_cur
     params = flat_params(model)
     from xrdslam_b200.dp import MappingDataParallel
     dp = MappingDataParallel(params)
     dp.broadcast_params(0)  # identical replicas
+    dp_parity = dp_preflight(model, dp, dev) if world > 1 else None
     model.dp = dp
     optim = algo.setup_optimizers(K, frames, is_mapping=True)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -207,7 +256,7 @@ def run_ours(args):
     def make_batch():
         """What CoSLAM.get_model_input builds, with the current-frame share raised
         to 2048 rays (the reference's first-keyframe shape) so R is fixed."""
-        algo.config.min_sample_pixels = MAP_CUR
+        algo.config.min_sample_pixels = map_cur
         inp = algo.get_model_input(frames, True)
         inp['smooth_rand'] = torch.rand(6)
         return inp
@@ -229,13 +278,13 @@ def run_ours(args):
 
     # ---------------- value: batches resident in HBM -----------------------
     # the mapping iteration is a CUDA graph (xrdslam_b200/coslam_graph.py) replayed from a
-    # device-resident batch; N > 1: three captured segments around two NCCL all-reduces
-    # (loss-normaliser counts, then ONE flat bucket of all gradients + loss terms).
+    # device-resident batch; N > 1: the two NCCL all-reduces (loss-normaliser counts, then ONE
+    # flat bucket of all gradients + loss terms) are nodes of the same graph.
     use_graph = algo._graph_ok(frames)
     sess = None
     batches = []
     if use_graph:
-        algo.config.min_sample_pixels = MAP_CUR
+        algo.config.min_sample_pixels = map_cur
         algo.bundle_adjust = True
         sess = algo.mapping_session(frames)
         sess.begin(frames)
@@ -314,7 +363,7 @@ def run_ours(args):
                         'the algorithmic bytes, see profiles/'}
 
     # ---------------- e2e: through the plugin, host ray bank ---------------
-    algo.config.min_sample_pixels = MAP_CUR
+    algo.config.min_sample_pixels = map_cur
     h2d = R * 7 * 4 + R * 8 + 128  # sampled rows + pose ids + per-iteration scalar block
     d2h = 4
     if use_graph:
@@ -375,7 +424,8 @@ def run_ours(args):
         line = {
             'metric': METRIC,
             'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': K, 'warmup': W,
-            'ms_per_step': ms_total / K, 'higher_is_better': True, 'scaling': 'weak',
+            'ms_per_step': ms_total / K, 'higher_is_better': True,
+            'scaling': 'strong' if strong else 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'precision': 'fp32 gathers/compositing/loss; decoder GEMMs 3xTF32 forward, TF32 backward (fp32 accumulate)',
                        'workload': WORKLOAD,
@@ -386,7 +436,8 @@ def run_ours(args):
                     'path': ('CoSLAM.mapping_session(frames).step(): host pinned ray bank, '
                              'random.sample, H2D, one CUDA graph (poses, rays, sample, fused '
                              'fwd/loss/bwd, smoothness, pose grads, Adam)' +
-                             (' in 3 captured segments around 2 NCCL all-reduces' if world > 1 else '') +
+                             ((' with the 2 NCCL all-reduces captured inside it' if getattr(sess, 'single_graph', True)
+                               else ' in 3 captured segments around 2 NCCL all-reduces') if world > 1 else '') +
                              ', loss.item()')
                     if use_graph else
                     ('CoSLAM.get_loss (host pinned ray bank, random.sample, H2D) -> '
@@ -400,7 +451,7 @@ def run_ours(args):
                                   'k_smooth_fwd/bwd/finalize, rays::k_bwd, k_adam x2 (torch glue '
                                   'not counted)'),
             'clocks': clk, 'roofline': roofline, 'cpu_baseline': cpu,
-            'torch_gpu_baseline': tgb,
+            'torch_gpu_baseline': tgb, 'dp_parity': dp_parity,
             'iters': {'mapping_iters_per_s': K / (ms_total * 1e-3),
                       **(trk or {})},
             'wall_s_value_leg': wall,

@@ -367,6 +367,35 @@ int xrd_nice_step(const XrdRays* rays, const XrdNiceGrid grids[3],
                   XrdNiceOut* out, XrdNiceGrads* grads, void* workspace,
                   size_t workspace_bytes, void* stream);
 
+/* Stage 'coarse' (slam/models/conv_onet.py:137-138 target_d = None, :397-402 near = 0.01 /
+ * far = bound exit, 32 uniform samples; slam/model_components/decoder_nice.py:237-320
+ * MLP_no_xyz, :389-393): its own decoder and grid; the grid is sampled with the scene bound
+ * multiplied by model_coarse_bound_enlarge (conv_onet.py:335-337) while the out-of-bound mask
+ * and the far plane use the scene bound.  Mapping depth loss only (conv_onet.py:176-181);
+ * the decoder is frozen, gradients go to the grid (ACCUMULATED into d_grid) and the rays. */
+typedef struct {
+  const float* pts_w[5]; /* DEVICE [32,32] x3, [32,64] (input = [feature, hidden]), [32,32] */
+  const float* pts_b[5]; /* DEVICE [32]                                                    */
+  const float* out_w;    /* DEVICE [1,32]                                                  */
+  const float* out_b;    /* DEVICE [1]                                                     */
+} XrdNiceCoarseDecoder;
+
+typedef struct {
+  int n_samples;               /* 32                                                      */
+  double bound_min[3];         /* scene bound after load_bound                            */
+  double bound_max[3];
+  double coarse_bound_min[3];  /* scene bound * model_coarse_bound_enlarge                */
+  double coarse_bound_max[3];
+  const float* t_uniform;      /* DEVICE [n_samples] torch.linspace(0,1,n_samples)        */
+} XrdNiceCoarseCfg;
+
+size_t xrd_nice_coarse_workspace_bytes(int n_rays, int n_samples, int with_grads);
+/* out->losses[0] = depth loss (losses[1] = 0).  with_grads = 0: forward only. */
+int xrd_nice_coarse_step(const XrdRays* rays, const XrdNiceGrid* grid,
+                         const XrdNiceCoarseDecoder* dec, const XrdNiceCoarseCfg* cfg,
+                         XrdNiceOut* out, float* d_grid, float* d_rays_o, float* d_rays_d,
+                         int with_grads, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- Vox-Fusion -------------------------------------------------------------
  *
  * Map structure (host side, once per mapping call -- SURVEY row f2):

@@ -35,6 +35,8 @@ import torch.nn.functional as F
 class NiceCfg:
     c_dim: int = 32
     hidden: int = 32
+    grid_len_coarse: float = 2.0
+    coarse_bound_enlarge: int = 2
     grid_len_middle: float = 0.32
     grid_len_fine: float = 0.16
     grid_len_color: float = 0.16
@@ -91,6 +93,28 @@ class DecoderMLP(nn.Module):
         return out if self.color else out.squeeze(-1)
 
 
+class CoarseMLP(nn.Module):
+    """MLP_no_xyz (decoder_nice.py:237-320): the grid feature is the only input; 5 blocks of
+    width 32, the feature re-concatenated after block 2, no positional embedding, no fc_c."""
+    def __init__(self, c_dim=32, hidden=32, gen=None):
+        super().__init__()
+        dims = [hidden, hidden, hidden, hidden + c_dim, hidden]
+        self.pts = nn.ModuleList([nn.Linear(d, hidden) for d in dims])
+        self.out = nn.Linear(hidden, 1)
+        for lin in list(self.pts) + [self.out]:
+            act = 'linear' if lin is self.out else 'relu'
+            nn.init.xavier_uniform_(lin.weight, gain=nn.init.calculate_gain(act))
+            nn.init.zeros_(lin.bias)
+
+    def forward(self, c):
+        h = c
+        for i in range(5):
+            h = F.relu(self.pts[i](h))
+            if i == 2:
+                h = torch.cat([c, h], -1)
+        return self.out(h).squeeze(-1)
+
+
 def normalize_3d(p, bound):
     p = p.reshape(-1, 3).clone()
     for d in range(3):
@@ -108,7 +132,7 @@ def sample_grid(p, grid, bound):
 
 
 class NiceOracle(nn.Module):
-    def __init__(self, bounding_box, cfg: NiceCfg = None, seed=0):
+    def __init__(self, bounding_box, cfg: NiceCfg = None, seed=0, coarse=False):
         super().__init__()
         self.cfg = cfg or NiceCfg()
         c = self.cfg
@@ -123,10 +147,26 @@ class NiceOracle(nn.Module):
                              ('grid_color', c.grid_len_color, 0.01)):
             shp = [1, c.c_dim] + grid_shape(self.bound, gl)
             self.grids[key] = nn.Parameter(torch.zeros(shp).normal_(0, std, generator=g))
+        # coarse level (conv_onet.py:256-275, :335-337): own decoder, grid over the bound
+        # scaled by model_coarse_bound_enlarge, sampled with that scaled bound
+        self.coarse = None
+        if not coarse:
+            return
+        self.coarse = CoarseMLP(c.c_dim, c.hidden, g)
+        xyz_len = (self.bound[:, 1] - self.bound[:, 0]) * c.coarse_bound_enlarge
+        s = list(map(int, (xyz_len / c.grid_len_coarse).tolist()))
+        s[0], s[2] = s[2], s[0]
+        self.grids['grid_coarse'] = nn.Parameter(
+            torch.zeros([1, c.c_dim] + s).normal_(0, 0.01, generator=g))
+        self.coarse_bound = self.bound * c.coarse_bound_enlarge
 
     # --- NICE.forward (decoder_nice.py:386-414) --------------------------------
     def decode(self, p, stage):
         b = self.bound
+        if stage == 'coarse':
+            raw = torch.zeros(p.shape[0], 4)
+            raw[..., -1] = self.coarse(sample_grid(p, self.grids['grid_coarse'], self.coarse_bound))
+            return raw
         c_mid = sample_grid(p, self.grids['grid_middle'], b)
         mid = self.middle(p, c_mid)
         raw = torch.zeros(p.shape[0], 4)
@@ -157,6 +197,16 @@ class NiceOracle(nn.Module):
     def sample_z(self, rays_o, rays_d, gt_depth):
         c = self.cfg
         N_samples, N_surface = c.n_samples, c.n_surface
+        if gt_depth is None:  # stage 'coarse' (conv_onet.py:137-138, :397-402): 32 uniform samples
+            with torch.no_grad():
+                det_o = rays_o.clone().detach().unsqueeze(-1)
+                det_d = rays_d.clone().detach().unsqueeze(-1)
+                t = (self.bound.unsqueeze(0) - det_o) / det_d
+                far_bb, _ = torch.min(torch.max(t, dim=2)[0], dim=1)
+                far_bb = far_bb.unsqueeze(-1)
+                far_bb += 0.01
+            t_vals = torch.linspace(0., 1., steps=N_samples)
+            return 0.01 * (1. - t_vals) + far_bb * t_vals
         gt_depth = gt_depth.reshape(-1, 1)
         near = gt_depth.repeat(1, N_samples) * 0.01
         with torch.no_grad():
@@ -184,7 +234,7 @@ class NiceOracle(nn.Module):
 
     def render(self, rays_o, rays_d, gt_depth, stage):
         N = rays_o.shape[0]
-        z_vals = self.sample_z(rays_o, rays_d, gt_depth)
+        z_vals = self.sample_z(rays_o, rays_d, None if stage == 'coarse' else gt_depth)
         pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
         raw = self.eval_points(pts.reshape(-1, 3), stage).reshape(N, z_vals.shape[1], -1)
         rgb = raw[..., :-1]

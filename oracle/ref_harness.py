@@ -124,6 +124,14 @@ def copy_nice_ref_to_oracle(ref, ora):
             o.out.bias.copy_(r.output_linear.bias)
         for k in ('grid_middle', 'grid_fine', 'grid_color'):
             ora.grids[k].copy_(ref.grid_c[k])
+        if getattr(ora, 'coarse', None) is not None:
+            r, o = ref.decoder.coarse_decoder, ora.coarse
+            for i in range(5):
+                o.pts[i].weight.copy_(r.pts_linears[i].weight)
+                o.pts[i].bias.copy_(r.pts_linears[i].bias)
+            o.out.weight.copy_(r.output_linear.weight)
+            o.out.bias.copy_(r.output_linear.bias)
+            ora.grids['grid_coarse'].copy_(ref.grid_c['grid_coarse'])
 
 
 # ---- Point-SLAM: the reference's ConvOnet2 with an exact-kNN stand-in for faiss -----------

@@ -159,3 +159,66 @@ def test_nice_cuda_matches_reference_golden(cuda_dev, tag, is_mapping):
         <= 2e-3 * float(g[tag + '.d_grid_color_norm'])
     assert rel_err(gc_ref_layout[:, 10:14, 10:14, 10:14],
                    torch.from_numpy(g[tag + '.d_grid_color_slice'])) < 2e-3
+
+
+@pytest.mark.gpu
+def test_nice_coarse_stage_parity(cuda_dev):
+    """Stage 'coarse' (reference default coarse=True: MLP_no_xyz on the 2 m grid over the doubled
+    bound, 32 uniform samples without depth guidance, mapping depth loss) against
+    oracle/nice.py, itself bit-identical to the reference ConvOnet(coarse=True)
+    (tests/test_oracle_cpu.py::test_nice_oracle_coarse_stage_matches_reference_class_live)."""
+    import warnings
+    from oracle.nice import NiceOracle
+    from xrdslam_b200.camera import Camera
+    from xrdslam_b200.conv_onet import ConvOnetConfig
+    ora = NiceOracle(BOUND, seed=2, coarse=True)
+    g = torch.Generator().manual_seed(9)
+    with torch.no_grad():
+        ora.grids['grid_coarse'].mul_(60.0)
+        for lin in list(ora.coarse.pts) + [ora.coarse.out]:
+            lin.bias.copy_(torch.randn(lin.bias.shape, generator=g) * 0.1)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore', RuntimeWarning)  # no pretrained checkpoints in the tests
+        model = ConvOnetConfig(coarse=True, mapping_frustum_feature_selection=False).setup(
+            camera=Camera(320., 320., 319.5, 239.5, 640, 480), bounding_box=BOUND)
+    assert tuple(model.grid_c['grid_coarse'].shape) == tuple(ora.grids['grid_coarse'].shape)
+    with torch.no_grad():
+        m = model.decoder.coarse_decoder
+        for i in range(5):
+            m.pts_linears[i].weight.copy_(ora.coarse.pts[i].weight)
+            m.pts_linears[i].bias.copy_(ora.coarse.pts[i].bias)
+        m.output_linear.weight.copy_(ora.coarse.out.weight)
+        m.output_linear.bias.copy_(ora.coarse.out.bias)
+        model.set_grid('grid_coarse', ora.grids['grid_coarse'])
+    model.to(cuda_dev)
+    R = 333
+    rays_o, rays_d, ts, td = rays(R, 31)
+    rays_o.requires_grad_(True)
+    rays_d.requires_grad_(True)
+    out_o, ld_o, tot_o = ora.step(rays_o, rays_d, ts, td, True, 'coarse')
+    tot_o.backward()
+    ro = rays_o.detach().to(cuda_dev).requires_grad_(True)
+    rd = rays_d.detach().to(cuda_dev).requires_grad_(True)
+    z = torch.empty(R, 32, dtype=torch.float64, device=cuda_dev)
+    model._z_capture = z
+    inp = dict(rays_o=ro, rays_d=rd, target_s=ts.to(cuda_dev), target_d=td.to(cuda_dev),
+               stage='coarse', is_mapping=True)
+    out = model(inp)
+    ld = model.get_loss_dict(out, inp, True, 'coarse')
+    assert set(ld) == set(ld_o) == {'depth_loss'}
+    sum(ld.values()).backward()
+    torch.cuda.synchronize()
+    assert torch.equal(z.cpu(), out_o['z_vals'])            # f64 sample depths: bit-exact
+    assert max_abs(out['depth'], out_o['depth']) < 2e-4
+    assert max_abs(out['uncertainty'], out_o['uncertainty']) < 2e-4
+    a, b = float(ld['depth_loss'].detach()), float(ld_o['depth_loss'].detach())
+    assert abs(a - b) <= 2e-4 * max(abs(b), 1.0)
+    g_o = ora.grids['grid_coarse'].grad.squeeze(0).permute(1, 2, 3, 0)
+    assert rel_err(model.grids['grid_coarse'].grad, g_o) < 2e-3
+    assert rel_err(ro.grad, rays_o.grad) < 5e-3
+    assert rel_err(rd.grad, rays_d.grad) < 5e-3
+    # forward-only (render_img) path returns the same maps
+    with torch.no_grad():
+        o2 = model(dict(rays_o=ro.detach(), rays_d=rd.detach(), target_s=None,
+                        target_d=td.to(cuda_dev), stage='coarse'))
+    assert torch.equal(o2['depth'], out['depth'])

@@ -211,6 +211,52 @@ def test_nice_oracle_matches_golden_reference_vectors():
 
 
 @pytest.mark.needs_reference
+def test_nice_oracle_coarse_stage_matches_reference_class_live():
+    """Stage 'coarse' (MLP_no_xyz on the 2 m grid over the doubled bound, 32 uniform samples,
+    no depth guidance): the reference's own ConvOnet(coarse=True) vs oracle/nice.py, outputs,
+    loss and the coarse-grid gradient bit-identical."""
+    from oracle import ref_harness
+    from oracle.nice import NiceOracle
+    bound = np.array([[-2.0, 2.0], [-2.5, 2.0], [-2.0, 2.3]])
+    torch.manual_seed(3)
+    ref = ref_harness.ref_conv_onet(bound, coarse=True)
+    ora = NiceOracle(bound, coarse=True)
+    ref_harness.copy_nice_ref_to_oracle(ref, ora)
+    assert tuple(ref.grid_c['grid_coarse'].shape) == tuple(ora.grids['grid_coarse'].shape)
+    with torch.no_grad():
+        ora.grids['grid_coarse'].mul_(30)
+        ref.grid_c['grid_coarse'] = ref.grid_c['grid_coarse'] * 30
+        for lin in list(ora.coarse.pts) + [ora.coarse.out]:
+            lin.bias.add_(0.05)
+        for i in range(5):
+            ref.decoder.coarse_decoder.pts_linears[i].bias.add_(0.05)
+        ref.decoder.coarse_decoder.output_linear.bias.add_(0.05)
+    ref.grid_c['grid_coarse'].requires_grad_(True)
+    assert torch.equal(ref.decoder.coarse_decoder.bound, ora.coarse_bound)
+    g = torch.Generator().manual_seed(4)
+    R = 50
+    rays_o = (torch.rand(R, 3, generator=g) - 0.5) * 0.5
+    rays_d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    td = torch.rand(R, 1, generator=g) * 1.5 + 0.3
+    td[3::7] = 0
+    ts = torch.rand(R, 3, generator=g)
+    inp = dict(rays_o=rays_o, rays_d=rays_d, target_s=ts, target_d=td, stage='coarse')
+    with ref_harness.cuda_calls_are_noops():
+        out_r = ref(inp)
+    out_o = ora.render(rays_o, rays_d, td, 'coarse')
+    assert out_o['z_vals'].shape == (R, 32)
+    for k in ('depth', 'uncertainty'):
+        assert torch.equal(out_r[k], out_o[k]), k
+    ld_r = ref.get_loss_dict(out_r, inp, True, 'coarse')
+    ld_o = ora.loss_dict(out_o, ts, td, True, 'coarse')
+    assert set(ld_r) == set(ld_o) == {'depth_loss'}
+    assert float(ld_r['depth_loss'].detach()) == float(ld_o['depth_loss'].detach())
+    ld_r['depth_loss'].backward()
+    ld_o['depth_loss'].backward()
+    assert torch.equal(ref.grid_c['grid_coarse'].grad, ora.grids['grid_coarse'].grad)
+
+
+@pytest.mark.needs_reference
 def test_nice_oracle_matches_reference_class_live():
     from oracle import ref_harness
     from oracle.nice import NiceOracle
@@ -525,3 +571,100 @@ def test_keyframe_selection_overlap_matches_reference_function():
         b = keyframe_selection_overlap(cam, frames[0], frames[1:], k, device='cpu')
         assert [f.fid for f in a] == [f.fid for f in b], k
     assert 8 not in [f.fid for f in b]  # the frame looking the other way has no overlap
+
+
+def test_convonet_load_pretrain_key_mapping(tmp_path):
+    """conv_onet.py:293-322: 'decoder.coarse.*' of the middle_fine checkpoint feeds the MIDDLE
+    decoder, 'decoder.fine.*' the fine decoder, 'decoder.*' of the coarse checkpoint the coarse
+    decoder; encoder keys are dropped; a set path must load."""
+    import warnings
+    from xrdslam_b200.camera import Camera
+    from xrdslam_b200.conv_onet import MLP, MLP_no_xyz, ConvOnetConfig
+    torch.manual_seed(0)
+    mid, fine, coarse = MLP('middle', 32, False), MLP('fine', 64, False), MLP_no_xyz('coarse', 32)
+    ck = {'model': {'encoder.x': torch.zeros(1)}}
+    ck['model'].update({'decoder.coarse.' + k: v.clone() for k, v in mid.state_dict().items()})
+    ck['model'].update({'decoder.fine.' + k: v.clone() for k, v in fine.state_dict().items()})
+    torch.save(ck, tmp_path / 'middle_fine.pt')
+    ck2 = {'model': {'decoder.' + k: v.clone() for k, v in coarse.state_dict().items()}}
+    ck2['model']['encoder.y'] = torch.zeros(1)
+    torch.save(ck2, tmp_path / 'coarse.pt')
+    cam = Camera(320., 320., 319.5, 239.5, 640, 480)
+    bound = np.array([[-2.0, 2.0], [-2.0, 2.0], [-2.0, 2.0]])
+    with warnings.catch_warnings():
+        warnings.simplefilter('error')  # both checkpoints given: nothing stays random
+        m = ConvOnetConfig(coarse=True, pretrained_decoders_coarse=tmp_path / 'coarse.pt',
+                           pretrained_decoders_middle_fine=tmp_path / 'middle_fine.pt'
+                           ).setup(camera=cam, bounding_box=bound)
+    for got, ref in ((m.decoder.middle_decoder, mid), (m.decoder.fine_decoder, fine),
+                     (m.decoder.coarse_decoder, coarse)):
+        for k, v in ref.state_dict().items():
+            assert torch.equal(got.state_dict()[k], v), k
+    assert 'grid_coarse' in m.grids and 'grid_coarse' in m.get_param_groups()
+    with pytest.warns(RuntimeWarning, match='randomly initialised'):
+        ConvOnetConfig().setup(camera=cam, bounding_box=bound)
+    with pytest.raises(Exception):
+        ConvOnetConfig(pretrained_decoders_middle_fine=tmp_path / 'missing.pt').setup(
+            camera=cam, bounding_box=bound)
+
+
+@pytest.mark.needs_reference
+def test_pixel_grad_sampler_bit_identical_to_reference_function():
+    """common.get_sample_uv_with_grad / get_samples_with_pixel_grad (Point-SLAM colour-gradient
+    pixels, default mapping_pixels_based_on_color_grad = 1000) against the reference's own
+    functions under the same numpy seed.  skimage (absent here) is handed to the reference as
+    the scipy.ndimage restatement the mirror uses -- "parity unpinned" at rgb2gray / sobel; the
+    selection logic (argpartition top ratio*n, region mask, np.random.choice, depth filter, ray
+    construction) is the reference's own code."""
+    from types import SimpleNamespace
+    from scipy import ndimage
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip('needs /root/reference')
+    ref_harness.install()
+    import slam.common.common as rc
+    from slam.common.camera import Camera as RCam
+    import xrdslam_b200.common as mc
+    from xrdslam_b200.synthetic import make_sequence
+    hs = np.array([[1, 2, 1], [0, 0, 0], [-1, -2, -1]], dtype=np.float64) / 4.0
+    rc.rgb2gray = mc.rgb2gray_np
+    rc.filters = SimpleNamespace(sobel_h=lambda im: ndimage.convolve(im, hs, mode='reflect'),
+                                 sobel_v=lambda im: ndimage.convolve(im, hs.T, mode='reflect'))
+    cam, poses, fr = make_sequence(1, width=160, height=120)
+    rcam = RCam(cam.fx, cam.fy, cam.cx, cam.cy, cam.width, cam.height)
+    c2w = torch.from_numpy(poses[0])
+    rgb, depth = fr[0]
+    np.random.seed(3)
+    a = rc.get_sample_uv_with_grad(5, 115, 7, 150, 40, rgb)
+    np.random.seed(3)
+    b = mc.get_sample_uv_with_grad(5, 115, 7, 150, 40, rgb)
+    assert np.array_equal(a, b) and len(set(a.tolist())) == 40
+    for kw in (dict(), dict(Hedge=4, Wedge=6, depth_limit=3.0)):
+        np.random.seed(11)
+        ra = rc.get_samples_with_pixel_grad(rcam, 60, c2w, depth, rgb, device='cpu', **kw)
+        np.random.seed(11)
+        rb = mc.get_samples_with_pixel_grad(cam, 60, c2w, depth, rgb, device='cpu', **kw)
+        assert len(ra) == len(rb) == 6
+        for x, y in zip(ra, rb):
+            assert x.dtype == y.dtype and torch.equal(x, y), kw
+
+
+def test_convonet2_load_pretrain(tmp_path):
+    """conv_onet_pointslam.py:228-246: geometry decoder <- 'decoder.coarse.*' (strict=False)."""
+    from xrdslam_b200.camera import Camera
+    from xrdslam_b200.conv_onet_pointslam import ConvOnet2Config
+    cam = Camera(320., 320., 319.5, 239.5, 640, 480)
+    with pytest.warns(RuntimeWarning, match='randomly initialised'):
+        src = ConvOnet2Config().setup(camera=cam)
+    sd = src.decoder.geo_decoder.state_dict()
+    torch.manual_seed(3)
+    ck = {'model': {'decoder.coarse.' + k: torch.randn_like(v) for k, v in sd.items()}}
+    ck['model']['decoder.fine.fc_c.0.weight'] = torch.zeros(32, 64)
+    ck['model']['encoder.z'] = torch.zeros(2)
+    torch.save(ck, tmp_path / 'middle_fine.pt')
+    m = ConvOnet2Config(pretrained_decoders_middle_fine=tmp_path / 'middle_fine.pt').setup(camera=cam)
+    for k, v in m.decoder.geo_decoder.state_dict().items():
+        assert torch.equal(v, ck['model']['decoder.coarse.' + k]), k
+    torch.save({'model': {'encoder.z': torch.zeros(2)}}, tmp_path / 'bad.pt')
+    with pytest.raises(RuntimeError):
+        ConvOnet2Config(pretrained_decoders_middle_fine=tmp_path / 'bad.pt').setup(camera=cam)

@@ -104,6 +104,16 @@ class XrdNiceCfg(C.Structure):
                 ('t_uniform', vp), ('t_surface', vp), ('max_depth_global', vp)]
 
 
+class XrdNiceCoarseDecoder(C.Structure):
+    _fields_ = [('pts_w', vp * 5), ('pts_b', vp * 5), ('out_w', vp), ('out_b', vp)]
+
+
+class XrdNiceCoarseCfg(C.Structure):
+    _fields_ = [('n_samples', C.c_int), ('bound_min', C.c_double * 3),
+                ('bound_max', C.c_double * 3), ('coarse_bound_min', C.c_double * 3),
+                ('coarse_bound_max', C.c_double * 3), ('t_uniform', vp)]
+
+
 class XrdNiceOut(C.Structure):
     _fields_ = [('rgb', vp), ('depth', vp), ('uncertainty', vp), ('z_vals', vp),
                 ('raw', vp), ('losses', vp)]
@@ -275,6 +285,11 @@ SYMBOLS = {
         C.POINTER(XrdNiceDecoder), C.POINTER(XrdPointColorDecoder), C.POINTER(XrdPointCfg),
         C.POINTER(XrdPointOut), C.POINTER(XrdPointGrads), vp, C.c_size_t, vp]),
     'xrd_nice_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    'xrd_nice_coarse_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    'xrd_nice_coarse_step': (C.c_int, [
+        C.POINTER(XrdRays), C.POINTER(XrdNiceGrid), C.POINTER(XrdNiceCoarseDecoder),
+        C.POINTER(XrdNiceCoarseCfg), C.POINTER(XrdNiceOut), vp, vp, vp, C.c_int, vp, C.c_size_t,
+        vp]),
     'xrd_nice_step': (C.c_int, [
         C.POINTER(XrdRays), C.POINTER(XrdNiceGrid), C.POINTER(XrdNiceDecoder),
         C.POINTER(XrdNiceCfg), C.POINTER(XrdNiceOut), C.POINTER(XrdNiceGrads), vp,

@@ -128,6 +128,75 @@ def get_sample_uv(H0, H1, W0, W1, n, depth, color, device='cuda:0',
     return i, j, d, c
 
 
+# ---- colour-gradient pixel selection (Point-SLAM, common.py:74-106, :230-285) ---------------
+# skimage.color.rgb2gray / skimage.filters.sobel_h, sobel_v are restated on scipy.ndimage (what
+# skimage itself calls): Y = 0.2125 R + 0.7154 G + 0.0721 B; sobel = 3x3 correlation-free
+# convolution with [1,2,1]^T x [1,0,-1] / 4, boundary mode 'reflect'.  skimage is not in this
+# image: "parity unpinned" at that boundary (float64 here); everything after the gradient image
+# (argpartition, region mask, np.random.choice) is the reference's own arithmetic.
+_HSOBEL = np.array([[1, 2, 1], [0, 0, 0], [-1, -2, -1]], dtype=np.float64) / 4.0
+
+
+def rgb2gray_np(image):
+    img = np.asarray(image, dtype=np.float64)
+    return img[..., 0] * 0.2125 + img[..., 1] * 0.7154 + img[..., 2] * 0.0721
+
+
+def sobel_magnitude_np(image):
+    from scipy import ndimage
+    gray = rgb2gray_np(image)
+    grad_y = ndimage.convolve(gray, _HSOBEL, mode='reflect')       # sobel_h
+    grad_x = ndimage.convolve(gray, _HSOBEL.T, mode='reflect')     # sobel_v
+    return np.sqrt(grad_x**2 + grad_y**2)
+
+
+def get_sample_uv_with_grad(H0, H1, W0, W1, n, image, ratio=15):
+    """n flat pixel indices drawn (np.random.choice, no replacement) from the ratio*n pixels
+    with the largest colour-gradient magnitude that fall inside rows H0..H1, cols W0..W1."""
+    image = np.asarray(image)
+    grad_mag = sobel_magnitude_np(image)
+    img_size = (image.shape[0], image.shape[1])
+    selected_index = np.argpartition(grad_mag, -ratio * n, axis=None)[-ratio * n:]
+    indices_h, indices_w = np.unravel_index(selected_index, img_size)
+    mask = (indices_h >= H0) & (indices_h < H1) & (indices_w >= W0) & (indices_w < W1)
+    indices_h, indices_w = indices_h[mask], indices_w[mask]
+    selected_index = np.ravel_multi_index(np.array((indices_h, indices_w)), img_size)
+    samples = np.random.choice(range(0, indices_h.shape[0]), size=n, replace=False)
+    return selected_index[samples]
+
+
+def get_samples_with_pixel_grad(camera, n_color, c2w, depth, color, device, Hedge=0, Wedge=0,
+                                depth_filter=True, return_index=True, depth_limit=None):
+    """Rays through n_color pixels chosen by colour gradient (common.py:230-285); depth /
+    colour are the frame's HOST arrays like in the reference."""
+    H, W = camera.height, camera.width
+    assert n_color > 0, 'invalid number of rays to sample.'
+    color_np = np.asarray(color)
+    index_color_grad = get_sample_uv_with_grad(Hedge, H - Hedge, Wedge, W - Wedge, n_color,
+                                               color_np)
+    merged = np.union1d(index_color_grad, [])
+    jj, ii = np.unravel_index(merged.astype(int), (H, W))  # row, column
+    i = torch.from_numpy(ii).to(device).float()
+    j = torch.from_numpy(jj).to(device).float()
+    rays_o, rays_d = get_rays_from_uv(i, j, c2w, camera.fx, camera.fy, camera.cx, camera.cy,
+                                      device)
+    i, j = i.long(), j.long()
+    depth_t = _as_dev(depth, device)
+    color_t = _as_dev(color, device)
+    sample_depth = depth_t[j, i].reshape(-1)
+    sample_color = color_t[j, i].reshape(-1, 3)
+    if depth_filter:
+        mask = sample_depth > 0
+        if depth_limit is not None:
+            mask = mask & (sample_depth < depth_limit)
+        rays_o, rays_d = rays_o[mask], rays_d[mask]
+        sample_depth, sample_color = sample_depth[mask], sample_color[mask]
+        i, j = i[mask], j[mask]
+    if return_index:
+        return rays_o, rays_d, sample_depth, sample_color, i.to(torch.int64), j.to(torch.int64)
+    return rays_o, rays_d, sample_depth, sample_color
+
+
 def get_samples(camera, n, c2w, depth, color, device, Hedge=0, Wedge=0,
                 depth_filter=False, return_index=False, depth_limit=None,
                 indices=None):

@@ -23,18 +23,18 @@ from torch import nn
 from torch.nn import Parameter
 
 from . import _cabi
-from ._cabi import (XrdNiceCfg, XrdNiceDecoder, XrdNiceDecoderGrads, XrdNiceGrads,
-                    XrdNiceGrid, XrdNiceOut, XrdRays, check, ptr)
+from ._cabi import (XrdNiceCfg, XrdNiceCoarseCfg, XrdNiceCoarseDecoder, XrdNiceDecoder,
+                    XrdNiceDecoderGrads, XrdNiceGrads, XrdNiceGrid, XrdNiceOut, XrdRays, check, ptr)
 from .base_model import Model, ModelConfig, scale_grads, upstream_scale
 
-STAGES = {'middle': 0, 'fine': 1, 'color': 2}
+STAGES = {'middle': 0, 'fine': 1, 'color': 2}  # 'coarse' has its own entry (xrd_nice_coarse_step)
 
 
 @dataclass
 class ConvOnetConfig(ModelConfig):
     """slam/models/conv_onet.py:18-63 (field names and defaults kept)."""
     _target: Type = field(default_factory=lambda: ConvOnet)
-    coarse: bool = False
+    coarse: bool = False  # model default (conv_onet.py:23); the nice-slam run config sets True
     occupancy: bool = True
     pretrained_decoders_coarse: Optional[Path] = None
     pretrained_decoders_middle_fine: Optional[Path] = None
@@ -101,10 +101,23 @@ class MLP(nn.Module):
         return t + [self.output_linear.weight, self.output_linear.bias]
 
 
-class NICE(nn.Module):
-    """decoder_nice.py:323-384 (coarse level unsupported, as in the reference config)."""
-    def __init__(self, c_dim=32):
+class MLP_no_xyz(nn.Module):
+    """Parameter container of decoder_nice.py:237-320 (the coarse decoder): 5 blocks of width
+    32 on the grid feature alone, the feature re-concatenated after block 2."""
+    def __init__(self, name, c_dim, hidden_size=32):
         super().__init__()
+        self.name, self.c_dim = name, c_dim
+        dims = [hidden_size, hidden_size, hidden_size, hidden_size + c_dim, hidden_size]
+        self.pts_linears = nn.ModuleList([_DenseLayer(d, hidden_size) for d in dims])
+        self.output_linear = _DenseLayer(hidden_size, 1, 'linear')
+
+
+class NICE(nn.Module):
+    """decoder_nice.py:323-384."""
+    def __init__(self, c_dim=32, coarse=False):
+        super().__init__()
+        if coarse:
+            self.coarse_decoder = MLP_no_xyz('coarse', c_dim)
         self.middle_decoder = MLP('middle', c_dim, False)
         self.fine_decoder = MLP('fine', 2 * c_dim, False)
         self.color_decoder = MLP('color', c_dim, True)
@@ -154,6 +167,29 @@ class _NiceStep(torch.autograd.Function):
         return (None, None, None, None, None, ro, rd, dg[0], dg[1], dg[2], *dc)
 
 
+class _NiceCoarseStep(torch.autograd.Function):
+    """(losses[2], rgb, depth, uncertainty) = fused coarse stage(rays, coarse grid)."""
+    @staticmethod
+    def forward(ctx, model, target_d, rays_o, rays_d, grid):
+        need_rays = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        need_grid = ctx.needs_input_grad[4]
+        outs, grads = model._launch_coarse(rays_o, rays_d, target_d, need_rays or need_grid,
+                                           need_rays, need_grid)
+        ctx.grads = grads
+        ret = (outs['losses'], outs['rgb'], outs['depth'], outs['uncertainty'])
+        ctx.mark_non_differentiable(*ret[1:])
+        return ret
+
+    @staticmethod
+    def backward(ctx, g_losses, *_):
+        g = ctx.grads
+        if g is None:
+            raise RuntimeError('backward through a forward-only NICE coarse pass')
+        ro, rd, dg = scale_grads([g['d_rays_o'], g['d_rays_d'], g['d_grid']],
+                                 upstream_scale(g_losses, 1))
+        return None, None, ro, rd, dg
+
+
 class ConvOnet(Model):
     """Model class (slam/models/conv_onet.py:66-524)."""
 
@@ -165,14 +201,15 @@ class ConvOnet(Model):
     def populate_modules(self):
         super().populate_modules()
         cfg = self.config
-        if cfg.coarse or cfg.rendering_n_importance or cfg.rendering_perturb or \
+        if cfg.rendering_n_importance or cfg.rendering_perturb or \
                 cfg.rendering_lindisp or not cfg.occupancy:
             raise NotImplementedError('B200 path covers the reference nice-slam config: '
-                                      'coarse=False, occupancy, no importance sampling')
+                                      'occupancy, no importance sampling / perturbation')
         self.bounding_box = torch.as_tensor(np.asarray(self.bounding_box),
                                             dtype=torch.float64).clone()
-        self.decoder = NICE(cfg.model_c_dim)
+        self.decoder = NICE(cfg.model_c_dim, coarse=cfg.coarse)
         self.load_bound()
+        self.load_pretrain()
         self.grid_init()
         self.grid_opti_mask = {}
         self.dp = None  # xrdslam_b200.dp.MappingDataParallel when mapping rays are sharded
@@ -187,15 +224,60 @@ class ConvOnet(Model):
         self.bounding_box[:, 1] = (((self.bounding_box[:, 1] - self.bounding_box[:, 0]) /
                                     bd).int() + 1) * bd + self.bounding_box[:, 0]
 
+    def load_pretrain(self):
+        """conv_onet.py:293-322: the frozen decoders come from the pretrained ConvONet
+        checkpoints -- ckpt['model'] keys 'decoder.*' -> coarse decoder, 'decoder.coarse.*' ->
+        MIDDLE decoder, 'decoder.fine.*' -> fine decoder (encoder keys dropped).  A path that
+        is set must load; without a path the decoders keep their seeded xavier init (the
+        reference checkpoints are Git-LFS objects that do not ship with the repository:
+        synthetic benchmarks and parity tests run that way) and a warning says so, because
+        NICE-SLAM never trains the middle / fine / coarse decoders."""
+        cfg = self.config
+
+        def load(path):
+            ckpt = torch.load(path, map_location='cpu', weights_only=False)
+            if not isinstance(ckpt, dict) or 'model' not in ckpt:
+                raise RuntimeError(f'{path}: not a ConvONet checkpoint (no "model" entry)')
+            return ckpt['model']
+        missing = []
+        if cfg.coarse:
+            if cfg.pretrained_decoders_coarse is not None:
+                sd = {k[8:]: v for k, v in load(cfg.pretrained_decoders_coarse).items()
+                      if 'decoder' in k and 'encoder' not in k}
+                self.decoder.coarse_decoder.load_state_dict(sd)
+            else:
+                missing.append('coarse')
+        if cfg.pretrained_decoders_middle_fine is not None:
+            mid, fine = {}, {}
+            for k, v in load(cfg.pretrained_decoders_middle_fine).items():
+                if 'decoder' in k and 'encoder' not in k:
+                    if 'coarse' in k:
+                        mid[k[8 + 7:]] = v
+                    elif 'fine' in k:
+                        fine[k[8 + 5:]] = v
+            self.decoder.middle_decoder.load_state_dict(mid)
+            self.decoder.fine_decoder.load_state_dict(fine)
+        else:
+            missing += ['middle', 'fine']
+        if missing:
+            import warnings
+            warnings.warn('ConvOnet: no pretrained checkpoint for the frozen ' + '/'.join(missing) +
+                          ' decoder(s) (pretrained_decoders_*): they stay randomly initialised',
+                          RuntimeWarning, stacklevel=3)
+
     def grid_init(self):
         """conv_onet.py:254-291 + feature_grid_nice.py (shapes), channel-last storage."""
         cfg = self.config
         xyz_len = self.bounding_box[:, 1] - self.bounding_box[:, 0]
         self.grids = nn.ParameterDict()
-        for key, gl, std in (('grid_middle', cfg.grid_len_middle, 0.01),
-                             ('grid_fine', cfg.grid_len_fine, 0.0001),
-                             ('grid_color', cfg.grid_len_color, 0.01)):
-            s = list(map(int, (xyz_len / gl).tolist()))  # (X, Y, Z) counts
+        levels = [('grid_middle', xyz_len, cfg.grid_len_middle, 0.01),
+                  ('grid_fine', xyz_len, cfg.grid_len_fine, 0.0001),
+                  ('grid_color', xyz_len, cfg.grid_len_color, 0.01)]
+        if cfg.coarse:  # conv_onet.py:256-275: the coarse grid spans the enlarged extent
+            levels.insert(0, ('grid_coarse', xyz_len * cfg.model_coarse_bound_enlarge,
+                              cfg.grid_len_coarse, 0.01))
+        for key, ext, gl, std in levels:
+            s = list(map(int, (ext / gl).tolist()))  # (X, Y, Z) counts
             val = torch.zeros([s[2], s[1], s[0], cfg.model_c_dim]).normal_(mean=0, std=std)
             self.grids[key] = nn.Parameter(val)
 
@@ -286,15 +368,84 @@ class ConvOnet(Model):
         check('xrd_nice_step', st)
         return o, g
 
+    def _launch_coarse(self, rays_o, rays_d, target_d, with_grads, need_rays=False,
+                       need_grid=False):
+        """Stage 'coarse' through xrd_nice_coarse_step (csrc/nice.cu)."""
+        cfg = self.config
+        if not cfg.coarse:
+            raise RuntimeError("stage 'coarse' needs ConvOnetConfig(coarse=True)")
+        grid = self.grids['grid_coarse']
+        dev = grid.device
+        if dev.type != 'cuda':
+            raise RuntimeError('xrdslam_b200 has no CPU path: model must be on a CUDA device')
+        lib = _cabi.lib()
+        f32 = dict(dtype=torch.float32, device=dev)
+        f64 = dict(dtype=torch.float64, device=dev)
+        rays_o = rays_o.detach().to(**f32).contiguous()
+        rays_d = rays_d.detach().to(**f32).contiguous()
+        R, S = rays_o.shape[0], cfg.rendering_n_samples
+        td = target_d.detach().to(**f32).reshape(-1).contiguous() if target_d is not None else None
+        o = dict(rgb=torch.zeros(R, 3, **f32), depth=torch.empty(R, **f64),
+                 uncertainty=torch.empty(R, **f64), losses=torch.zeros(2, **f32))
+        rays = XrdRays(R, ptr(rays_o), ptr(rays_d), None, ptr(td))
+        g = grid.detach()
+        gs = XrdNiceGrid(ptr(g), g.shape[2], g.shape[1], g.shape[0])
+        d = self.decoder.coarse_decoder
+        keep = [t.detach() for l in d.pts_linears for t in (l.weight, l.bias)] + \
+            [d.output_linear.weight.detach(), d.output_linear.bias.detach()]
+        dec = XrdNiceCoarseDecoder()
+        for i in range(5):
+            dec.pts_w[i], dec.pts_b[i] = ptr(keep[2 * i]), ptr(keep[2 * i + 1])
+        dec.out_w, dec.out_b = ptr(keep[10]), ptr(keep[11])
+        c = XrdNiceCoarseCfg()
+        c.n_samples = S
+        e = cfg.model_coarse_bound_enlarge
+        for k in range(3):
+            c.bound_min[k] = float(self.bounding_box[k, 0])
+            c.bound_max[k] = float(self.bounding_box[k, 1])
+            c.coarse_bound_min[k] = float(self.bounding_box[k, 0] * e)
+            c.coarse_bound_max[k] = float(self.bounding_box[k, 1] * e)
+        c.t_uniform = ptr(self._t_uniform)
+        zc = getattr(self, '_z_capture', None)
+        out = XrdNiceOut(ptr(o['rgb']), ptr(o['depth']), ptr(o['uncertainty']), ptr(zc), None,
+                         ptr(o['losses']))
+        gr = None
+        if with_grads:
+            if td is None:
+                raise RuntimeError('gradients need target_d')
+            gr = dict(d_grid=torch.zeros_like(grid) if need_grid else None,
+                      d_rays_o=torch.empty(R, 3, **f32) if need_rays else None,
+                      d_rays_d=torch.empty(R, 3, **f32) if need_rays else None)
+        nb = lib.xrd_nice_coarse_workspace_bytes(R, S, int(with_grads))
+        ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            st = lib.xrd_nice_coarse_step(
+                C.byref(rays), C.byref(gs), C.byref(dec), C.byref(c), C.byref(out),
+                ptr(gr['d_grid']) if gr else None, ptr(gr['d_rays_o']) if gr else None,
+                ptr(gr['d_rays_d']) if gr else None, int(with_grads), ptr(ws), nb,
+                torch.cuda.current_stream(dev).cuda_stream)
+        check('xrd_nice_coarse_step', st)
+        return o, gr
+
     # --------------------------------------------------------- Model API ---
     def get_outputs(self, input) -> Dict[str, Union[torch.Tensor, List]]:
         """conv_onet.py:132-143."""
         stage = input['stage']
-        if stage == 'coarse':
-            raise NotImplementedError('coarse level (reference: "TODO: support True")')
         rays_o, rays_d = input['rays_o'], input['rays_d']
         target_d, target_s = input['target_d'], input.get('target_s')
         fused = torch.is_grad_enabled() and target_s is not None and 'is_mapping' in input
+        if stage == 'coarse':
+            # conv_onet.py:137-138: the coarse level renders without depth guidance; the
+            # target depth only enters the (mapping) loss
+            if fused:
+                grid = self.grids['grid_coarse']
+                if getattr(self, 'freeze_map_grads', False):
+                    grid = grid.detach()
+                losses, rgb, depth, unc = _NiceCoarseStep.apply(self, target_d, rays_o, rays_d, grid)
+                return {'rgb': rgb, 'depth': depth, 'uncertainty': unc, '_losses': losses}
+            o, _ = self._launch_coarse(rays_o, rays_d, target_d, False)
+            o.pop('losses')
+            return o
         if fused:
             cparams = self.decoder.color_decoder.tensors()
             grids = [self.grids[k] for k in ('grid_middle', 'grid_fine', 'grid_color')]
@@ -341,6 +492,8 @@ class ConvOnet(Model):
         bb = self.bounding_box
         c2w = cur_frame.get_pose().detach()
         for key, g in self.grids.items():
+            if key == 'grid_coarse':
+                continue  # utils.py:323-325: the coarse grid is optimised whole
             Z, Y, X = g.shape[:3]
             zs = torch.linspace(float(bb[2][0]), float(bb[2][1]), Z)
             ys = torch.linspace(float(bb[1][0]), float(bb[1][1]), Y)
@@ -367,9 +520,10 @@ class ConvOnet(Model):
             dec += list(self.decoder.color_decoder.parameters())
         if dec:
             groups['decoder'] = dec
-        for key in ('grid_middle', 'grid_fine', 'grid_color'):
+        for key in self.grids:  # conv_onet.py:197-211: every grid of grid_c, coarse included
             p = self.grids[key]
+            # get_mask_from_c2w returns an all-ones mask for 'grid_coarse' (utils.py:323-325)
             p._xrd_row_mask = self.grid_opti_mask.get(key) \
-                if self.config.mapping_frustum_feature_selection else None
+                if (self.config.mapping_frustum_feature_selection and key != 'grid_coarse') else None
             groups[key] = [p]
         return groups

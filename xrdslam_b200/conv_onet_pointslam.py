@@ -182,9 +182,34 @@ class ConvOnet2(Model):
                 cfg.rendering_sample_near_pcl or cfg.model_encode_exposure:
             raise NotImplementedError('B200 path covers the reference point-slam config')
         self.decoder = POINT(cfg.model_c_dim)
+        self.load_pretrain()
         self.neural_point_cloud = None
         self.register_buffer('_t_surface', torch.linspace(0.0, 1.0, steps=cfg.rendering_n_surface),
                              persistent=False)
+
+    def load_pretrain(self):
+        """conv_onet_pointslam.py:228-246: the (frozen) geometry decoder takes the
+        'decoder.coarse.*' entries of the pretrained ConvONet middle_fine checkpoint,
+        strict=False (the checkpoint has no colour-only members).  A path that is set must
+        load; without one the decoder keeps its seeded init and a warning says so (the
+        reference checkpoints are Git-LFS objects that do not ship with the repository)."""
+        path = self.config.pretrained_decoders_middle_fine
+        if path is None:
+            import warnings
+            warnings.warn('ConvOnet2: no pretrained checkpoint for the frozen geometry decoder '
+                          '(pretrained_decoders_middle_fine): it stays randomly initialised',
+                          RuntimeWarning, stacklevel=3)
+            return
+        ckpt = torch.load(path, map_location='cpu', weights_only=False)
+        if not isinstance(ckpt, dict) or 'model' not in ckpt:
+            raise RuntimeError(f'{path}: not a ConvONet checkpoint (no "model" entry)')
+        middle = {}
+        for k, v in ckpt['model'].items():
+            if 'decoder' in k and 'encoder' not in k and 'coarse' in k:
+                middle[k[8 + 7:]] = v
+        res = self.decoder.geo_decoder.load_state_dict(middle, strict=False)
+        if len(res.missing_keys) == len(self.decoder.geo_decoder.state_dict()):
+            raise RuntimeError(f'{path}: no decoder.coarse.* entries for the geometry decoder')
 
     def model_update(self, device=None):
         """conv_onet_pointslam.py:98-128: create the point cloud lazily."""

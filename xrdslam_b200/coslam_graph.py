@@ -165,10 +165,9 @@ class MappingGraphSession:
                   lib.xrd_coslam_step(C.byref(rays), C.byref(grid), C.byref(mlp), C.byref(c), None,
                                       C.byref(out), None, ptr(self.ws), self.ws.numel(), stream))
 
-    def _part_b(self, stream):
+    def _part_b(self, stream, smooth=True, pose=True):
         """fused forward / loss / backward (+ smoothness, pose-gradient reduction)."""
         model, cfg, lib = self.model, self.model.config, _cabi.lib()
-        R, n = self.R, self.n_poses
         rays, grid, mlp, c, out = self._step_structs(2 if self.world > 1 else 0)
         G = self.grads
         gs = XrdCoslamGrads(ptr(G[self.table]), *(ptr(G[t]) for t in self.weights),
@@ -178,21 +177,35 @@ class MappingGraphSession:
         check('xrd_coslam_step',
               lib.xrd_coslam_step(C.byref(rays), C.byref(grid), C.byref(mlp), C.byref(c), None,
                                   C.byref(out), C.byref(gs), ptr(self.ws), self.ws.numel(), stream))
-        if not self.first:
-            # sharded: every rank evaluates the SAME lattice (shared generator) at weight / W,
-            # so the all-reduced sum is the single-GPU term
-            check('xrd_coslam_smoothness_dev', lib.xrd_coslam_smoothness_dev(
-                C.byref(grid), cfg.trainging_smooth_pts, cfg.trainging_smooth_vox,
-                cfg.trainging_smooth_margin, cfg.trainging_smooth_weight / self.world,
-                self.dyn.data_ptr() + 8, ptr(self.smooth_loss), ptr(G[self.table]), 1.0,
-                ptr(self.ws_s), self.ws_s.numel(), stream))
-        if self.ba:
-            check('xrd_rays_pose_grads', lib.xrd_rays_pose_grads(
-                R, ptr(self.dirs), ptr(self.ids), n, ptr(self.d_rays_o), ptr(self.d_rays_d),
-                ptr(self.d_poses), stream))
-            check('xrd_pose_matrices_grads', lib.xrd_pose_matrices_grads(
-                n, ptr(self.rot), ptr(self.d_poses), ptr(self.fixed), ptr(self.d_rot_it),
-                ptr(self.d_trans_it), stream))
+        if smooth:
+            self._part_smooth(stream)
+        if pose:
+            self._part_pose(stream)
+
+    def _part_smooth(self, stream):
+        """Smoothness / TV term into the same table-gradient buffer (red.add, order-free).
+        Sharded: every rank evaluates the SAME lattice (shared generator) at weight / W, so
+        the all-reduced sum is the single-GPU term."""
+        if self.first:
+            return
+        model, cfg, lib = self.model, self.model.config, _cabi.lib()
+        grid = model._grid_struct(self.table.detach())
+        check('xrd_coslam_smoothness_dev', lib.xrd_coslam_smoothness_dev(
+            C.byref(grid), cfg.trainging_smooth_pts, cfg.trainging_smooth_vox,
+            cfg.trainging_smooth_margin, cfg.trainging_smooth_weight / self.world,
+            self.dyn.data_ptr() + 8, ptr(self.smooth_loss), ptr(self.grads[self.table]), 1.0,
+            ptr(self.ws_s), self.ws_s.numel(), stream))
+
+    def _part_pose(self, stream):
+        if not self.ba:
+            return
+        lib, R, n = _cabi.lib(), self.R, self.n_poses
+        check('xrd_rays_pose_grads', lib.xrd_rays_pose_grads(
+            R, ptr(self.dirs), ptr(self.ids), n, ptr(self.d_rays_o), ptr(self.d_rays_d),
+            ptr(self.d_poses), stream))
+        check('xrd_pose_matrices_grads', lib.xrd_pose_matrices_grads(
+            n, ptr(self.rot), ptr(self.d_poses), ptr(self.fixed), ptr(self.d_rot_it),
+            ptr(self.d_trans_it), stream))
 
     def _part_c(self, stream, with_adam):
         """Adam on table + decoder, pose-gradient accumulation (accum_step), total loss."""
@@ -214,26 +227,56 @@ class MappingGraphSession:
             self.d_trans += self.d_trans_it
         self.loss_total = self.flat[-8:-3].sum()
 
+    def _iteration(self, with_adam):
+        """The whole iteration on the current stream.  Sharded (world > 1): the two NCCL
+        all-reduces are issued in place -- under stream capture they become nodes of the SAME
+        graph (no host launch between segments, no host-side rank synchronisation), and the
+        smoothness term runs on a forked stream so that it overlaps the 12-byte counts
+        all-reduce whose latency would otherwise sit on the critical path."""
+        dev = self.dev
+        cur = torch.cuda.current_stream(dev)
+        self._part_a(cur.cuda_stream)
+        if self.world == 1:
+            self._part_b(cur.cuda_stream)
+        else:
+            side = self._side
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                self._part_smooth(side.cuda_stream)
+            self.dp.all_reduce_sum(self.counts)   # batch-global loss normalisers (Q9)
+            self._part_b(cur.cuda_stream, smooth=False, pose=False)
+            cur.wait_stream(side)
+            self._part_pose(cur.cuda_stream)
+            self.dp.all_reduce_sum(self.flat)     # ONE collective: all gradients + loss terms
+        self._part_c(cur.cuda_stream, with_adam=with_adam)
+
     def _capture(self):
         dev = self.dev
         cur = lambda: torch.cuda.current_stream(dev).cuda_stream
+        self.single_graph = True
         with torch.cuda.device(dev):
-            # eager warm-up (lazy module loading, attribute calls), then capture
+            # eager warm-up (lazy module loading, attribute calls, NCCL communicator set-up),
+            # then capture
             self.rows[:, 2] = -1.0
             self.rows[:, 6] = 1.0
-            self._part_a(cur())
-            self._part_b(cur())
-            self._part_c(cur(), with_adam=False)
+            self._side = torch.cuda.Stream(dev) if self.world > 1 else None
+            self._iteration(with_adam=False)
             torch.cuda.synchronize(dev)
-            if self.world == 1:
+            try:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, capture_error_mode='relaxed'):
-                    self._part_a(cur())
-                    self._part_b(cur())
-                    self._part_c(cur(), with_adam=True)
+                    self._iteration(with_adam=True)
                 self.graphs = [g]
-            else:  # NCCL all-reduces run between the three captured segments
+            except Exception as e:  # noqa
+                if self.world == 1:
+                    raise
+                # NCCL refused capture on this build: three captured segments around the two
+                # host-issued all-reduces (the round-1 path)
+                self.single_graph = False
+                self.capture_error = repr(e)
+                torch.cuda.synchronize(dev)
                 pool = None
+                self.graphs = []
                 for part in (self._part_a, self._part_b,
                              lambda st: self._part_c(st, with_adam=True)):
                     g = torch.cuda.CUDAGraph()
@@ -333,8 +376,8 @@ class MappingGraphSession:
         if self._dyn_ev[k] is None:
             self._dyn_ev[k] = torch.cuda.Event()
         self._dyn_ev[k].record(torch.cuda.current_stream(self.dev))
-        if self.world == 1:
-            self.graphs[0].replay()
+        if len(self.graphs) == 1:
+            self.graphs[0].replay()  # world > 1: the NCCL all-reduces are nodes of this graph
         else:
             self.graphs[0].replay()
             self.dp.all_reduce_sum(self.counts)   # batch-global loss normalisers (Q9)

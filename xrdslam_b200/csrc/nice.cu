@@ -117,6 +117,7 @@ static __global__ void k_maxdepth(const float* d, int R, float* out) {
 
 struct SampleParams {
   int R, ns, nsurf;
+  int no_depth;  // stage 'coarse': gt_depth = None -> near = 0.01, far = far_bb, no surface samples
   const float *rays_o, *rays_d, *target_d;
   double bmin[3], bmax[3];
   const float *t_uniform, *t_surface;  // torch.linspace(0,1,n) tables
@@ -131,8 +132,8 @@ static __global__ void __launch_bounds__(128) k_sample(SampleParams p) {
   if (r >= p.R) return;
   const int S = p.ns + p.nsurf;
   double* z = zs[warp];
-  const float maxd = p.maxd[0];
-  const float gt = p.target_d[r];
+  const float maxd = p.no_depth ? 0.f : p.maxd[0];
+  const float gt = p.no_depth ? 0.f : p.target_d[r];
   // far_bb = min_d max_side (bound - o) / d  (+0.01), all in f64 (conv_onet.py:407-414)
   double far_bb = INFINITY;
 #pragma unroll
@@ -143,8 +144,8 @@ static __global__ void __launch_bounds__(128) k_sample(SampleParams p) {
   }
   far_bb += 0.01;
   const float cap = __fmul_rn(maxd, 1.2f);  // torch.max(gt_depth * 1.2): f32
-  const double far = fmin(fmax(far_bb, 0.0), (double)cap);
-  const float near = __fmul_rn(gt, 0.01f);
+  const double far = p.no_depth ? far_bb : fmin(fmax(far_bb, 0.0), (double)cap);
+  const float near = p.no_depth ? 0.01f : __fmul_rn(gt, 0.01f);
   for (int k = lane; k < S; k += 32) {
     double v;
     if (k < p.ns) {
@@ -554,6 +555,113 @@ static __global__ void __launch_bounds__(T) k_decoder_bwd(const DecParams P) {
   }
 }
 
+// --------------------------------------------------- coarse level (N6) ---
+// MLP_no_xyz (decoder_nice.py:237-320): h = c; 5 x [h = relu(W h + b)], [c, h] re-concatenated
+// after block 2, occupancy = w_out h + b_out.  The grid feature c is sampled with the COARSE
+// bound (scene bound x model_coarse_bound_enlarge, conv_onet.py:335-337); no positional
+// embedding, no fc_c.  The decoder is frozen (pretrained): gradients go to the grid (and rays).
+struct CoarseW {
+  const float* pts_w[5];  // torch layout [32][in], in = 32, 32, 32, 64, 32
+  const float* pts_b[5];
+  const float* out_w;     // [1][32]
+  const float* out_b;     // [1]
+};
+constexpr int CW_L3 = 3 * H * H;            // block 3: [64][32]
+constexpr int CW_L4 = CW_L3 + 2 * H * H;
+constexpr int CW_OUT = CW_L4 + H * H;
+constexpr int CW_B = CW_OUT + H;            // biases 5 x 32, then out bias
+constexpr int CW_TOTAL = CW_B + 5 * H + 4;
+
+static __device__ void stage_coarse(const CoarseW& w, float* sw) {
+  const int in[5] = {H, H, H, 2 * H, H};
+  const int off[5] = {0, H * H, 2 * H * H, CW_L3, CW_L4};
+  for (int l = 0; l < 5; ++l) {
+    for (int q = threadIdx.x; q < in[l] * H; q += blockDim.x) {
+      const int i = q / H, j = q % H;
+      sw[off[l] + q] = w.pts_w[l][j * in[l] + i];  // transposed: [in][out]
+    }
+    for (int q = threadIdx.x; q < H; q += blockDim.x) sw[CW_B + l * H + q] = w.pts_b[l][q];
+  }
+  for (int q = threadIdx.x; q < H; q += blockDim.x) sw[CW_OUT + q] = w.out_w[q];
+  if (threadIdx.x == 0) sw[CW_B + 5 * H] = w.out_b[0];
+}
+
+template <bool BWD>
+static __global__ void __launch_bounds__(T) k_coarse(const DecParams P, const CoarseW W) {
+  extern __shared__ __align__(16) float smem[];
+  float* sw = smem;
+  float* ccol = sw + CW_TOTAL;  // [32][T]: grid feature (fwd) / its gradient (bwd)
+  stage_coarse(W, sw);
+  __syncthreads();
+  const int tid = threadIdx.x, tbase = tid & ~31;
+  const int n_tiles = (P.P + T - 1) / T;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int p = tile * T + tid;
+    const bool active = p < P.P;
+    double pt[3] = {0.0, 0.0, 0.0};
+    if (active) point_f64(P, p, pt);
+    const Cell ca = make_cell(P, P.ga, pt);
+    float* c = ccol + tid;
+    if (!BWD) {
+      trilerp_coop(P.ga, ca, active, ccol, tbase);
+      __syncwarp();
+      if (active) {
+        float h[H], acc[H];
+#pragma unroll 1
+        for (int l = 0; l < 5; ++l) {
+#pragma unroll
+          for (int j = 0; j < H; ++j) acc[j] = sw[CW_B + l * H + j];
+          if (l == 0) dense_col(acc, sw, c, H);
+          else if (l == 3) { dense_col(acc, sw + CW_L3, c, H); dense_reg(acc, sw + CW_L3 + H * H, h); }
+          else dense_reg(acc, sw + (l == 4 ? CW_L4 : l * H * H), h);
+          uint32_t mask = 0;
+#pragma unroll
+          for (int j = 0; j < H; ++j) {
+            mask |= (acc[j] > 0.f) ? (1u << j) : 0u;
+            h[j] = fmaxf(acc[j], 0.f);
+          }
+          if (P.masks) P.masks[(size_t)l * P.P + p] = mask;
+        }
+        float o = sw[CW_B + 5 * H];
+#pragma unroll
+        for (int j = 0; j < H; ++j) o = fmaf(h[j], sw[CW_OUT + j], o);
+        P.out[0][p] = o;
+      }
+      __syncwarp();
+    } else {
+      float dpf[3] = {0.f, 0.f, 0.f};
+      if (active) {
+        for (int m = 0; m < H; ++m) c[m * T] = 0.f;
+        float dh[H], g[H];
+        const float dov = P.dout[0][p];
+#pragma unroll
+        for (int j = 0; j < H; ++j) dh[j] = dov * sw[CW_OUT + j];
+#pragma unroll 1
+        for (int l = 4; l >= 0; --l) {
+          const uint32_t mask = P.masks[(size_t)l * P.P + p];
+#pragma unroll
+          for (int j = 0; j < H; ++j) g[j] = ((mask >> j) & 1u) ? dh[j] : 0.f;
+          if (l == 0) denseT_col(c, sw, g, H);
+          else if (l == 3) { denseT_col(c, sw + CW_L3, g, H); denseT_reg(dh, sw + CW_L3 + H * H, g); }
+          else denseT_reg(dh, sw + (l == 4 ? CW_L4 : l * H * H), g);
+        }
+      }
+      __syncwarp();
+      float gi[3];
+      trilerp_coop_bwd(P.ga, ca, active, ccol, tbase, P.need_dp != 0, gi);
+      if (active && P.need_dp) {
+        const float m3[3] = {ca.mx, ca.my, ca.mz};
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const float gp = (float)((double)(gi[d] * m3[d]) * 2.0 / (P.bmax[d] - P.bmin[d]));
+          P.dp[(size_t)d * P.P + p] += gp + dpf[d];
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // ------------------------------------------------------------- composite ---
 struct CompParams {
   int R, S;
@@ -882,7 +990,7 @@ extern "C" int xrd_nice_step(const XrdRays* rays, const XrdNiceGrid grids[3],
     XRD_LAUNCH_CHECK();
   }
   SampleParams sp;
-  sp.R = R; sp.ns = cfg->n_samples; sp.nsurf = cfg->n_surface;
+  sp.R = R; sp.ns = cfg->n_samples; sp.nsurf = cfg->n_surface; sp.no_depth = 0;
   sp.rays_o = rays->rays_o; sp.rays_d = rays->rays_d; sp.target_d = rays->target_d;
   for (int d = 0; d < 3; ++d) { sp.bmin[d] = cfg->bound_min[d]; sp.bmax[d] = cfg->bound_max[d]; }
   sp.maxd = cfg->max_depth_global ? cfg->max_depth_global : maxd; sp.z = z;
@@ -1002,6 +1110,106 @@ extern "C" int xrd_nice_step(const XrdRays* rays, const XrdNiceGrid grids[3],
   if (grads->d_rays_o || grads->d_rays_d) {
     k_rayreduce<<<(R + 3) / 4, 128, 0, stream>>>(R, S, P, z, reinterpret_cast<const float*>(ws + L.dp),
                                                  grads->d_rays_o, grads->d_rays_d);
+    XRD_LAUNCH_CHECK();
+  }
+  return XRD_OK;
+}
+
+extern "C" size_t xrd_nice_coarse_workspace_bytes(int n_rays, int n_samples, int with_grads) {
+  return ws_layout(n_rays, n_samples, with_grads).total;
+}
+
+// Stage 'coarse' (conv_onet.py:137-138,397-402; decoder_nice.py:389-393): 32 uniform samples up
+// to the bound exit, MLP_no_xyz on the coarse grid, occupancy compositing, mapping depth loss,
+// gradient w.r.t. the coarse grid (and the rays).
+extern "C" int xrd_nice_coarse_step(const XrdRays* rays, const XrdNiceGrid* grid,
+                                    const XrdNiceCoarseDecoder* dec, const XrdNiceCoarseCfg* cfg,
+                                    XrdNiceOut* out, float* d_grid, float* d_rays_o, float* d_rays_d,
+                                    int with_grads, void* workspace, size_t workspace_bytes,
+                                    void* stream_) {
+  if (!rays || !grid || !dec || !cfg || !out || !workspace) return XRD_E_NULL;
+  if (!rays->rays_o || !rays->rays_d || !grid->data || !cfg->t_uniform) return XRD_E_NULL;
+  if (!out->rgb || !out->depth || !out->uncertainty) return XRD_E_NULL;
+  if (with_grads && (!rays->target_d || !out->losses)) return XRD_E_NULL;
+  const int R = rays->n_rays, S = cfg->n_samples;
+  if (R <= 0) return XRD_OK;
+  if (S < 2 || S > 64) return XRD_E_SHAPE;
+  const WsLayout L = ws_layout(R, S, with_grads);
+  if (workspace_bytes < L.total) return XRD_E_WORKSPACE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  char* ws = reinterpret_cast<char*>(workspace);
+  const int P = R * S, Pp = (int)align_up((size_t)P, 64);
+  double* z = out->z_vals ? out->z_vals : reinterpret_cast<double*>(ws + L.z);
+  float* occ = reinterpret_cast<float*>(ws + L.occ_mid);
+
+  SampleParams sp;
+  sp.R = R; sp.ns = S; sp.nsurf = 0; sp.no_depth = 1;
+  sp.rays_o = rays->rays_o; sp.rays_d = rays->rays_d; sp.target_d = nullptr;
+  for (int d = 0; d < 3; ++d) { sp.bmin[d] = cfg->bound_min[d]; sp.bmax[d] = cfg->bound_max[d]; }
+  sp.maxd = nullptr; sp.z = z; sp.t_uniform = cfg->t_uniform; sp.t_surface = nullptr;
+  k_sample<<<(R + 3) / 4, 128, 0, stream>>>(sp);
+  XRD_LAUNCH_CHECK();
+
+  DecParams D;
+  D.P = P; D.S = S; D.z = z; D.rays_o = rays->rays_o; D.rays_d = rays->rays_d;
+  for (int k = 0; k < 3; ++k) { D.bmin[k] = cfg->coarse_bound_min[k]; D.bmax[k] = cfg->coarse_bound_max[k]; }
+  D.ga.data = grid->data; D.ga.nx = grid->nx; D.ga.ny = grid->ny; D.ga.nz = grid->nz;
+  D.ga.grad = with_grads ? d_grid : nullptr;
+  D.gb.data = nullptr; D.gb.grad = nullptr; D.gb.nx = D.gb.ny = D.gb.nz = 1;
+  for (int k = 0; k < 4; ++k) { D.out[k] = nullptr; D.dout[k] = nullptr; }
+  D.out[0] = occ;
+  D.masks = with_grads ? reinterpret_cast<uint32_t*>(ws + L.masks) : nullptr;
+  D.acts = nullptr; D.Pp = Pp;
+  D.dp = with_grads ? reinterpret_cast<float*>(ws + L.dp) : nullptr;
+  D.need_dp = with_grads && (d_rays_o || d_rays_d);
+  D.zf = nullptr; D.ext_c = nullptr; D.ext_dc = nullptr; D.embed_scale = 1.0f;
+  D.dec = XrdNiceDecoder{};
+  CoarseW W;
+  for (int l = 0; l < 5; ++l) { W.pts_w[l] = dec->pts_w[l]; W.pts_b[l] = dec->pts_b[l]; }
+  W.out_w = dec->out_w; W.out_b = dec->out_b;
+  const size_t smem = sizeof(float) * ((size_t)CW_TOTAL + (size_t)H * T);
+  const int n_tiles = (P + T - 1) / T;
+  const int sms = num_sms();
+  const int gridx = n_tiles < sms ? n_tiles : sms;
+  XRD_CUDA_TRY(cudaFuncSetAttribute(k_coarse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    KernelTimer kt(stream);
+    k_coarse<false><<<gridx, T, smem, stream>>>(D, W);
+  }
+  XRD_LAUNCH_CHECK();
+
+  CompParams C;
+  C.R = R; C.S = S; C.z = z; C.rays_o = rays->rays_o; C.rays_d = rays->rays_d;
+  C.target_s = rays->target_s; C.target_d = rays->target_d;
+  for (int d = 0; d < 3; ++d) { C.bmin[d] = cfg->bound_min[d]; C.bmax[d] = cfg->bound_max[d]; }
+  C.occ_a = occ; C.occ_b = nullptr;
+  for (int c = 0; c < 3; ++c) C.rgb[c] = nullptr;
+  C.o_rgb = out->rgb; C.o_depth = out->depth; C.o_var = out->uncertainty; C.o_raw = out->raw;
+  C.gd = nullptr; C.gc = nullptr; C.d_occ = nullptr; C.d_rgb[0] = C.d_rgb[1] = C.d_rgb[2] = nullptr;
+  k_composite<false><<<(R + 3) / 4, 128, 0, stream>>>(C);
+  XRD_LAUNCH_CHECK();
+  if (!with_grads) return XRD_OK;
+
+  LossParams LP;
+  LP.R = R; LP.is_mapping = 1; LP.with_color = 0; LP.handle_dynamic = 0; LP.use_color_in_tracking = 0;
+  LP.w_color = 0.f; LP.target_s = rays->target_s; LP.target_d = rays->target_d;
+  LP.rgb = out->rgb; LP.depth = out->depth; LP.var = out->uncertainty;
+  LP.gd = reinterpret_cast<float*>(ws + L.gd); LP.gc = reinterpret_cast<float*>(ws + L.gc);
+  LP.tmp = reinterpret_cast<double*>(ws + L.tmp); LP.losses = out->losses;
+  k_loss<<<1, 1024, 0, stream>>>(LP);
+  XRD_LAUNCH_CHECK();
+  C.gd = LP.gd; C.gc = LP.gc;
+  C.d_occ = reinterpret_cast<float*>(ws + L.d_occ);
+  k_composite<true><<<(R + 3) / 4, 128, 0, stream>>>(C);
+  XRD_LAUNCH_CHECK();
+  XRD_CUDA_TRY(cudaMemsetAsync(ws + L.dp, 0, 3 * (size_t)P * 4, stream));
+  D.dout[0] = C.d_occ;
+  XRD_CUDA_TRY(cudaFuncSetAttribute(k_coarse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_coarse<true><<<gridx, T, smem, stream>>>(D, W);
+  XRD_LAUNCH_CHECK();
+  if (d_rays_o || d_rays_d) {
+    k_rayreduce<<<(R + 3) / 4, 128, 0, stream>>>(R, S, P, z, reinterpret_cast<const float*>(ws + L.dp),
+                                                 d_rays_o, d_rays_d);
     XRD_LAUNCH_CHECK();
   }
   return XRD_OK;

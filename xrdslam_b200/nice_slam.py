@@ -33,11 +33,11 @@ def _nice_optimizers():
 
 @dataclass
 class NiceSLAMConfig(AlgorithmConfig):
-    """nice_slam.py:14-47 + the nice-slam entry of input_config.py:45-157 (coarse level off:
-    the reference model config says "TODO: support True")."""
+    """nice_slam.py:14-47 + the nice-slam entry of input_config.py:45-157 (coarse=True there:
+    a coarse mapper runs after every mapping call, nice_slam.py:102-109)."""
     _target: Type = field(default_factory=lambda: NiceSLAM)
     model: ConvOnetConfig = field(default_factory=ConvOnetConfig)
-    coarse: bool = False
+    coarse: bool = True
     tracking_n_iters: int = 10
     mapping_n_iters: int = 60
     mapping_first_n_iters: int = 1500
@@ -89,6 +89,9 @@ class NiceSLAM(Algorithm):
                 frames = self.select_optimize_frames(
                     cur_frame, self.config.keyframe_selection_method)
             self.optimize_update(n_iters, frames, is_mapping=True, coarse=False)
+        if self.config.coarse:  # coarse mapper (nice_slam.py:102-109)
+            frames = self.select_optimize_frames(cur_frame, 'random')
+            self.optimize_update(n_iters, frames, is_mapping=True, coarse=True)
         if not self.is_initialized():
             self.set_initialized()
 

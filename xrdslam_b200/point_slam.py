@@ -16,7 +16,7 @@ import torch
 import torch.nn.functional as F
 
 from .algorithm import Algorithm, AlgorithmConfig
-from .common import get_samples
+from .common import get_samples, get_samples_with_pixel_grad
 from .conv_onet_pointslam import ConvOnet2Config
 from .keyframe_selection import frustum_mask
 from .optimizers import AdamOptimizerConfig
@@ -58,7 +58,7 @@ class PointSLAMConfig(AlgorithmConfig):
     tracking_Wedge: int = 100
     tracking_Hedge: int = 100
     mapping_geo_iter_ratio: float = 0.4
-    mapping_pixels_based_on_color_grad: int = 0
+    mapping_pixels_based_on_color_grad: int = 1000
     mapping_frustum_feature_selection: bool = True
     mapping_frustum_edge: int = -4
     mapping_BA: bool = False
@@ -135,7 +135,13 @@ class PointSLAM(Algorithm):
         npc.add_neural_points(ro.detach(), rd.detach(), d, c,
                               dynamic_radius=r_add[j, i] if r_add is not None else None)
         if cfg.mapping_pixels_based_on_color_grad > 0:
-            raise NotImplementedError('get_samples_with_pixel_grad (colour-gradient pixels)')
+            # point_slam.py:124-142: a second insertion pass over the pixels with the largest
+            # colour gradient, searched with the (smaller) per-pixel add radius / radius_min
+            ro_g, rd_g, d_g, c_g, i_g, j_g = get_samples_with_pixel_grad(
+                self.camera, cfg.mapping_pixels_based_on_color_grad, c2w, cur_frame.depth,
+                cur_frame.rgb, device=self.device, depth_filter=True, return_index=True)
+            npc.add_neural_points(ro_g.detach(), rd_g.detach(), d_g, c_g, is_pts_grad=True,
+                                  dynamic_radius=r_add[j_g, i_g] if r_add is not None else None)
         if cfg.mapping_frustum_feature_selection and npc.pts_num() > 0:
             m = frustum_mask(self.camera, c2w.detach(), npc.cloud_pos(), cur_frame.depth,
                              edge=cfg.mapping_frustum_edge)
@@ -158,14 +164,25 @@ class PointSLAM(Algorithm):
             n = int(np.maximum(cfg.mapping_sample // len(optimize_frames), cfg.min_sample_pixels))
             Hedge = Wedge = 0
         if not is_mapping and cfg.tracking_sample_with_color_grad:
-            raise NotImplementedError('tracking_sample_with_color_grad')
-        rays_o, rays_d, gt_depth, gt_color, i, j = self._sample_window(
-            optimize_frames, n, Hedge, Wedge, return_index=True)
+            # point_slam.py:192-205: tracking pixels by colour gradient (per frame, host draw)
+            parts = [get_samples_with_pixel_grad(self.camera, n, f.get_pose(), f.depth, f.rgb,
+                                                 device=self.device, Hedge=Hedge, Wedge=Wedge,
+                                                 depth_filter=True, return_index=True)
+                     for f in optimize_frames]
+            rays_o, rays_d = torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
+            gt_depth = torch.cat([p[2] for p in parts]).reshape(-1, 1)
+            gt_color = torch.cat([p[3] for p in parts])
+            i, j = torch.cat([p[4] for p in parts]), torch.cat([p[5] for p in parts])
+            fidx = torch.cat([torch.full((p[0].shape[0],), k, device=self.device)
+                              for k, p in enumerate(parts)])
+        else:
+            rays_o, rays_d, gt_depth, gt_color, i, j = self._sample_window(
+                optimize_frames, n, Hedge, Wedge, return_index=True)
+            fidx = torch.arange(len(optimize_frames), device=self.device).repeat_interleave(n)
         r_query = None
         if cfg.use_dynamic_radius:
             maps = torch.stack([self.dynamic_r_query_allkeyframe[str(int(f.fid))]
                                 for f in optimize_frames])  # [F,H,W]
-            fidx = torch.arange(len(optimize_frames), device=self.device).repeat_interleave(n)
             r_query = maps[fidx, j, i]
         with torch.no_grad():
             d = gt_depth.squeeze(-1)
