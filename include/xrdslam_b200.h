@@ -274,6 +274,16 @@ int xrd_coslam_smoothness_dev(const XrdHashGrid* grid, int sample_points,
                           float grad_scale, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* Point queries of the mesher path (slam/models/joint_encoding.py:408-481 query_fn /
+ * color_func / query_sdf / query_color_sdf; slam/common/mesher.py:138-263 calls them on
+ * marching-cubes lattice points): pts DEVICE [P,3], world coordinates (normalised = 0: the
+ * kernel applies (p - bbox_min) / (bbox_max - bbox_min) in float64 like the reference) or
+ * already normalised (1).  Any of raw [P,4] (rgb logits ++ sdf), geo [P,15], feat [P,32]
+ * (hash features, query_sdf(embed=True)) may be NULL. */
+int xrd_coslam_query(const XrdHashGrid* grid, const XrdCoslamMlp* mlp, const float* pts,
+                     int n_points, int normalised, float* raw, float* geo, float* feat,
+                     void* stream);
+
 /* Hash-grid encoding only (used by the mesher path query_sdf(embed=True) and
  * by the index-parity tests): x DEVICE [P,3] normalised coords ->
  * feat [P,2*n_levels]; idx (optional) [P,n_levels,8] uint32 entry indices. */

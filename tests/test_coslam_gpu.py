@@ -248,3 +248,35 @@ def test_cuda_matches_reference_golden(cuda_dev):
     gt = model.embed_fn.params.grad
     assert abs(float(gt.double().norm()) - float(g['d_table_norm'])) <= TOL_GRAD * float(g['d_table_norm'])
     assert rel_err(gt[:4096], torch.from_numpy(g['d_table_head'])) < TOL_GRAD
+
+
+def test_mesher_queries_match_oracle(cuda_dev):
+    """query_fn / color_func / query_sdf / query_color_sdf / run_network (mesher path, SURVEY f4;
+    joint_encoding.py:408-507) against the oracle's query_color_sdf: exact fp32 decoders."""
+    ora, model = coslam_pair(cuda_dev)
+    g = torch.Generator().manual_seed(12)
+    P = 3001
+    world = torch.rand(P, 3, generator=g) * torch.tensor([7.0, 7.5, 5.5]) + torch.tensor([-3.5, -4.5, -2.5])
+    bb = torch.as_tensor(BOUND, dtype=torch.float64)
+    xn = ((world - bb[:, 0]) / (bb[:, 1] - bb[:, 0]))  # float64, like the reference
+    with torch.no_grad():
+        raw_o = ora.query_color_sdf(xn)
+    sdf = model.query_fn(world.to(cuda_dev))
+    col = model.color_func(world.to(cuda_dev))
+    assert sdf.shape == (P, 1) and col.shape == (P, 1, 3)
+    assert max_abs(sdf[:, 0], raw_o[:, 3]) < 2e-5
+    assert max_abs(col[:, 0], torch.sigmoid(raw_o[:, :3])) < 2e-5
+    raw = model.run_network(world[:1000].reshape(100, 10, 3).to(cuda_dev))
+    assert raw.shape == (100, 10, 4) and max_abs(raw.reshape(-1, 4), raw_o[:1000]) < 2e-5
+    # normalised-coordinate entry points
+    xn32 = xn.float()
+    with torch.no_grad():
+        raw_n = ora.query_color_sdf(xn32)
+    got = model.query_color_sdf(xn32.reshape(P, 1, 3).to(cuda_dev))
+    assert got.shape == (P, 1, 4) and max_abs(got[:, 0], raw_n) < 2e-5
+    s2, geo = model.query_sdf(xn32.reshape(P, 1, 3).to(cuda_dev), return_geo=True)
+    assert s2.shape == (P, 1) and geo.shape == (P, 1, 15)
+    assert max_abs(s2[:, 0], raw_n[:, 3]) < 2e-5
+    emb = model.query_sdf(xn32.reshape(P, 1, 3).to(cuda_dev), embed=True)
+    with torch.no_grad():
+        assert max_abs(emb[:, 0], ora.embed_fn(xn32)) < 1e-6

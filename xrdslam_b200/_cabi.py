@@ -276,6 +276,8 @@ SYMBOLS = {
         C.POINTER(XrdVoxOut), C.POINTER(XrdVoxGrads), vp, C.c_size_t, vp]),
     'xrd_pointslam_knn_query': (C.c_int, [C.POINTER(XrdPointIndex), vp, vp, C.c_int, C.c_int,
                                           vp, vp, vp, vp]),
+    'xrd_coslam_query': (C.c_int, [C.POINTER(XrdHashGrid), C.POINTER(XrdCoslamMlp), vp, C.c_int,
+                                   C.c_int, vp, vp, vp, vp]),
     'xrd_debug_gemm_mode': (C.c_int, [C.c_int]),
     'xrd_debug_gemm': (C.c_int, [C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, vp,
                                  C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp]),

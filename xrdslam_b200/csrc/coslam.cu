@@ -1750,6 +1750,85 @@ __global__ void __launch_bounds__(256) k_encode(GridDev g, const float* table, c
   }
 }
 
+// ------------------------------------------------------- point queries (mesher) ---
+// query_color_sdf / query_sdf at arbitrary points (joint_encoding.py:425-481): thread per point,
+// hash + OneBlob encoding into a shared-memory record, the two decoders in plain fp32 FMAs
+// (the mesher path is not hot; exact fp32 keeps it within 1e-6 of the oracle).
+struct QueryParams {
+  GridDev g;
+  const float* table;
+  const float *w_sdf0, *w_sdf1, *w_col0, *w_col1;
+  const float* pts;   // [P,3]
+  int P, normalised;  // normalised = 1: pts are already (p - min) / (max - min)
+  float* raw;         // [P,4] rgb logits ++ sdf, or NULL
+  float* geo;         // [P,15] or NULL
+  float* feat;        // [P,32] hash features (query_sdf(embed=True)) or NULL
+};
+
+__global__ void __launch_bounds__(128) k_query(const QueryParams Q) {
+  extern __shared__ __align__(16) float qrec[];  // 128 records
+  __shared__ Lv s_lv[kL];
+  load_levels(s_lv, Q.g);
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Q.P) return;
+  float* rec = qrec + threadIdx.x * REC;
+  float xn[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float v = Q.pts[(size_t)p * 3 + d];
+    xn[d] = Q.normalised ? v : normalise(v, Q.g.bmin[d], Q.g.bmax[d]);
+  }
+  Params P{};  // encode_point reads table / n_levels only
+  P.table = Q.table;
+  P.g.n_levels = Q.g.n_levels;
+  encode_point(P, s_lv, xn, rec);
+  if (Q.feat)
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) Q.feat[(size_t)p * 32 + j] = rec[R_FEAT + j];
+  if (!Q.raw && !Q.geo) return;
+  // h1 = relu(W0 [feat, blob]);  [sdf, geo] = W1 h1  (torch rows: 0 = sdf, 1..15 = geo)
+  float h1[32];
+#pragma unroll 1
+  for (int j = 0; j < 32; ++j) {
+    float a = 0.f;
+    const float* w = Q.w_sdf0 + j * 80;
+    for (int i = 0; i < 80; ++i) a = fmaf(__ldg(w + i), rec[R_FEAT + i], a);  // FEAT|BLOB contiguous
+    h1[j] = fmaxf(a, 0.f);
+  }
+  float so[16];
+#pragma unroll 1
+  for (int j = 0; j < 16; ++j) {
+    float a = 0.f;
+    const float* w = Q.w_sdf1 + j * 32;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a = fmaf(__ldg(w + i), h1[i], a);
+    so[j] = a;
+  }
+  if (Q.geo)
+    for (int j = 0; j < 15; ++j) Q.geo[(size_t)p * 15 + j] = so[1 + j];
+  if (!Q.raw) return;
+  // colour: c1 = relu(Wc0 [blob, geo]);  rgb logits = Wc1 c1
+  float c1[32];
+#pragma unroll 1
+  for (int j = 0; j < 32; ++j) {
+    float a = 0.f;
+    const float* w = Q.w_col0 + j * 63;
+    for (int i = 0; i < 48; ++i) a = fmaf(__ldg(w + i), rec[R_BLOB + i], a);
+    for (int i = 0; i < 15; ++i) a = fmaf(__ldg(w + 48 + i), so[1 + i], a);
+    c1[j] = fmaxf(a, 0.f);
+  }
+  float o3[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a = fmaf(__ldg(Q.w_col1 + k * 32 + i), c1[i], a);
+    o3[k] = a;
+  }
+  *reinterpret_cast<float4*>(Q.raw + (size_t)p * 4) = make_float4(o3[0], o3[1], o3[2], so[0]);
+}
+
 static int fill_grid(GridDev& g, const XrdHashGrid* h) {
   if (h->n_levels < 1 || h->n_levels > kL) return XRD_E_SHAPE;
   g.n_levels = h->n_levels;
@@ -1996,6 +2075,27 @@ extern "C" int xrd_coslam_smoothness_dev(const XrdHashGrid* grid, int sample_poi
                                          void* workspace, size_t workspace_bytes, void* stream_) {
   return smoothness_impl(grid, sample_points, voxel_size, margin, weight, smooth_rand, true, loss,
                          d_table, grad_scale, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int xrd_coslam_query(const XrdHashGrid* grid, const XrdCoslamMlp* mlp, const float* pts,
+                                int n_points, int normalised, float* raw, float* geo, float* feat,
+                                void* stream_) {
+  if (!grid || !grid->table || !pts) return XRD_E_NULL;
+  if ((raw || geo) && (!mlp || !mlp->w_sdf0 || !mlp->w_sdf1)) return XRD_E_NULL;
+  if (raw && (!mlp->w_col0 || !mlp->w_col1)) return XRD_E_NULL;
+  if (n_points <= 0) return XRD_OK;
+  QueryParams Q;
+  int st = fill_grid(Q.g, grid);
+  if (st != XRD_OK) return st;
+  Q.table = grid->table;
+  Q.w_sdf0 = mlp ? mlp->w_sdf0 : nullptr; Q.w_sdf1 = mlp ? mlp->w_sdf1 : nullptr;
+  Q.w_col0 = mlp ? mlp->w_col0 : nullptr; Q.w_col1 = mlp ? mlp->w_col1 : nullptr;
+  Q.pts = pts; Q.P = n_points; Q.normalised = normalised; Q.raw = raw; Q.geo = geo; Q.feat = feat;
+  const size_t smem = 128 * REC * sizeof(float);
+  XRD_CUDA_TRY(cudaFuncSetAttribute(k_query, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_query<<<(n_points + 127) / 128, 128, smem, (cudaStream_t)stream_>>>(Q);
+  XRD_LAUNCH_CHECK();
+  return XRD_OK;
 }
 
 extern "C" int xrd_hashgrid_encode(const XrdHashGrid* grid, const float* x, int n_points,

@@ -456,10 +456,58 @@ class JointEncoding(Model):
         return _SmoothFn.apply(self.embed_fn.params, self, rand6, weight)
 
     # ---- mesher-facing queries (joint_encoding.py:408-481) ----------------
-    def _query_raw(self, pts_norm):
-        """raw [P,4] at normalised coords through the fused forward kernel
-        (one sample per 'ray': o = p, d = 0)."""
-        raise NotImplementedError('mesher path is SURVEY section 8(f4)')
+    def _query(self, pts, normalised, want_raw=True, want_geo=False, want_feat=False):
+        """xrd_coslam_query on [..., 3] points -> dict of flat [P, k] tensors (inference)."""
+        table = self.embed_fn.params
+        dev = table.device
+        if dev.type != 'cuda':
+            raise RuntimeError('xrdslam_b200 has no CPU path: model must be on a CUDA device')
+        flat = pts.detach().reshape(-1, 3).to(device=dev, dtype=torch.float32).contiguous()
+        P = flat.shape[0]
+        f32 = dict(dtype=torch.float32, device=dev)
+        raw = torch.empty(P, 4, **f32) if want_raw else None
+        geo = torch.empty(P, 15, **f32) if want_geo else None
+        feat = torch.empty(P, 32, **f32) if want_feat else None
+        grid = self._grid_struct(table.detach())
+        mlp = XrdCoslamMlp(*(ptr(w.detach()) for w in self._weights()))
+        with torch.cuda.device(dev):
+            st = _cabi.lib().xrd_coslam_query(C.byref(grid), C.byref(mlp), ptr(flat), P,
+                                              int(normalised), ptr(raw), ptr(geo), ptr(feat),
+                                              torch.cuda.current_stream(dev).cuda_stream)
+        check('xrd_coslam_query', st)
+        return dict(raw=raw, geo=geo, feat=feat)
+
+    def query_fn(self, pi):
+        """:409-416: SDF at world points [N,3] -> [N,1]."""
+        return self._query(pi, False)['raw'][:, 3:4]
+
+    def color_func(self, pi):
+        """:419-425: colour at world points [N,3] -> [N,1,3]."""
+        return torch.sigmoid(self._query(pi, False)['raw'][:, None, :3])
+
+    def query_sdf(self, query_points, return_geo=False, embed=False):
+        """:427-456, points already normalised to the unit cube."""
+        shp = list(query_points.shape[:-1])
+        if embed:
+            return self._query(query_points, True, False, False, True)['feat'].reshape(shp + [32])
+        o = self._query(query_points, True, True, return_geo)
+        sdf = o['raw'][:, 3].reshape(shp)
+        if not return_geo:
+            return sdf
+        return sdf, o['geo'].reshape(shp + [15])
+
+    def query_color_sdf(self, query_points):
+        """:463-481 -> raw [..., 4] (rgb logits ++ sdf) at normalised points."""
+        return self._query(query_points, True)['raw'].reshape(list(query_points.shape[:-1]) + [4])
+
+    def query_color(self, query_points):
+        """:458-461."""
+        return torch.sigmoid(self.query_color_sdf(query_points)[..., :3])
+
+    def run_network(self, inputs):
+        """:483-507: raw [..., 4] at WORLD points (normalised inside, float64 like the
+        reference's bounding-box arithmetic)."""
+        return self._query(inputs, False)['raw'].reshape(list(inputs.shape[:-1]) + [4])
 
 
 class _SmoothFn(torch.autograd.Function):
