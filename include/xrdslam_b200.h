@@ -377,6 +377,16 @@ int xrd_nice_step(const XrdRays* rays, const XrdNiceGrid grids[3],
                   XrdNiceOut* out, XrdNiceGrads* grads, void* workspace,
                   size_t workspace_bytes, void* stream);
 
+/* Mesher queries (slam/models/conv_onet.py:213-240 query_fn = NICE.forward(stage 'fine'),
+ * color_func = stage 'color'; slam/common/mesher.py:138-167): raw [P,4] = (rgb or 0, occupancy
+ * logit middle [+ fine]) at free points DEVICE [P,3] fp32; no out-of-bound masking (the mesher
+ * applies its own). */
+size_t xrd_nice_query_workspace_bytes(int n_points);
+int xrd_nice_query(const float* points, int n_points, const XrdNiceGrid grids[3],
+                   const XrdNiceDecoder decoders[3], const double bound_min[3],
+                   const double bound_max[3], int stage, float* raw, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
 /* Stage 'coarse' (slam/models/conv_onet.py:137-138 target_d = None, :397-402 near = 0.01 /
  * far = bound exit, 32 uniform samples; slam/model_components/decoder_nice.py:237-320
  * MLP_no_xyz, :389-393): its own decoder and grid; the grid is sampled with the scene bound
@@ -561,7 +571,15 @@ typedef struct {
 } XrdPointIndex;
 
 /* bucket of cell (ix,iy,iz): ((ix*73856093) ^ (iy*19349663) ^ (iz*83492791)) & (table-1),
- * uint32 arithmetic, ix = floor(x / cell). */
+ * uint32 arithmetic, ix = floor(x * (1/cell)).
+ * xrd_pointslam_knn_build fills cell_start / cell_end [table_size] and sorted_ids [n_points]
+ * (ids ascending inside a bucket) for DEVICE positions [n_points,3] -- what faiss's
+ * index.add() does in the reference (slam/model_components/neural_point_cloud.py:48-52,
+ * 173-176), on the device with no host round trip. */
+size_t xrd_pointslam_knn_build_workspace_bytes(int table_size);
+int xrd_pointslam_knn_build(const float* pos, int n_points, float cell, int table_size,
+                            int32_t* cell_start, int32_t* cell_end, int32_t* sorted_ids,
+                            void* workspace, size_t workspace_bytes, void* stream);
 int xrd_pointslam_knn_query(const XrdPointIndex* index, const float* queries, const float* radius,
                             int radius_stride, int n_queries, float* D, int32_t* I,
                             int32_t* neighbor_num, void* stream);

@@ -222,3 +222,20 @@ def test_nice_coarse_stage_parity(cuda_dev):
         o2 = model(dict(rays_o=ro.detach(), rays_d=rd.detach(), target_s=None,
                         target_d=td.to(cuda_dev), stage='coarse'))
     assert torch.equal(o2['depth'], out['depth'])
+
+
+@pytest.mark.gpu
+def test_nice_mesher_queries_match_oracle(cuda_dev):
+    """ConvOnet.query_fn / color_func (mesher path, conv_onet.py:213-240) == the oracle's
+    NICE.forward restatement at free points, inside and outside the bound."""
+    ora, model = nice_pair(cuda_dev)
+    g = torch.Generator().manual_seed(4)
+    pts = (torch.rand(2500, 3, generator=g) - 0.5) * 4.6  # some outside [-2, 2]^3 (border clamp)
+    with torch.no_grad():
+        fine_o = ora.decode(pts, 'fine')
+        col_o = ora.decode(pts, 'color')
+    fine = model.query_fn(pts.to(cuda_dev))
+    col = model.color_func(pts.to(cuda_dev))
+    assert fine.shape == (2500, 4) and col.shape == (2500, 4)
+    assert max_abs(fine, fine_o) < 2e-4
+    assert max_abs(col, col_o) < 2e-4

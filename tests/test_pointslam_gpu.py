@@ -238,3 +238,22 @@ def test_pointslam_color_forward_only_matches_fused(cuda_dev):
                    rand_feat_color=torch.from_numpy(g['rand_feat_color']).to(cuda_dev))
         o2 = model(inp)
     assert torch.equal(o2['rgb'], out['rgb']) and torch.equal(o2['depth'], out['depth'])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('N', [1, 777, 200000])
+def test_knn_index_device_build_equals_stable_argsort(cuda_dev, N):
+    """xrd_pointslam_knn_build (histogram / scan / scatter / per-bucket sort on the device) ==
+    the torch construction it replaces (stable argsort of the bucket keys), bit for bit."""
+    from xrdslam_b200.neural_point_cloud import NeuralPointCloud
+    npc = NeuralPointCloud(device=cuda_dev)
+    g = torch.Generator().manual_seed(N)
+    pos = (torch.rand(N, 3, generator=g) - 0.5) * torch.tensor([6.0, 6.0, 3.0])
+    pos[: N // 3] = pos[: N // 3].round(decimals=1)  # crowded cells
+    npc.set_cloud(pos, torch.zeros(N, 32))
+    npc.rebuild_index()
+    ref = npc.rebuild_index_torch()
+    torch.cuda.synchronize()
+    for k in ('cell_start', 'cell_end'):
+        assert torch.equal(npc._index[k], ref[k]), k
+    assert torch.equal(npc._index['sorted_ids'][:N], ref['sorted_ids'])

@@ -287,6 +287,13 @@ SYMBOLS = {
         C.POINTER(XrdNiceDecoder), C.POINTER(XrdPointColorDecoder), C.POINTER(XrdPointCfg),
         C.POINTER(XrdPointOut), C.POINTER(XrdPointGrads), vp, C.c_size_t, vp]),
     'xrd_nice_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    'xrd_pointslam_knn_build_workspace_bytes': (C.c_size_t, [C.c_int]),
+    'xrd_pointslam_knn_build': (C.c_int, [vp, C.c_int, C.c_float, C.c_int, vp, vp, vp, vp, C.c_size_t,
+                                          vp]),
+    'xrd_nice_query_workspace_bytes': (C.c_size_t, [C.c_int]),
+    'xrd_nice_query': (C.c_int, [vp, C.c_int, C.POINTER(XrdNiceGrid), C.POINTER(XrdNiceDecoder),
+                                 C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, vp, vp,
+                                 C.c_size_t, vp]),
     'xrd_nice_coarse_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     'xrd_nice_coarse_step': (C.c_int, [
         C.POINTER(XrdRays), C.POINTER(XrdNiceGrid), C.POINTER(XrdNiceCoarseDecoder),

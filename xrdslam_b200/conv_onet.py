@@ -462,6 +462,46 @@ class ConvOnet(Model):
         o.pop('losses')
         return o
 
+    # ---- mesher-facing queries (conv_onet.py:213-240) -----------------------------------
+    def _query(self, pi, stage):
+        dev = self.grids['grid_middle'].device
+        if dev.type != 'cuda':
+            raise RuntimeError('xrdslam_b200 has no CPU path: model must be on a CUDA device')
+        lib = _cabi.lib()
+        pts = pi.detach().reshape(-1, 3).to(device=dev, dtype=torch.float32).contiguous()
+        P = pts.shape[0]
+        keys = ('grid_middle', 'grid_fine', 'grid_color')
+        grids = (XrdNiceGrid * 3)()
+        for i, k in enumerate(keys):
+            g = self.grids[k].detach()
+            grids[i] = XrdNiceGrid(ptr(g), g.shape[2], g.shape[1], g.shape[0])
+        decs = (XrdNiceDecoder * 3)()
+        keep = []
+        for i, m in enumerate((self.decoder.middle_decoder, self.decoder.fine_decoder,
+                               self.decoder.color_decoder)):
+            t = [x.detach() for x in m.tensors()]
+            keep.append(t)
+            decs[i] = _dec_struct(t, m.c_dim, 4 if m.color else 1)
+        bmin = (C.c_double * 3)(*[float(self.bounding_box[d, 0]) for d in range(3)])
+        bmax = (C.c_double * 3)(*[float(self.bounding_box[d, 1]) for d in range(3)])
+        raw = torch.empty(P, 4, dtype=torch.float32, device=dev)
+        nb = lib.xrd_nice_query_workspace_bytes(P)
+        ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            st = lib.xrd_nice_query(ptr(pts), P, grids, decs, bmin, bmax, STAGES[stage], ptr(raw),
+                                    ptr(ws), nb, torch.cuda.current_stream(dev).cuda_stream)
+        check('xrd_nice_query', st)
+        return raw
+
+    def query_fn(self, pi):
+        """conv_onet.py:213-230: NICE.forward(stage='fine') at points [N,3] -> raw [N,4]
+        (zeros, occupancy logit middle + fine)."""
+        return self._query(pi, 'fine')
+
+    def color_func(self, pi):
+        """conv_onet.py:232-239: stage 'color' -> raw [N,4] (rgb, occupancy logit)."""
+        return self._query(pi, 'color')
+
     def get_loss_dict(self, outputs, inputs, is_mapping, stage=None) -> Dict[str, torch.Tensor]:
         """conv_onet.py:145-185: terms come from the fused pass (forward needs
         ``input['is_mapping']`` -- the Algorithm sets it -- to pick the loss form)."""

@@ -1115,6 +1115,69 @@ extern "C" int xrd_nice_step(const XrdRays* rays, const XrdNiceGrid grids[3],
   return XRD_OK;
 }
 
+// ---- mesher queries (conv_onet.py:213-240 query_fn / color_func): NICE.forward at free points
+static __global__ void k_query_pack(int P, const float* occ_mid, const float* occ_fine,
+                                    const float* rgb, float* raw) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  float4 o = make_float4(0.f, 0.f, 0.f, occ_mid[p] + (occ_fine ? occ_fine[p] : 0.f));
+  if (rgb) { o.x = rgb[p]; o.y = rgb[P + p]; o.z = rgb[2 * (size_t)P + p]; }
+  *reinterpret_cast<float4*>(raw + (size_t)p * 4) = o;
+}
+
+extern "C" size_t xrd_nice_query_workspace_bytes(int n_points) {
+  const size_t P = (size_t)n_points;
+  return align_up(P * 8, 256) + align_up(P * 12, 256) + 2 * align_up(P * 4, 256) + align_up(P * 12, 256);
+}
+
+extern "C" int xrd_nice_query(const float* points, int n_points, const XrdNiceGrid grids[3],
+                              const XrdNiceDecoder decoders[3], const double bound_min[3],
+                              const double bound_max[3], int stage, float* raw, void* workspace,
+                              size_t workspace_bytes, void* stream_) {
+  if (!points || !grids || !decoders || !bound_min || !bound_max || !raw || !workspace) return XRD_E_NULL;
+  if (n_points <= 0) return XRD_OK;
+  if (stage < XRD_NICE_MIDDLE || stage > XRD_NICE_COLOR) return XRD_E_SHAPE;
+  if (workspace_bytes < xrd_nice_query_workspace_bytes(n_points)) return XRD_E_WORKSPACE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int P = n_points;
+  char* ws = reinterpret_cast<char*>(workspace);
+  double* z = reinterpret_cast<double*>(ws); ws += align_up((size_t)P * 8, 256);
+  float* zero_d = reinterpret_cast<float*>(ws); ws += align_up((size_t)P * 12, 256);
+  float* occ_mid = reinterpret_cast<float*>(ws); ws += align_up((size_t)P * 4, 256);
+  float* occ_fine = reinterpret_cast<float*>(ws); ws += align_up((size_t)P * 4, 256);
+  float* rgb = reinterpret_cast<float*>(ws);
+  // point = rays_o + rays_d * z with rays_o = the query point, rays_d = 0, z = 0 (exact)
+  XRD_CUDA_TRY(cudaMemsetAsync(z, 0, (size_t)P * 8, stream));
+  XRD_CUDA_TRY(cudaMemsetAsync(zero_d, 0, (size_t)P * 12, stream));
+  const int sms = num_sms();
+  const int n_tiles = (P + T - 1) / T;
+  const int gridx = n_tiles < sms ? n_tiles : sms;
+  for (int d = 0; d <= stage; ++d) {
+    DecParams D;
+    D.P = P; D.S = 1; D.z = z; D.rays_o = points; D.rays_d = zero_d;
+    for (int k = 0; k < 3; ++k) { D.bmin[k] = bound_min[k]; D.bmax[k] = bound_max[k]; }
+    D.ga.data = grids[d].data; D.ga.nx = grids[d].nx; D.ga.ny = grids[d].ny; D.ga.nz = grids[d].nz;
+    D.ga.grad = nullptr;
+    D.gb.data = nullptr; D.gb.grad = nullptr; D.gb.nx = D.gb.ny = D.gb.nz = 1;
+    if (d == 1) { D.gb.data = grids[0].data; D.gb.nx = grids[0].nx; D.gb.ny = grids[0].ny; D.gb.nz = grids[0].nz; }
+    D.dec = decoders[d];
+    for (int k = 0; k < 4; ++k) { D.out[k] = nullptr; D.dout[k] = nullptr; }
+    if (d == 0) D.out[0] = occ_mid;
+    if (d == 1) D.out[0] = occ_fine;
+    if (d == 2) { D.out[0] = rgb; D.out[1] = rgb + P; D.out[2] = rgb + 2 * (size_t)P; }
+    D.masks = nullptr; D.acts = nullptr; D.Pp = (int)align_up((size_t)P, 64); D.dp = nullptr; D.need_dp = 0;
+    D.zf = nullptr; D.ext_c = nullptr; D.ext_dc = nullptr; D.embed_scale = 1.0f;
+    const size_t smem = sizeof(float) * ((size_t)woff(decoders[d].c_dim).total + (size_t)(E + CMAX) * T);
+    XRD_CUDA_TRY(cudaFuncSetAttribute(k_decoder_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_decoder_fwd<<<gridx, T, smem, stream>>>(D);
+    XRD_LAUNCH_CHECK();
+  }
+  k_query_pack<<<(P + 255) / 256, 256, 0, stream>>>(P, occ_mid, stage >= XRD_NICE_FINE ? occ_fine : nullptr,
+                                                    stage == XRD_NICE_COLOR ? rgb : nullptr, raw);
+  XRD_LAUNCH_CHECK();
+  return XRD_OK;
+}
+
 extern "C" size_t xrd_nice_coarse_workspace_bytes(int n_rays, int n_samples, int with_grads) {
   return ws_layout(n_rays, n_samples, with_grads).total;
 }

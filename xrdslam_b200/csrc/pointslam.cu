@@ -440,6 +440,121 @@ __global__ void __launch_bounds__(128) k_rayreduce_f(int R, int S, int P, const 
 using namespace xrd;
 using namespace xrd::point;
 
+// ---- index build (SURVEY f2 / VERDICT r01 row 9): counting sort of the point ids by bucket,
+// all on the device: histogram -> exclusive scan -> scatter -> per-bucket id sort (the kNN
+// result does not depend on the order inside a bucket; sorting makes the index deterministic
+// and equal to a stable argsort of the bucket keys).
+namespace xrd {
+namespace point {
+static __global__ void k_ix_hist(const float* pos, int n, float inv_cell, int table, int* count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* x = pos + (size_t)i * 3;
+  const uint32_t b = bucket_of((int)floorf(x[0] * inv_cell), (int)floorf(x[1] * inv_cell),
+                               (int)floorf(x[2] * inv_cell), table);
+  atomicAdd(count + b, 1);
+}
+// single-block exclusive scan over `table` counters (table <= 2^24, power of two): 4096 per
+// round (int4 per thread), warp scans + one carry
+static __global__ void __launch_bounds__(1024) k_ix_scan(const int* count, int table, int* start, int* end,
+                                                          int* cursor) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < table; base += 4096) {
+    const int i = base + threadIdx.x * 4;
+    int c[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c[k] = (i + k < table) ? count[i + k] : 0;
+    const int mine = c[0] + c[1] + c[2] + c[3];
+    int inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      int t = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += v;
+      }
+      warp_tot[lane] = t;  // inclusive over warps
+    }
+    __syncthreads();
+    int before = carry + (warp ? warp_tot[warp - 1] : 0) + inc - mine;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i + k < table) { start[i + k] = before; end[i + k] = before + c[k]; cursor[i + k] = before; }
+      before += c[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) carry += warp_tot[31];
+    __syncthreads();
+  }
+}
+static __global__ void k_ix_fill(const float* pos, int n, float inv_cell, int table, int* cursor, int* ids) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* x = pos + (size_t)i * 3;
+  const uint32_t b = bucket_of((int)floorf(x[0] * inv_cell), (int)floorf(x[1] * inv_cell),
+                               (int)floorf(x[2] * inv_cell), table);
+  ids[atomicAdd(cursor + b, 1)] = i;
+}
+static __global__ void k_ix_sort(int table, const int* start, const int* end, int* ids) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= table) return;
+  const int s = start[b], e = end[b];
+  for (int i = s + 1; i < e; ++i) {  // insertion sort: buckets hold a handful of points
+    const int v = ids[i];
+    int j = i - 1;
+    while (j >= s && ids[j] > v) { ids[j + 1] = ids[j]; --j; }
+    ids[j + 1] = v;
+  }
+}
+}  // namespace point
+}  // namespace xrd
+
+extern "C" size_t xrd_pointslam_knn_build_workspace_bytes(int table_size) {
+  return 2 * align_up((size_t)table_size * sizeof(int), 256);
+}
+
+extern "C" int xrd_pointslam_knn_build(const float* pos, int n_points, float cell, int table_size,
+                                       int32_t* cell_start, int32_t* cell_end, int32_t* sorted_ids,
+                                       void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!cell_start || !cell_end || !workspace) return XRD_E_NULL;
+  if (n_points > 0 && (!pos || !sorted_ids)) return XRD_E_NULL;
+  if (table_size < 1 || table_size > (1 << 24) || (table_size & (table_size - 1)) || !(cell > 0.f))
+    return XRD_E_SHAPE;
+  if (workspace_bytes < xrd_pointslam_knn_build_workspace_bytes(table_size)) return XRD_E_WORKSPACE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int* count = reinterpret_cast<int*>(workspace);
+  int* cursor = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) +
+                                       align_up((size_t)table_size * sizeof(int), 256));
+  const float inv = (1.0f / cell);
+  XRD_CUDA_TRY(cudaMemsetAsync(count, 0, (size_t)table_size * sizeof(int), stream));
+  if (n_points > 0) {
+    point::k_ix_hist<<<(n_points + 255) / 256, 256, 0, stream>>>(pos, n_points, inv, table_size, count);
+    XRD_LAUNCH_CHECK();
+  }
+  point::k_ix_scan<<<1, 1024, 0, stream>>>(count, table_size, cell_start, cell_end, cursor);
+  XRD_LAUNCH_CHECK();
+  if (n_points > 0) {
+    point::k_ix_fill<<<(n_points + 255) / 256, 256, 0, stream>>>(pos, n_points, inv, table_size, cursor,
+                                                                 sorted_ids);
+    XRD_LAUNCH_CHECK();
+    point::k_ix_sort<<<(table_size + 255) / 256, 256, 0, stream>>>(table_size, cell_start, cell_end,
+                                                                   sorted_ids);
+    XRD_LAUNCH_CHECK();
+  }
+  return XRD_OK;
+}
+
 extern "C" int xrd_pointslam_knn_query(const XrdPointIndex* index, const float* queries,
                                        const float* radius, int radius_stride, int n_queries,
                                        float* D, int32_t* I, int32_t* neighbor_num, void* stream) {

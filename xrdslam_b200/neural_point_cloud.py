@@ -60,7 +60,26 @@ class NeuralPointCloud(nn.Module):
 
     # ---- index ----------------------------------------------------------------
     def rebuild_index(self):
-        """Bucket = hash(floor(x / cell)) as in csrc/pointslam.cu:bucket_of."""
+        """Bucket = hash(floor(x / cell)) as in csrc/pointslam.cu:bucket_of; built on the device
+        by xrd_pointslam_knn_build (histogram, scan, scatter, per-bucket id sort)."""
+        N = self._pos.shape[0]
+        dev = self.device
+        lib = _cabi.lib()
+        i32 = dict(dtype=torch.int32, device=dev)
+        start, end = torch.empty(self.table_size, **i32), torch.empty(self.table_size, **i32)
+        ids = torch.empty(max(N, 1), **i32)
+        nb = lib.xrd_pointslam_knn_build_workspace_bytes(self.table_size)
+        ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            st = lib.xrd_pointslam_knn_build(ptr(self._pos), N, self.cell, self.table_size, ptr(start),
+                                             ptr(end), ptr(ids), ptr(ws), nb,
+                                             torch.cuda.current_stream(dev).cuda_stream)
+        check('xrd_pointslam_knn_build', st)
+        self._index = dict(sorted_ids=ids, cell_start=start, cell_end=end, n=N)
+
+    def rebuild_index_torch(self):
+        """The same index with torch ops (stable argsort of the bucket keys): the reference
+        the device build is tested against."""
         N = self._pos.shape[0]
         inv = float(np.float32(1.0) / np.float32(self.cell))
         ijk = torch.floor(self._pos * inv).to(torch.int64)
@@ -71,9 +90,9 @@ class NeuralPointCloud(nn.Module):
         skey = key[order]
         counts = torch.bincount(skey, minlength=self.table_size)
         end = torch.cumsum(counts, 0)
-        self._index = dict(sorted_ids=order.to(torch.int32).contiguous(),
-                           cell_start=(end - counts).to(torch.int32).contiguous(),
-                           cell_end=end.to(torch.int32).contiguous(), n=N)
+        return dict(sorted_ids=order.to(torch.int32).contiguous(),
+                    cell_start=(end - counts).to(torch.int32).contiguous(),
+                    cell_end=end.to(torch.int32).contiguous(), n=N)
 
     def index_struct(self):
         if self._index is None or self._index['n'] != self._pos.shape[0]:
