@@ -139,3 +139,43 @@ def test_vox_oracle_torch_part_matches_reference_python():
     assert (ge_o - ge_r).abs().max() <= 1e-5 * ge_r.abs().max()
     assert (od.sdf_out.weight.grad - ref.decoder.sdf_out.weight.grad).abs().max() <= \
         1e-5 * ref.decoder.sdf_out.weight.grad.abs().max()
+
+
+def test_device_octree_equals_host_octree_numbering():
+    """octree_device.DeviceOctree (data-parallel build: unique / sort / searchsorted) produces
+    the SAME node ids, codes, child tables and corner-leaf tables as the host C++ octree (which
+    is bit-exact against the reference's compiled svo.Octree, test above) -- over duplicate
+    voxels, two successive insert calls, coordinates at the grid edge (wrap quirk) and an
+    empty second call.  Runs on the host here; the same tensor program runs on the GPU."""
+    from xrdslam_b200 import _cabi
+    from xrdslam_b200.octree_device import DeviceOctree
+    lib = _cabi.lib()
+
+    def host(vlist):
+        t = lib.xrd_octree_create(256)
+        for v in vlist:
+            v = v.int().contiguous()
+            lib.xrd_octree_insert(t, v.data_ptr(), v.shape[0])
+        N = lib.xrd_octree_num_nodes(t)
+        vo, ch, fe = torch.empty(N, 4), torch.empty(N, 8), torch.empty(N, 8, dtype=torch.int32)
+        lib.xrd_octree_export(t, vo.data_ptr(), ch.data_ptr(), fe.data_ptr())
+        lib.xrd_octree_destroy(t)
+        return vo, ch, fe
+    g = torch.Generator().manual_seed(0)
+    for trial, (n1, n2) in enumerate([(50, 30), (2000, 1500), (1, 1), (5000, 5000), (300, 0)]):
+        base = torch.randint(100, 150, (max(n1 // 4, 1), 3), generator=g)
+        v1 = base[torch.randint(0, base.shape[0], (n1,), generator=g)] + \
+            torch.randint(-2, 3, (n1, 3), generator=g)
+        v2 = base[torch.randint(0, base.shape[0], (max(n2, 1),), generator=g)][:n2] + \
+            torch.randint(-6, 7, (n2, 3), generator=g)
+        if trial == 3:
+            v1[:5] = torch.tensor([[255, 255, 255], [0, 0, 0], [255, 0, 128], [254, 255, 3],
+                                   [128, 128, 128]])
+        ref = host([v1, v2] if n2 else [v1])
+        t = DeviceOctree(256)
+        t.insert(v1)
+        t.insert(v2)
+        got = t.export()
+        assert t.num_nodes() == ref[0].shape[0]
+        for a, b in zip(ref, got):
+            assert a.dtype == b.dtype and torch.equal(a, b), trial

@@ -319,3 +319,30 @@ def test_full_step_vs_oracle_chained_through_reference_grid(cuda_dev, R):
         assert rel_err(p.grad, sd_o[n].grad) < TOL, n
     assert rel_err(ro.grad, ro_o.grad) < TOL
     assert rel_err(rd.grad, rd_o.grad) < TOL
+
+
+def test_device_octree_on_gpu_equals_host_octree(cuda_dev):
+    """The map grown on the device (default) == the map grown by the host C++ octree: same
+    node count, centres, structure and vertex tables after two frames."""
+    from xrdslam_b200.sparse_voxel import SparseVoxelConfig
+    from xrdslam_b200.synthetic import make_sequence
+    cam, poses, frames = make_sequence(2, width=160, height=120, offset=(OFFSET,) * 3)
+    H, W = cam.height, cam.width
+    j, i = torch.meshgrid(torch.arange(H, dtype=torch.float32),
+                          torch.arange(W, dtype=torch.float32), indexing='ij')
+    dirs = torch.stack([(i - cam.cx) / cam.fx, -(j - cam.cy) / cam.fy, -torch.ones_like(i)], -1)
+    models = [SparseVoxelConfig(device_octree=flag).setup(camera=cam).to(cuda_dev)
+              for flag in (True, False)]
+    for (rgb, depth), c2w in zip(frames, poses):
+        c2w = torch.from_numpy(c2w)
+        d = torch.from_numpy(depth)
+        pts = (dirs * d[..., None])[d > 0].reshape(-1, 3)
+        pts = (pts @ c2w[:3, :3].T + c2w[:3, 3]).to(cuda_dev)
+        for m in models:
+            m.insert_points(pts)
+    a, b = models[0].map_states, models[1].map_states
+    assert models[0]._dev_svo is not None and models[1]._dev_svo is None
+    for k in ('voxel_vertex_idx', 'voxel_center_xyz', 'voxel_structure'):
+        assert a[k].shape == b[k].shape and torch.equal(a[k], b[k]), k
+    for x, y in zip(models[0].export_octree(), models[1].export_octree()):
+        assert torch.equal(x, y)

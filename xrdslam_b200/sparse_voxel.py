@@ -57,6 +57,7 @@ class SparseVoxelConfig(ModelConfig):
     # --- B200 path knobs ---
     max_samples_per_ray: int = 256  # capacity of the per-ray sample arrays
     seed: int = 0
+    device_octree: bool = True  # grow the octree on the device (octree_device.py)
 
 
 class Decoder(nn.Module):
@@ -119,6 +120,7 @@ class SparseVoxel(Model):
         cfg = self.config
         if (cfg.depth, cfg.width, cfg.in_dim, cfg.embed_dim, cfg.embedder) != (2, 128, 16, 16, 'none'):
             raise NotImplementedError('decoder shape fixed to the reference vox-fusion config')
+        self._dev_svo = None
         self.get_octree()
         self.get_decoder()
         self.map_states = None
@@ -146,11 +148,29 @@ class SparseVoxel(Model):
 
     # ---------------------------------------------------------- map update ---
     def insert_points(self, points):
-        """sparse_voxel.py:325-332: voxel coords = floor(p / voxel_size), int32, on the host."""
+        """sparse_voxel.py:325-332: voxel coords = floor(p / voxel_size), int32.  With the map on
+        a CUDA device the octree is grown ON THE DEVICE (octree_device.DeviceOctree: same node
+        ids as the reference's host insertion, no D2H of the ~300 k points per mapping frame and
+        no H2D of the exported tables); otherwise by the host C++ octree (csrc/octree.cpp)."""
         voxels = torch.div(points, self.config.voxel_size, rounding_mode='floor')
+        if self.config.device_octree and self.embeddings.device.type == 'cuda':
+            if self._dev_svo is None:
+                from .octree_device import DeviceOctree
+                if _cabi.lib().xrd_octree_num_nodes(self._svo) != 1:
+                    raise RuntimeError('octree already holds host-inserted voxels')
+                self._dev_svo = DeviceOctree(self.config.voxels_each_dim, self.embeddings.device)
+            n = self._dev_svo.insert(voxels.to(torch.int64))
+            if n > self.config.num_embeddings:
+                raise RuntimeError(f'octree has {n} nodes > num_embeddings='
+                                   f'{self.config.num_embeddings} (the reference indexes past '
+                                   'the table here, SURVEY Q4)')
+            self.update_map_states()
+            return
         self.insert_voxels(voxels.cpu().int())
 
     def insert_voxels(self, voxels_i32):
+        if self._dev_svo is not None:
+            raise RuntimeError('octree lives on the device: use insert_points')
         v = voxels_i32.contiguous()
         n = _cabi.lib().xrd_octree_insert(self._svo, v.data_ptr(), v.shape[0])
         if n < 0:
@@ -161,6 +181,9 @@ class SparseVoxel(Model):
         self.update_map_states()
 
     def export_octree(self):
+        """voxels f32 [N,4], children f32 [N,8], features i32 [N,8] (HOST tensors)."""
+        if self._dev_svo is not None:
+            return tuple(t.cpu() for t in self._dev_svo.export())
         lib = _cabi.lib()
         N = lib.xrd_octree_num_nodes(self._svo)
         voxels = torch.empty(N, 4)
@@ -171,7 +194,10 @@ class SparseVoxel(Model):
 
     def update_map_states(self):
         """sparse_voxel.py:334-351."""
-        voxels, children, features = self.export_octree()
+        if self._dev_svo is not None:
+            voxels, children, features = self._dev_svo.export()  # stays on the device
+        else:
+            voxels, children, features = self.export_octree()
         centres = (voxels[:, :3] + voxels[:, -1:] / 2) * self.config.voxel_size
         children = torch.cat([children, voxels[:, -1:]], -1)
         dev = self.embeddings.device
