@@ -656,6 +656,8 @@ typedef struct {
  * kernel where the shape qualifies, mma.sync otherwise, 2 = plain TF32 (mma.sync),
  * 3 = 3xTF32 on mma.sync only.  Thread-local, like the error state. */
 int xrd_debug_gemm_mode(int mode);
+/* bring-up hook of the tcgen05 GEMM (descriptor field variants); 0 = production */
+int xrd_debug_gemm_variant(int variant);
 
 /* The wide-MLP GEMM itself (unit tests): C[m][n] = act(sum_k A(m,k) B[k][n] + bias[m]) with
  * A(m,k) = transA ? A[k*lda+m] : A[m*lda+k]; act 0 none, 1 relu, 2 softplus(beta 100),

@@ -279,6 +279,7 @@ SYMBOLS = {
     'xrd_coslam_query': (C.c_int, [C.POINTER(XrdHashGrid), C.POINTER(XrdCoslamMlp), vp, C.c_int,
                                    C.c_int, vp, vp, vp, vp]),
     'xrd_debug_gemm_mode': (C.c_int, [C.c_int]),
+    'xrd_debug_gemm_variant': (C.c_int, [C.c_int]),
     'xrd_debug_gemm': (C.c_int, [C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, vp,
                                  C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp]),
     'xrd_pointslam_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),

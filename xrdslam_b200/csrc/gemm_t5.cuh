@@ -4,20 +4,20 @@
 // error compensation for fp32-level parity.
 //
 //   C[m][n] = epi( sum_k A(m,k) * B[k][n] )      (same contract as gemm.cuh: k_gemm / k_gemm_tc)
-//   MMA M = 128 output features (weights, zero padded), MMA N = 256 points per tile, K = 8/step.
+//   MMA M = 128 output features (weights, zero padded), MMA N = BN points per tile (256, or 128
+//   when K > 128 so that the resident weights still fit), K = 8 per instruction.
 //
-// Shared-memory operand layouts are the "no swizzle" canonical UMMA layouts (core matrix = 8
-// rows x 16 bytes, cute/atom/mma_traits_sm100.hpp make_umma_desc):
-//   A (weights), K-major:  off(m,k) = (k/4)*2048 + m*16 + (k%4)*4       SBO = 128 B, LBO = 2048 B
-//      staged ONCE per CTA by all threads (handles transA / lda / padding) as  big = x with the
-//      13 low mantissa bits cleared and  small = x - big;  resident for every point tile.
-//   B (activations [K][N], points contiguous), MN-major, 128-byte swizzle: per stage 8 TMA boxes of
-//      (32 points, BK rows) land as 8 swizzle atoms (row = 128 B, 8-row groups 1024 B apart, the
-//      TMA and the UMMA descriptor apply the same address-bit XOR): LBO = BK*128 B between
-//      32-point groups, SBO = 1024 B between 8-row groups.  A splitter warp-group turns the landed
-//      tile into big / small in place (element-wise, so it never needs to know the swizzle).
-//   D: 128 lanes x 256 fp32 columns of TMEM, two accumulators (512 columns) so that the epilogue
-//      of tile i overlaps the MMAs of tile i+1.
+// Both operands sit in shared memory in the canonical "no swizzle" K-major UMMA layout (core
+// matrix = 8 rows x 16 bytes; cute/atom/mma_traits_sm100.hpp make_umma_desc<Major::K>):
+//      off(row, k) = (k/4) * (ROWS*16) + row*16 + (k%4)*4      LBO = ROWS*16 B, SBO = 128 B
+//   A (weights, ROWS = 128): staged ONCE per CTA by all threads (handles transA / lda /
+//      padding) as  big = x with the 13 low mantissa bits cleared,  small = x - big.
+//   B (activations [K][N], points contiguous in HBM, ROWS = BN): one TMA box (BN points x BK
+//      rows, row-major) per stage lands in a raw staging tile; the splitter warp-group
+//      transposes it into the K-major layout while splitting big / small (each thread reads
+//      4 k-values of a point from 4 rows and writes one 16-byte chunk: conflict-free).
+//   D: 128 lanes x BN fp32 columns of TMEM, two accumulators, so the epilogue of tile i overlaps
+//      the MMAs of tile i+1.
 // Roles (384 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected
 // lane), warps 4-7 = epilogue (tcgen05.ld 32x32b, bias / activation / mask / addend, 128-byte
 // row stores), warps 8-11 = splitter.  All hand-offs are mbarriers; every wait is bounded (a
@@ -30,16 +30,16 @@
 namespace xrd {
 namespace t5 {
 
-constexpr int BM = 128, BN = 256, BK = 16;
+constexpr int BM = 128, BK = 16;
 constexpr int NTHREADS = 384;
-constexpr int B_STAGE_BYTES = BK * BN * 4;  // 16 KB
+constexpr int RAW_STAGES = 2, OP_STAGES = 2;
 constexpr uint32_t SPIN_LIMIT = 1u << 27;
 
 struct Params {
   GemmArgs G;
   int Kpad;      // K rounded up to BK
   int n_tiles;   // ceil(N / BN)
-  int stages;    // 2 or 3 (shared-memory budget)
+  int variant;   // debug (xrd_debug_gemm_variant): bit 0 swaps LBO / SBO in the descriptors
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -144,38 +144,47 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)(layout_type & 7) << 61;
   return d;
 }
-// instruction descriptor: D = F32, A = B = TF32, A K-major, B MN-major, M = 128, N = 256
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major,
+// M = 128, N = BN
+template <int BN>
 __host__ __device__ constexpr uint32_t make_idesc() {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
+  return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(BN >> 3) << 17) |
          ((uint32_t)(BM >> 4) << 24);
 }
 
 __device__ __forceinline__ float tf32_big(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
+template <int BN>
 static __global__ void __launch_bounds__(NTHREADS, 1)
 k_gemm_t5(const __grid_constant__ CUtensorMap tmap_b, const Params P) {
+  constexpr int RAW_BYTES = BK * BN * 4;  // one TMA box: BK rows x BN points, row-major
+  constexpr int OP_BYTES = BK * BN * 4;   // the same tile in the K-major operand layout
   extern __shared__ __align__(1024) uint8_t smem[];
   const GemmArgs& G = P.G;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int Kpad = P.Kpad, S = P.stages;
+  const int Kpad = P.Kpad;
   const int a_bytes = BM * Kpad * 4;
   float* a_big = reinterpret_cast<float*>(smem);
   float* a_small = reinterpret_cast<float*>(smem + a_bytes);
-  uint8_t* b_base = smem + 2 * a_bytes;  // [S][big 16 KB | small 16 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)S * 2 * B_STAGE_BYTES);
-  uint64_t* full = bars;            // [S]  TMA bytes landed
-  uint64_t* split = bars + 4;       // [S]  big/small ready (128 splitter arrivals)
-  uint64_t* empty = bars + 8;       // [S]  MMAs that read the stage are complete
-  uint64_t* tfull = bars + 12;      // [2]  accumulator complete
-  uint64_t* tempty = bars + 14;     // [2]  accumulator drained (128 epilogue arrivals)
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 16);
+  uint8_t* raw_base = smem + 2 * a_bytes;                       // [RAW_STAGES][RAW_BYTES]
+  uint8_t* op_base = raw_base + RAW_STAGES * RAW_BYTES;         // [OP_STAGES][big | small]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(op_base + OP_STAGES * 2 * OP_BYTES);
+  uint64_t* full = bars;            // [RAW_STAGES] TMA bytes landed
+  uint64_t* rawfree = bars + 2;     // [RAW_STAGES] raw tile consumed by the splitter (128 arrivals)
+  uint64_t* split = bars + 4;       // [OP_STAGES]  big / small operand tiles ready (128 arrivals)
+  uint64_t* empty = bars + 6;       // [OP_STAGES]  MMAs that read the operand tiles are complete
+  uint64_t* tfull = bars + 8;       // [2]  accumulator complete
+  uint64_t* tempty = bars + 10;     // [2]  accumulator drained (128 epilogue arrivals)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 12);
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(split + s, 128); mbar_init(empty + s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 128); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(full + s, 1); mbar_init(rawfree + s, 128); mbar_init(split + s, 128);
+      mbar_init(empty + s, 1); mbar_init(tfull + s, 1); mbar_init(tempty + s, 128);
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_holder, 512);
+  if (warp == 1) tmem_alloc(tmem_holder, 2 * BN);
   // ---- stage the weights once: A(m,k) -> canonical K-major core-matrix layout, big / small
   for (int e = tid; e < BM * Kpad; e += NTHREADS) {
     const int m = e % BM, k = e / BM;
@@ -192,6 +201,11 @@ k_gemm_t5(const __grid_constant__ CUtensorMap tmap_b, const Params P) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
   const int n_kb = Kpad / BK;
+  const bool swap = (P.variant & 1) != 0;
+  // K-major, no swizzle: LBO = distance between the two 16-byte K chunks of one MMA,
+  // SBO = distance between 8-row groups
+  const uint32_t a_lbo = swap ? 128u : BM * 16u, a_sbo = swap ? BM * 16u : 128u;
+  const uint32_t b_lbo = swap ? 128u : BN * 16u, b_sbo = swap ? BN * 16u : 128u;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -199,20 +213,16 @@ k_gemm_t5(const __grid_constant__ CUtensorMap tmap_b, const Params P) {
       int it = 0;
       for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
         for (int kb = 0; kb < n_kb; ++kb, ++it) {
-          const int s = it % S;
-          const uint32_t ph = (it / S) & 1;
-          mbar_wait(empty + s, ph ^ 1);
-          mbar_expect_tx(full + s, B_STAGE_BYTES);
-          uint8_t* dst = b_base + (size_t)s * 2 * B_STAGE_BYTES;
-#pragma unroll
-          for (int j = 0; j < BN / 32; ++j)  // one 128-byte-swizzle atom (32 points x BK rows) each
-            tma_load_2d(dst + j * (BK * 128), &tmap_b, full + s, tile * BN + j * 32, kb * BK);
+          const int s = it % RAW_STAGES;
+          mbar_wait(rawfree + s, ((it / RAW_STAGES) & 1) ^ 1);
+          mbar_expect_tx(full + s, RAW_BYTES);
+          tma_load_2d(raw_base + (size_t)s * RAW_BYTES, &tmap_b, full + s, tile * BN, kb * BK);
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = make_idesc();
+    const uint32_t idesc = make_idesc<BN>();
     int it = 0, lt = 0;
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++lt) {
       const int acc = lt & 1;
@@ -220,50 +230,56 @@ k_gemm_t5(const __grid_constant__ CUtensorMap tmap_b, const Params P) {
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
       for (int kb = 0; kb < n_kb; ++kb, ++it) {
-        const int s = it % S;
-        mbar_wait(split + s, (it / S) & 1);
+        const int s = it % OP_STAGES;
+        mbar_wait(split + s, (it / OP_STAGES) & 1);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t bb = smem_u32(b_base + (size_t)s * 2 * B_STAGE_BYTES);
-          const uint32_t bs = bb + B_STAGE_BYTES;
+          const uint32_t bb = smem_u32(op_base + (size_t)s * 2 * OP_BYTES);
+          const uint32_t bs = bb + OP_BYTES;
 #pragma unroll
           for (int ks = 0; ks < BK / 8; ++ks) {
-            const int kc = (kb * (BK / 8) + ks) * 2;  // first of the two 16-byte K chunks
-            const uint64_t da_b = make_desc(smem_u32(a_big) + kc * (BM * 16), BM * 16, 128, 0);
-            const uint64_t da_s = make_desc(smem_u32(a_small) + kc * (BM * 16), BM * 16, 128, 0);
-            const uint64_t db_b = make_desc(bb + ks * 1024, BK * 128, 1024, 2);
-            const uint64_t db_s = make_desc(bs + ks * 1024, BK * 128, 1024, 2);
+            const int kca = (kb * (BK / 8) + ks) * 2;  // 16-byte K chunk index in the resident A
+            const int kcb = ks * 2;                    // ... and in this stage's B tile
+            const uint64_t da_b = make_desc(smem_u32(a_big) + kca * (BM * 16), a_lbo, a_sbo, 0);
+            const uint64_t da_s = make_desc(smem_u32(a_small) + kca * (BM * 16), a_lbo, a_sbo, 0);
+            const uint64_t db_b = make_desc(bb + kcb * (BN * 16), b_lbo, b_sbo, 0);
+            const uint64_t db_s = make_desc(bs + kcb * (BN * 16), b_lbo, b_sbo, 0);
             const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
             umma_tf32(d_tmem, da_s, db_b, idesc, first);  // small terms first (3xTF32)
             umma_tf32(d_tmem, da_b, db_s, idesc, 1u);
             umma_tf32(d_tmem, da_b, db_b, idesc, 1u);
           }
-          umma_commit(empty + s);                      // stage reusable once these MMAs retire
+          umma_commit(empty + s);                      // operand stage reusable once these retire
           if (kb == n_kb - 1) umma_commit(tfull + acc);  // accumulator complete
         }
         __syncwarp();
       }
     }
   } else if (warp >= 8) {
-    // ===================== splitter: landed fp32 tile -> big (in place) + small =====================
+    // ============ splitter: raw [BK][BN] fp32 tile -> K-major big / small operand tiles ============
     const int st = tid - 256;  // 0..127
     int it = 0;
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < n_kb; ++kb, ++it) {
-        const int s = it % S;
-        mbar_wait(full + s, (it / S) & 1);
-        float4* big = reinterpret_cast<float4*>(b_base + (size_t)s * 2 * B_STAGE_BYTES);
-        float4* sml = reinterpret_cast<float4*>(b_base + (size_t)s * 2 * B_STAGE_BYTES + B_STAGE_BYTES);
+        const int rs = it % RAW_STAGES, os = it % OP_STAGES;
+        mbar_wait(full + rs, (it / RAW_STAGES) & 1);          // TMA landed
+        mbar_wait(empty + os, ((it / OP_STAGES) & 1) ^ 1);    // operand slot no longer read by MMAs
+        const float* raw = reinterpret_cast<const float*>(raw_base + (size_t)rs * RAW_BYTES);
+        float4* big = reinterpret_cast<float4*>(op_base + (size_t)os * 2 * OP_BYTES);
+        float4* sml = reinterpret_cast<float4*>(op_base + (size_t)os * 2 * OP_BYTES + OP_BYTES);
 #pragma unroll
-        for (int q = 0; q < B_STAGE_BYTES / 16 / 128; ++q) {
-          const int i = st + q * 128;
-          const float4 v = big[i];
-          const float4 b = make_float4(tf32_big(v.x), tf32_big(v.y), tf32_big(v.z), tf32_big(v.w));
-          big[i] = b;
-          sml[i] = make_float4(v.x - b.x, v.y - b.y, v.z - b.z, v.w - b.w);
+        for (int q = 0; q < (BK / 4) * BN / 128; ++q) {
+          const int c = st + q * 128;      // chunk = (k quad, point)
+          const int kq = c / BN, n = c - kq * BN;
+          const float v0 = raw[(kq * 4 + 0) * BN + n], v1 = raw[(kq * 4 + 1) * BN + n];
+          const float v2 = raw[(kq * 4 + 2) * BN + n], v3 = raw[(kq * 4 + 3) * BN + n];
+          const float4 b = make_float4(tf32_big(v0), tf32_big(v1), tf32_big(v2), tf32_big(v3));
+          big[kq * BN + n] = b;
+          sml[kq * BN + n] = make_float4(v0 - b.x, v1 - b.y, v2 - b.z, v3 - b.w);
         }
         fence_proxy_async();
-        mbar_arrive(split + s);
+        mbar_arrive(split + os);
+        mbar_arrive(rawfree + rs);
       }
     }
   } else if (warp >= 4) {
@@ -286,37 +302,37 @@ k_gemm_t5(const __grid_constant__ CUtensorMap tmap_b, const Params P) {
         tmem_ld32(t0 + c * 32, v);
         const int nb = n0 + c * 32;
         if (row_ok && nb < G.N) {
-        const int nv = min(32, G.N - nb);
+          const int nv = min(32, G.N - nb);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j] + bias, G.act);
-        if (G.relu_mask) {
-          const float* mk = G.relu_mask + (size_t)m * G.ldmask + nb;
+          for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j] + bias, G.act);
+          if (G.relu_mask) {
+            const float* mk = G.relu_mask + (size_t)m * G.ldmask + nb;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nv && !(mk[j] > 0.f)) v[j] = 0.f;
-        }
-        if (G.act_out) {
-          float* ao = G.act_out + (size_t)m * G.ldact + nb;
+            for (int j = 0; j < 32; ++j)
+              if (j < nv && !(mk[j] > 0.f)) v[j] = 0.f;
+          }
+          if (G.act_out) {
+            float* ao = G.act_out + (size_t)m * G.ldact + nb;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nv) ao[j] = v[j];
-        }
-        if (G.addend) {
-          const float* ad = G.addend + (size_t)m * G.ldadd + nb;
+            for (int j = 0; j < 32; ++j)
+              if (j < nv) ao[j] = v[j];
+          }
+          if (G.addend) {
+            const float* ad = G.addend + (size_t)m * G.ldadd + nb;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nv) v[j] += ad[j];
-        }
-        float* cp = G.C + (size_t)m * G.ldc + nb;
-        if (vec && nv == 32 && !G.accumulate) {
+            for (int j = 0; j < 32; ++j)
+              if (j < nv) v[j] += ad[j];
+          }
+          float* cp = G.C + (size_t)m * G.ldc + nb;
+          if (vec && nv == 32 && !G.accumulate) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nv) cp[j] = G.accumulate ? (cp[j] + v[j]) : v[j];
-        }
+            for (int j = 0; j < 32; ++j)
+              if (j < nv) cp[j] = G.accumulate ? (cp[j] + v[j]) : v[j];
+          }
         }
         __syncwarp();  // tcgen05.ld is warp-collective: reconverge before the next chunk
       }
@@ -328,7 +344,7 @@ k_gemm_t5(const __grid_constant__ CUtensorMap tmap_b, const Params P) {
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -358,33 +374,42 @@ static inline bool eligible(const GemmArgs& G) {
          ((((uintptr_t)G.B) & 15) == 0) && encode_fn() != nullptr;
 }
 
-static inline cudaError_t launch(const GemmArgs& G, cudaStream_t stream) {
+extern thread_local int g_t5_variant;
+
+template <int BN>
+static inline cudaError_t launch_bn(const GemmArgs& G, cudaStream_t stream) {
   Params P;
   P.G = G;
   P.Kpad = (G.K + BK - 1) / BK * BK;
   P.n_tiles = (G.N + BN - 1) / BN;
-  P.stages = P.Kpad > 128 ? 2 : 3;
-  // B [K][ldb] fp32 as a 2-D tensor (points innermost); box = (32 points = 128 B, BK rows) with the
-  // 128-byte swizzle; rows >= K and columns >= ldb read as zero (out-of-bounds fill)
+  P.variant = g_t5_variant;
+  // B [K][ldb] fp32 as a 2-D tensor (points innermost); box = (BN points, BK rows), no swizzle;
+  // rows >= K and columns >= ldb read as zero (out-of-bounds fill)
   CUtensorMap tm;
   const cuuint64_t dims[2] = {(cuuint64_t)G.ldb, (cuuint64_t)G.K};
   const cuuint64_t strides[1] = {(cuuint64_t)G.ldb * 4};  // bytes, dim 1
-  const cuuint32_t box[2] = {32, BK};
+  const cuuint32_t box[2] = {BN, BK};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(G.B), dims, strides,
-                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
-  const size_t smem = 2 * (size_t)BM * P.Kpad * 4 + (size_t)P.stages * 2 * B_STAGE_BYTES + 256;
+  const size_t smem = 2 * (size_t)BM * P.Kpad * 4 + (size_t)RAW_STAGES * BK * BN * 4 +
+                      (size_t)OP_STAGES * 2 * BK * BN * 4 + 256;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_t5, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_t5<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   int grid = P.n_tiles < num_sms() ? P.n_tiles : num_sms();
-  k_gemm_t5<<<grid, NTHREADS, smem, stream>>>(tm, P);
+  k_gemm_t5<BN><<<grid, NTHREADS, smem, stream>>>(tm, P);
   return cudaGetLastError();
+}
+
+static inline cudaError_t launch(const GemmArgs& G, cudaStream_t stream) {
+  // resident weights (big + small) + 2 raw + 2 x 2 operand stages must fit 227 KB
+  return G.K > 128 ? launch_bn<128>(G, stream) : launch_bn<256>(G, stream);
 }
 
 }  // namespace t5
