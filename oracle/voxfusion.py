@@ -135,7 +135,9 @@ def _inverse_cdf_block(pts_idx, min_depth, max_depth, noise, probs, steps):
             s_depth[j, s] = f32(float(f32(z + z_low)) * .5)
             z_low = z
             s += 1
-        while (z_low < cmax) and (num_rays > (H + curr_bin)):
+        # (curr_bin == max_hits happens when a ray consumed every bin above: the kernel then
+        #  reads one element past its row -- undefined; the restatement stops)
+        while (z_low < cmax) and (num_rays > (H + curr_bin)) and curr_bin < max_hits:
             s_idx[j, s] = pts_idx[j, curr_bin]
             s_dist[j, s] = f32(cmax - z_low)
             s_depth[j, s] = f32(float(f32(cmax + z_low)) * .5)
