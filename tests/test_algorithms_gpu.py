@@ -57,6 +57,9 @@ def test_nice_slam_mapping_tracking(cuda_dev):
     algo.set_initialized()
     # frustum feature selection: voxels outside the mask keep their values exactly
     for k, g in algo.model.grids.items():
+        if k == 'grid_coarse':  # optimised whole, and only by the coarse mapper (do_mapping)
+            assert torch.equal(g.detach(), g_before[k])
+            continue
         m = algo.model.grid_opti_mask[k].bool()
         assert 0 < int(m.sum()) < m.numel()
         assert torch.equal(g.detach()[~m], g_before[k][~m])
@@ -153,3 +156,36 @@ def test_coslam_mapping_tracking(cuda_dev):
     algo.config.graph_mapping = False
     rec2, _ = _losses(algo, window, 5, True)
     assert all(np.isfinite(rec2))
+
+
+@pytest.mark.gpu
+def test_nice_slam_coarse_mapper(cuda_dev):
+    """The coarse mapper of the reference run config (coarse=True, nice_slam.py:102-109):
+    optimize_update(coarse=True) renders stage 'coarse' and moves ONLY the coarse grid."""
+    from xrdslam_b200.nice_slam import NiceSLAMConfig
+    torch.manual_seed(0)
+    cam, poses, fr = _frames(2, rot_rep='quat')
+    algo = NiceSLAMConfig(mapping_bound=[[-3.2, 3.2], [-4.2, 2.7], [-2.2, 2.7]],
+                          marching_cubes_bound=[[-3.2, 3.2], [-4.2, 2.7], [-2.2, 2.7]]).setup(
+        camera=cam, device=cuda_dev)
+    assert algo.config.coarse and 'grid_coarse' in algo.model.grids
+    g_before = {k: v.detach().clone() for k, v in algo.model.grids.items()}
+    algo.add_keyframe(fr[0])
+    rec = []
+    orig = algo.get_loss
+
+    def wrapped(*a, **k):
+        loss = orig(*a, **k)
+        rec.append(float(loss.detach()))
+        assert algo.stage == 'coarse'
+        return loss
+    algo.get_loss = wrapped
+    algo.optimize_update(40, [fr[0]], is_mapping=True, coarse=True)
+    algo.get_loss = orig
+    assert len(rec) == 40 and all(np.isfinite(rec))
+    assert np.mean(rec[-5:]) < np.mean(rec[:5])
+    for k, g in algo.model.grids.items():
+        if k == 'grid_coarse':
+            assert not torch.equal(g.detach(), g_before[k])
+        else:
+            assert torch.equal(g.detach(), g_before[k]), k

@@ -164,6 +164,7 @@ def test_pointslam_render_img_vs_oracle(cuda_dev):
     g.update(cloud_pos=npc.cloud_pos().cpu().numpy(), geo_feats=npc.geo_feats.detach().cpu().numpy(),
              col_feats=npc.col_feats.detach().cpu().numpy())
     ora = pointslam_from_golden(g, 'oracle')
+    ora.frustum_mask = npc.frustum_mask.bool().cpu().reshape(-1, 1)  # set by pre_precessing
     gen = torch.Generator().manual_seed(3)
     rf, rfc = torch.randn(32, generator=gen) * 0.01, torch.randn(32, generator=gen) * 0.01
     depth = fr[1][1]

@@ -153,8 +153,10 @@ class _PointStep(torch.autograd.Function):
             need_col_feats=color and need[11], need_cdec=color and any(need[12:]))
         ctx.grads = grads
         ctx.n_c = len(cparams)
-        ctx.n_live = 2 if ((is_mapping and color) or
-                           (not is_mapping and model.config.tracking_use_color_in_tracking)) else 1
+        # the colour term enters the in-kernel gradient only in stage 'color' (get_loss_dict
+        # lists ls[1] in geometry-stage tracking too, where it is identically 0)
+        ctx.n_live = 2 if (color and (is_mapping or model.config.tracking_use_color_in_tracking)) \
+            else 1
         ret = (outs['losses'], outs['rgb'], outs['depth'], outs['uncertainty'],
                outs['valid_ray_mask'])
         ctx.mark_non_differentiable(*ret[1:])
