@@ -91,7 +91,7 @@ class CoslamOracle(torch.nn.Module):
             z_samples[target_d.squeeze(-1) <= 0] = torch.linspace(
                 c.near, c.far, steps=c.n_range_d).to(target_d)
             z_vals = torch.linspace(c.near, c.far,
-                                    c.n_sample_d)[None, :].repeat(n_rays, 1)
+                                    c.n_sample_d)[None, :].repeat(n_rays, 1).to(target_d.device)
             z_vals, _ = torch.sort(torch.cat([z_vals, z_samples], -1), -1)
         else:
             z_vals = torch.linspace(c.near, c.far,
@@ -105,7 +105,7 @@ class CoslamOracle(torch.nn.Module):
 
     # ---- network ------------------------------------------------------------
     def normalise(self, pts_flat):
-        bb = self.bounding_box
+        bb = self.bounding_box.to(pts_flat.device)
         return (pts_flat - bb[:, 0]) / (bb[:, 1] - bb[:, 0])  # f64 (C2)
 
     def query_color_sdf(self, x_norm):
@@ -190,12 +190,13 @@ class CoslamOracle(torch.nn.Module):
         """pts (f64, normalised) of the smoothness lattice; smooth_rand[0] is
         torch.rand(3) of :176, smooth_rand[1] the torch.rand((1,1,1,3)) of :179."""
         c = self.cfg
-        bb = self.bounding_box
+        bb = self.bounding_box.to(self.embed_fn.params.device)
+        smooth_rand = smooth_rand.to(bb.device)
         n = c.smooth_pts - 1
         grid_size = (c.smooth_pts - 1) * c.smooth_vox
         offset_max = bb[:, 1] - bb[:, 0] - grid_size - 2 * c.smooth_margin
         offset = smooth_rand[0].to(offset_max) * offset_max + c.smooth_margin
-        ar = torch.arange(0, n, dtype=torch.long)
+        ar = torch.arange(0, n, dtype=torch.long, device=bb.device)
         x, y, z = torch.meshgrid(ar, ar, ar, indexing='ij')
         coords = torch.stack([x, y, z], -1).float().to(bb)
         pts = (coords + smooth_rand[1].reshape(1, 1, 1, 3).to(bb)

@@ -94,18 +94,19 @@ def hashgrid_indices(x: torch.Tensor, table: dict):
     assert x.dtype == torch.float32
     L = len(table['scale'])
     P = x.shape[0]
-    scale = torch.from_numpy(table['scale'])  # [L] f32
+    dev = x.device  # (constants follow the points: the bench's torch-on-GPU leg runs this on cuda)
+    scale = torch.from_numpy(table['scale']).to(dev)  # [L] f32
     # fmaf(scale, x, 0.5f): f64 product of two f32 is exact, one rounding left
     pos = (scale.double()[None, :, None] * x.double()[:, None, :] +
            0.5).float()  # [P,L,3]
     cell = torch.floor(pos)
     w = pos - cell
     g = cell.to(torch.int64) & U32  # (uint32)(int)cell
-    res = torch.from_numpy(table['resolution'].astype(np.int64))[None, :]
-    size = torch.from_numpy(table['size'].astype(np.int64))[None, :]
-    off = torch.from_numpy(table['offset'].astype(np.int64))[None, :]
-    hashed = torch.from_numpy(table['hashed'])[None, :]
-    idx = torch.empty(P, L, 8, dtype=torch.int64)
+    res = torch.from_numpy(table['resolution'].astype(np.int64))[None, :].to(dev)
+    size = torch.from_numpy(table['size'].astype(np.int64))[None, :].to(dev)
+    off = torch.from_numpy(table['offset'].astype(np.int64))[None, :].to(dev)
+    hashed = torch.from_numpy(table['hashed'])[None, :].to(dev)
+    idx = torch.empty(P, L, 8, dtype=torch.int64, device=dev)
     for c in range(8):
         gx = (g[..., 0] + ((c >> 0) & 1)) & U32
         gy = (g[..., 1] + ((c >> 1) & 1)) & U32
@@ -154,7 +155,7 @@ class HashGridRestated(nn.Module):
     def forward(self, x):
         x = x.to(torch.float32).contiguous()
         idx, w_exact = hashgrid_indices(x.detach(), self.table)
-        scale = torch.from_numpy(self.table['scale'])[None, :, None]
+        scale = torch.from_numpy(self.table['scale'])[None, :, None].to(x.device)
         xs = x[:, None, :] * scale  # differentiable carrier, d w/d x = scale
         w = w_exact + (xs - xs.detach())  # [P,L,3]
         tab = self.params.view(-1, self.F)
@@ -187,7 +188,7 @@ class OneBlobRestated(nn.Module):
     def forward(self, x):
         x = x.to(torch.float32)
         nb = self.n_bins
-        edges = torch.arange(nb + 1, dtype=torch.float32) / nb  # scalbnf
+        edges = torch.arange(nb + 1, dtype=torch.float32, device=x.device) / nb  # scalbnf
         d = edges[None, None, :] - x[:, :, None]  # [P,3,nb+1]
         s = float(nb)
         cdf = quartic_cdf(d, s) + quartic_cdf(d - 1.0, s) + quartic_cdf(
