@@ -457,8 +457,18 @@ def run_ours(args):
             'wall_s_value_leg': wall,
         }
         print(json.dumps(line))
+    _finish(world)
+
+
+def _finish(world):
+    """Multi-rank exit: captured graphs hold NCCL nodes and rank 0 runs single-GPU legs after
+    the other ranks are done, so tearing the communicator down collectively can stall; the
+    JSON line is out -- flush and leave (the OS reclaims the NCCL resources)."""
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 # ------------------------------------------------------------ CPU baseline ---
@@ -690,6 +700,8 @@ def run_workload(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * R * Ke / float(t.item())
 
+    n_launch = count_launches(wl, min(K, 5))  # every rank: the step holds collectives
+    barrier()
     trk = wl.tracking() if rank == 0 else None
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -712,10 +724,9 @@ def run_workload(args):
             'iters': {'mapping_iters_per_s': K / (ms_total * 1e-3), **(trk or {})},
             'wall_s_value_leg': wall,
         }
-        line['gpu_launches'] = count_launches(wl, min(K, 5))
+        line['gpu_launches'] = n_launch
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    _finish(world)
 
 
 def count_launches(wl, n):

@@ -96,8 +96,8 @@ def test_sharded_mapping_equals_single_gpu():
 
 
 def _worker_graph(rank, world, port, ret):
-    """CUDA-graph mapping iteration, rays sharded over 2 ranks (3 captured segments + 2 NCCL
-    all-reduces) == the single-GPU captured iteration on the whole batch."""
+    """CUDA-graph mapping iteration, rays sharded over 2 ranks (ONE captured graph holding the 2
+    NCCL all-reduces) == the single-GPU captured iteration on the whole batch."""
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     os.environ['MASTER_ADDR'] = '127.0.0.1'
@@ -131,7 +131,9 @@ def _worker_graph(rank, world, port, ret):
     loss_s = float(sess_s.step_resident(0, (rows, ids)))
     flat_s = sess_s.flat.clone()
     algo_d, frames_d, sess_d = build(2048, True)
-    assert sess_d.world == 2 and sess_d.R == 4096 and len(sess_d.graphs) == 3
+    assert sess_d.world == 2 and sess_d.R == 4096
+    # one graph holding both NCCL all-reduces (3 segments only if NCCL refused capture)
+    assert len(sess_d.graphs) == (1 if sess_d.single_graph else 3)
     sl = slice(rank * 4096, (rank + 1) * 4096)
     loss_d = float(sess_d.step_resident(0, (rows[sl].contiguous(), ids[sl].contiguous())))
     out = {'loss': abs(loss_d - loss_s) / abs(loss_s)}
@@ -146,7 +148,12 @@ def _worker_graph(rank, world, port, ret):
     # after the (replicated) Adam step the replicas still agree with the single-GPU model
     out['param'] = max(float((p.detach() - q.detach()).abs().max()) for p, q in
                        zip(algo_d.model.decoder.parameters(), algo_s.model.decoder.parameters()))
+    out['single_graph'] = bool(sess_d.single_graph)
     ret[rank] = out
+    sess_d.release()  # drop the captured NCCL nodes before the communicator goes away
+    sess_s.release()
+    torch.cuda.synchronize()
+    dist.barrier()
     dist.destroy_process_group()
 
 

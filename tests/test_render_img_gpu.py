@@ -1,6 +1,6 @@
 """render_img parity: the full-frame inference path of every algorithm
 (slam/algorithms/coslam.py:245-289, nice_slam.py:234, voxfusion.py:125, point_slam.py:274)
-on a 160x120 frame against the oracle's forward pass on the same rays, and the K-iteration
+on a small (80x60) frame against the oracle's forward pass on the same rays, and the K-iteration
 Co-SLAM loss trajectory against the oracle's own optimisation from identical parameters
 (north_star: "at matched loss")."""
 import random
@@ -13,7 +13,7 @@ import torch
 from helpers import BOUND, max_abs
 
 pytestmark = pytest.mark.gpu
-W, H = 160, 120
+W, H = 80, 60  # small frames: the CPU oracles render them too
 
 
 def _host_rays(cam, c2w):
@@ -83,7 +83,7 @@ def test_voxfusion_render_img_vs_oracle(cuda_dev):
     from xrdslam_b200.frame import Frame
     from xrdslam_b200.synthetic import make_sequence
     from xrdslam_b200.voxfusion import VoxFusionConfig
-    w, h = 80, 60  # the CPU oracle marches in python loops
+    w, h = 64, 50  # the CPU oracle marches in python loops; 3200 rays = 2 chunks of ray_batch_size
     cam, poses, fr = make_sequence(2, width=w, height=h, offset=(25.6,) * 3)
     algo = VoxFusionConfig().setup(camera=cam, device=cuda_dev)
     frames = [Frame(k, fr[k][0], fr[k][1], init_pose=poses[k]) for k in range(2)]
@@ -143,7 +143,9 @@ def test_pointslam_render_img_vs_oracle(cuda_dev):
     cam, poses, fr = make_sequence(2, width=W, height=H)
     with warnings.catch_warnings():
         warnings.simplefilter('ignore', RuntimeWarning)
-        algo = PointSLAMConfig().setup(camera=cam, device=cuda_dev)
+        # 80x60 = 4800 pixels: the colour-gradient pass takes the top 15 n of them
+        algo = PointSLAMConfig(pixels_adding=2000, mapping_pixels_based_on_color_grad=200).setup(
+            camera=cam, device=cuda_dev)
     frames = [Frame(k, fr[k][0], fr[k][1], init_pose=poses[k], separate_LR=True,
                     rot_rep='axis_angle') for k in range(2)]
     np.random.seed(0)
