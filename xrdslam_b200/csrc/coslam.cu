@@ -26,6 +26,7 @@
 //              level 4*nt+t of rows g, g+8) and scatters with red.global.add.v2.f32.
 //   k_finalize loss accumulators -> the 4 weighted loss terms.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -67,6 +68,8 @@ struct Params {
   double* loss_acc;   // 4 sums
   int NR;             // rays per tile
   int n_tiles;
+  float* jac;         // k_fused_g: [R*S][2 halves][8 levels][6] d feat / d xn, written by the forward
+                      // gather when position gradients are wanted (replaces the backward re-gather)
 };
 
 // ------------------------------------------------------------------ sample ---
@@ -320,14 +323,14 @@ template <int NL>
 __device__ __noinline__ float3 hash_backward_multi(const Params& P, const Lv* __restrict__ lv,
                                                    int l0, const bool (&on)[NL], float x0,
                                                    float x1, float x2, const float (&g)[NL][2],
-                                                   bool need_dx, bool scatter) {
+                                                   bool need_dx, bool scatter, int lstride = 4) {
   const float2* __restrict__ tab = reinterpret_cast<const float2*>(P.table);
   const float x[3] = {x0, x1, x2};
   float w[NL][3], sc[NL];
   uint32_t idx[NL][8];
 #pragma unroll
   for (int h = 0; h < NL; ++h) {
-    const Lv L = lv[on[h] ? l0 + 4 * h : 0];
+    const Lv L = lv[on[h] ? l0 + lstride * h : 0];
     sc[h] = L.scale;
     uint32_t c[3];
 #pragma unroll
@@ -1002,13 +1005,19 @@ __device__ __forceinline__ void group_sync(int grp) {
 
 // hash levels half, half+2, ... and the OneBlob dims of this half (0: x,y  1: z)
 __device__ __forceinline__ void encode_half(const Params& P, const Lv* __restrict__ lv,
-                                            const float xn[3], float* __restrict__ rec, int half) {
+                                            const float xn[3], float* __restrict__ rec, int half,
+                                            float* __restrict__ jac) {
   const float2* __restrict__ tab = reinterpret_cast<const float2*>(P.table);
 #pragma unroll 2
   for (int i = 0; i < kL / 2; ++i) {
     const int l = half + 2 * i;
     if (l >= P.g.n_levels) {
       *reinterpret_cast<float2*>(rec + R_FEAT + 2 * l) = make_float2(0.f, 0.f);
+      if (jac) {
+        *reinterpret_cast<float2*>(jac + 6 * i) = make_float2(0.f, 0.f);
+        *reinterpret_cast<float2*>(jac + 6 * i + 2) = make_float2(0.f, 0.f);
+        *reinterpret_cast<float2*>(jac + 6 * i + 4) = make_float2(0.f, 0.f);
+      }
       continue;
     }
     float w[3];
@@ -1032,6 +1041,22 @@ __device__ __forceinline__ void encode_half(const Params& P, const Lv* __restric
       f1 = fmaf(wk, v[k].y, f1);
     }
     *reinterpret_cast<float2*>(rec + R_FEAT + 2 * l) = make_float2(f0, f1);
+    if (jac) {
+      // d feat / d xn while the 8 corners are in registers: [f0: dx dy dz | f1: dx dy dz] * scale
+      const float w0 = w[0], w1 = w[1], w2 = w[2], sc = L.scale;
+      const float a00 = (1 - w1) * (1 - w2), a10 = w1 * (1 - w2), a01 = (1 - w1) * w2, a11 = w1 * w2;
+      const float b00 = (1 - w0) * (1 - w2), b10 = w0 * (1 - w2), b01 = (1 - w0) * w2, b11 = w0 * w2;
+      const float c00 = (1 - w0) * (1 - w1), c10 = w0 * (1 - w1), c01 = (1 - w0) * w1, c11 = w0 * w1;
+      const float jx0 = a00 * (v[1].x - v[0].x) + a10 * (v[3].x - v[2].x) + a01 * (v[5].x - v[4].x) + a11 * (v[7].x - v[6].x);
+      const float jy0 = b00 * (v[2].x - v[0].x) + b10 * (v[3].x - v[1].x) + b01 * (v[6].x - v[4].x) + b11 * (v[7].x - v[5].x);
+      const float jz0 = c00 * (v[4].x - v[0].x) + c10 * (v[5].x - v[1].x) + c01 * (v[6].x - v[2].x) + c11 * (v[7].x - v[3].x);
+      const float jx1 = a00 * (v[1].y - v[0].y) + a10 * (v[3].y - v[2].y) + a01 * (v[5].y - v[4].y) + a11 * (v[7].y - v[6].y);
+      const float jy1 = b00 * (v[2].y - v[0].y) + b10 * (v[3].y - v[1].y) + b01 * (v[6].y - v[4].y) + b11 * (v[7].y - v[5].y);
+      const float jz1 = c00 * (v[4].y - v[0].y) + c10 * (v[5].y - v[1].y) + c01 * (v[6].y - v[2].y) + c11 * (v[7].y - v[3].y);
+      *reinterpret_cast<float2*>(jac + 6 * i) = make_float2(sc * jx0, sc * jy0);
+      *reinterpret_cast<float2*>(jac + 6 * i + 2) = make_float2(sc * jz0, sc * jx1);
+      *reinterpret_cast<float2*>(jac + 6 * i + 4) = make_float2(sc * jy1, sc * jz1);
+    }
   }
   const int d_lo = half ? 2 : 0, d_hi = half ? 3 : 2;
   for (int d = d_lo; d < d_hi; ++d) {
@@ -1187,7 +1212,8 @@ __global__ void __launch_bounds__(GT * NGROUPS, 1) k_fused_g(const Params P, int
         zbuf[p] = zv;
         xnb[p * 3] = xn[0]; xnb[p * 3 + 1] = xn[1]; xnb[p * 3 + 2] = xn[2];
       }
-      encode_half(P, s_lv, xn, rec, half);
+      encode_half(P, s_lv, xn, rec, half,
+                  (need_dx && P.jac) ? P.jac + ((size_t)((size_t)r * S + k) * 2 + half) * 48 : nullptr);
     } else if (p < prev_npts) {
       // rows left dirty by a larger unit must read as zero in every GEMM
       float* z0 = rec + half * (REC / 2);
@@ -1422,6 +1448,8 @@ __global__ void __launch_bounds__(GT * NGROUPS, 1) k_fused_g(const Params P, int
     // d w_sdf0 += x^T dh1pre
     dw_phase(22, 42, R_FEAT, R_H1, 4);
     // (readers of C1 / GEO slots are done: dW phases 2 and 3 finished before the last barrier)
+    float cfeat[4][4];
+    zero_c1<4>(cfeat);
     if (warp_active) {
       if (need_dx) {
         // dblob = dc1pre Wc0[:, 0:48] + dh1pre W0[:, 32:80]  -> scratch (C1 slots 0..31, GEO 32..47)
@@ -1439,67 +1467,76 @@ __global__ void __launch_bounds__(GT * NGROUPS, 1) k_fused_g(const Params P, int
           *reinterpret_cast<float2*>(q0 + 8 * REC) = make_float2(c[nt][2], c[nt][3]);
         }
       }
-      float hdx[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-      if (map_grads || need_dx) {
-        // dfeat = dh1pre W0[:, 0:32]; lane (g,t) holds (f0,f1) of level 4*nt+t for rows g, g+8
-        float c[4][4];
-        zero_c1<4>(c);
-        warp_gemm1<4, 4, true, BPREC3>(wrec, R_H1, sw + SW0, LD0, 0, 0, c);
+      // dfeat = dh1pre W0[:, 0:32]
+      if (map_grads || need_dx) warp_gemm1<4, 4, true, BPREC3>(wrec, R_H1, sw + SW0, LD0, 0, 0, cfeat);
+    }
+    group_sync(grp);  // every warp is past the x^T dh1pre tiles: the FEAT slots are free
+    if (warp_active && (map_grads || need_dx)) store_c1<4, false>(wrec, R_FEAT, cfeat);
+    group_sync(grp);
+    // ---- hash backward, point-parallel and BALANCED: thread (pp, half) owns levels half, half+2, ..
+    // of point pp = every 6th point of the unit per warp (a ray's samples behind the surface carry
+    // no gradient: ray-major assignment would leave whole warps idle).  d loss / d xn comes from
+    // the Jacobian cached by the forward gather (no second gather); the table gradient is
+    // scattered with red.global.add.v2.
+    {
+      const int qd = gt >> 1;
+      const int pp = (qd & 15) * GW + (qd >> 4);
+      const bool act2 = pp < npts;
+      float* rec2 = recs + pp * REC;
+      float dxh[3] = {0.f, 0.f, 0.f};
+      float xq[3] = {0.f, 0.f, 0.f};
+      if (act2) { xq[0] = xnb[pp * 3]; xq[1] = xnb[pp * 3 + 1]; xq[2] = xnb[pp * 3 + 2]; }
+      if (act2 && (map_grads || need_dx)) {
+        const float* jp = (need_dx && P.jac) ? P.jac + ((size_t)((size_t)r0 * S + pp) * 2 + half) * 48 : nullptr;
+#pragma unroll 1
+        for (int i2 = 0; i2 < kL / 2; i2 += 2) {  // two levels per call: half + 2 i2, half + 2 i2 + 2
+          bool on[2];
+          float gg[2][2];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int row = gw * 16 + g + 8 * h;
-          if (row < npts) {
-            const float x0 = xnb[row * 3], x1 = xnb[row * 3 + 1], x2 = xnb[row * 3 + 2];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {  // levels t + 8 j, t + 8 j + 4
-              bool on[2];
-              float gg[2][2];
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int nt = 2 * j + e;
-                gg[e][0] = c[nt][2 * h]; gg[e][1] = c[nt][2 * h + 1];
-                on[e] = (4 * nt + t) < P.g.n_levels && (gg[e][0] != 0.f || gg[e][1] != 0.f);
-              }
-              if (on[0] || on[1]) {
-                const float3 d3 = hash_backward_multi<2>(P, s_lv, t + 8 * j, on, x0, x1, x2, gg,
-                                                         need_dx, map_grads);
-                hdx[h][0] += d3.x; hdx[h][1] += d3.y; hdx[h][2] += d3.z;
-              }
+          for (int e = 0; e < 2; ++e) {
+            const int l = half + 2 * (i2 + e);
+            const float2 gv = *reinterpret_cast<const float2*>(rec2 + R_FEAT + 2 * l);
+            gg[e][0] = gv.x; gg[e][1] = gv.y;
+            on[e] = l < P.g.n_levels && (gv.x != 0.f || gv.y != 0.f);
+            if (jp && on[e]) {
+              const float2 j0 = *reinterpret_cast<const float2*>(jp + 6 * (i2 + e));
+              const float2 j1 = *reinterpret_cast<const float2*>(jp + 6 * (i2 + e) + 2);
+              const float2 j2 = *reinterpret_cast<const float2*>(jp + 6 * (i2 + e) + 4);
+              dxh[0] = fmaf(gv.x, j0.x, fmaf(gv.y, j1.y, dxh[0]));
+              dxh[1] = fmaf(gv.x, j0.y, fmaf(gv.y, j2.x, dxh[1]));
+              dxh[2] = fmaf(gv.x, j1.x, fmaf(gv.y, j2.y, dxh[2]));
             }
+          }
+          if ((map_grads || (need_dx && !jp)) && (on[0] || on[1])) {
+            const float3 d3 = hash_backward_multi<2>(P, s_lv, half + 2 * i2, on, xq[0], xq[1], xq[2],
+                                                     gg, need_dx && !jp, map_grads, 2);
+            dxh[0] += d3.x; dxh[1] += d3.y; dxh[2] += d3.z;
           }
         }
       }
       if (need_dx) {
-        // reduce the hash-path dx over the 4 lanes (t) that share a row, park it in RAW[0..2]
+        // the two halves of a point are adjacent lanes: sum their level shares
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            float v = hdx[h][d];
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            if (t == 0) wrec[(g + 8 * h) * REC + R_RAW + d] = v;
-          }
-        __syncwarp();
-        // blob path + chain rule; half 0 owns x, y and half 1 owns z of the point
+        for (int d = 0; d < 3; ++d) dxh[d] += __shfl_xor_sync(0xffffffffu, dxh[d], 1);
         float dp0 = 0.f, dp1 = 0.f;
-        if (active) {
-          auto dblob = [&](int i) { return (i < 32) ? rec[R_C1 + i] : rec[R_GEO + i - 32]; };
+        if (act2) {
+          auto dblob = [&](int i) { return (i < 32) ? rec2[R_C1 + i] : rec2[R_GEO + i - 32]; };
           if (half == 0) {
-            dp0 = (float)((double)(blob_backward_dim(xn[0], 0, dblob) + rec[R_RAW + 0]) * P.g.binv[0]);
-            dp1 = (float)((double)(blob_backward_dim(xn[1], 1, dblob) + rec[R_RAW + 1]) * P.g.binv[1]);
+            dp0 = (float)((double)(blob_backward_dim(xq[0], 0, dblob) + dxh[0]) * P.g.binv[0]);
+            dp1 = (float)((double)(blob_backward_dim(xq[1], 1, dblob) + dxh[1]) * P.g.binv[1]);
           } else {
-            dp0 = (float)((double)(blob_backward_dim(xn[2], 2, dblob) + rec[R_RAW + 2]) * P.g.binv[2]);
+            dp0 = (float)((double)(blob_backward_dim(xq[2], 2, dblob) + dxh[2]) * P.g.binv[2]);
           }
         }
         __syncwarp();  // both halves have read the dblob scratch before C1[0..5] is reused
-        if (active) {
+        if (act2) {
+          const float zq = zbuf[pp];
           // park d loss / d pts and z * d loss / d pts in the (dead) C1 slots 0..5
           if (half == 0) {
-            rec[R_C1 + 0] = dp0; rec[R_C1 + 3] = dp0 * zv;
-            rec[R_C1 + 1] = dp1; rec[R_C1 + 4] = dp1 * zv;
+            rec2[R_C1 + 0] = dp0; rec2[R_C1 + 3] = dp0 * zq;
+            rec2[R_C1 + 1] = dp1; rec2[R_C1 + 4] = dp1 * zq;
           } else {
-            rec[R_C1 + 2] = dp0; rec[R_C1 + 5] = dp0 * zv;
+            rec2[R_C1 + 2] = dp0; rec2[R_C1 + 5] = dp0 * zq;
           }
         }
       }
@@ -1850,9 +1887,16 @@ static int fill_grid(GridDev& g, const XrdHashGrid* h) {
 using namespace xrd;
 using namespace xrd::coslam;
 
+// Jacobian cache of the grouped kernel: 2 halves x 8 levels x 6 floats per sample point.
+static constexpr size_t kJacBytesPerPoint = 2 * 48 * sizeof(float);
+static constexpr size_t kJacMaxBytes = (size_t)512 << 20;  // beyond this the backward re-gathers
+static size_t jac_bytes(int n_rays, int n_samples) {
+  const size_t b = (size_t)n_rays * n_samples * kJacBytesPerPoint;
+  return b <= kJacMaxBytes ? b : 0;
+}
 extern "C" size_t xrd_coslam_workspace_bytes(int n_rays, int n_samples) {
-  // [counts int[4] | loss_acc double[4] | z_vals R*S floats]
-  return 256 + align_up((size_t)n_rays * n_samples * sizeof(float), 256);
+  // [counts int[4] | loss_acc double[4] | z_vals R*S floats | Jacobian cache]
+  return 256 + align_up((size_t)n_rays * n_samples * sizeof(float), 256) + jac_bytes(n_rays, n_samples);
 }
 
 static int pick_rays_per_tile(int S, int requested) {
@@ -1937,11 +1981,17 @@ extern "C" int xrd_coslam_step(const XrdRays* rays, const XrdHashGrid* grid,
   } else {
     P.d_table = P.d_w_sdf0 = P.d_w_sdf1 = P.d_w_col0 = P.d_w_col1 = P.d_rays_o = P.d_rays_d = nullptr;
   }
+  P.jac = nullptr;
   const int sms = num_sms();
   if (cfg->rays_per_tile == 0 && S <= GP) {
     // grouped persistent kernel (k_fused_g): units of NR rays pulled from a queue
     P.NR = GP / S;
     P.n_tiles = (R + P.NR - 1) / P.NR;
+    static const bool no_jac = getenv("XRD_COSLAM_NO_JAC") != nullptr;  // A/B switch (profiling)
+    P.jac = (grads && (grads->d_rays_o || grads->d_rays_d) && jac_bytes(R, S) && !no_jac)
+                ? reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256 +
+                                           align_up((size_t)R * S * sizeof(float), 256))
+                : nullptr;
     int* queue = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + 128);  // zeroed above
     const size_t smem_g = sizeof(float) * ((size_t)SW_TOTAL + (size_t)NGROUPS * GP * (REC + 6));
     int gridx = (P.n_tiles + NGROUPS - 1) / NGROUPS;
