@@ -351,12 +351,12 @@ def run_ours(args):
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
     achieved = R * BYTES_PER_RAY / (k_ms * 1e-3) / 1e9
-    roofline = {'bound': 'hbm', 'kernel': 'xrd::coslam::k_fused<true>',
+    roofline = {'bound': 'hbm', 'kernel': 'xrd::coslam::k_fused_g<true> (grouped persistent fused kernel)',
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak,
                 'peak_source': 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback 6650',
                 # dram__bytes_read.sum + dram__bytes_write.sum of one 4096-ray launch
-                # (ncu --set full, profiles/r01_coslam_fused_v4_4096rays_ncu.txt)
+                # (ncu --set full, profiles/r02_coslam_fused_g_4096rays_ncu.txt)
                 'traffic': ncu_traffic(), 'kernel_ms': k_ms,
                 'algorithmic_bytes_per_launch': R * BYTES_PER_RAY,
                 'note': 'table (6.56 MB) is L2-resident: DRAM traffic is far below '
@@ -367,8 +367,24 @@ def run_ours(args):
     h2d = R * 7 * 4 + R * 8 + 128  # sampled rows + pose ids + per-iteration scalar block
     d2h = 4
     if use_graph:
+        # the session is asynchronous (pinned staging ring of depth 4, like CoSLAM's own mapping
+        # loop which never reads the loss): every step's loss is copied D2H into a pinned ring
+        # and read on the host two steps later, so host sampling + H2D of step i+1 overlap the
+        # graph of step i.  The final barrier()/synchronize closes the timed region.
+        loss_ring = [torch.zeros(1).pin_memory() for _ in range(4)]
+        loss_ev = [torch.cuda.Event() for _ in range(4)]
+        host_losses = []
+
         def e2e_step(i):
-            return sess.step(i, frames).item()  # H2D rows/ids/scalars, graph, D2H loss
+            lt = sess.step(i, frames)   # H2D rows/ids/scalars + the captured iteration
+            k = i % 4
+            loss_ring[k].copy_(lt.detach().reshape(1), non_blocking=True)  # D2H loss, every step
+            loss_ev[k].record()
+            j = i - 2
+            if j >= 0:
+                loss_ev[j % 4].synchronize()
+                host_losses.append(float(loss_ring[j % 4][0]))
+            return lt
     else:
         h2d = R * 7 * 4 + R * 8 + len(frames) * 16 * 4
 
@@ -433,6 +449,7 @@ def run_ours(args):
                        'l2': 'flushed between timed steps (256 MB write); ray batches differ every step'},
             'e2e': {'value': e2e_value, 'unit': 'rays/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h,
+                    'loss_readback': 'async D2H into a pinned ring every step, consumed by the host 2 steps later',
                     'path': ('CoSLAM.mapping_session(frames).step(): host pinned ray bank, '
                              'random.sample, H2D, one CUDA graph (poses, rays, sample, fused '
                              'fwd/loss/bwd, smoothness, pose grads, Adam)' +

@@ -198,7 +198,9 @@ typedef struct {
   const float* lin_nodepth;  /* [n_range_d]   linspace(near, far)             */
   const float* lin_full;     /* [n_samples]   used when target_d == NULL      */
   uint64_t seed;             /* Philox seed when noise == NULL                */
-  int rays_per_tile;         /* 0 = library default                           */
+  int rays_per_tile;         /* 0 = automatic (grouped kernel for large gradient
+                              * batches, tile kernel otherwise); -1 = tile kernel,
+                              * -2 = grouped kernel, > 0 = tile kernel, rays/tile */
   int precision;             /* decoder GEMMs on the tensor cores:
                               * 0 = 3xTF32 everywhere (fp32-level accuracy),
                               * 1 = 3xTF32 forward (outputs/losses fp32-level),

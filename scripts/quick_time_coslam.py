@@ -8,7 +8,7 @@ import os
 _, model = coslam_pair(dev, table_amp=1e-2, precision=int(os.environ.get("XRD_PREC", "0")))
 for R in [1024, 4096, 16384, 65536]:
     for nr in ([0] if len(sys.argv) < 2 else [int(a) for a in sys.argv[1:]]):
-        model.config.rays_per_tile = nr
+        model.config.rays_per_tile = nr  # 0 auto, -1 tile kernel, -2 grouped kernel
         rays_o, rays_d, ts, td, noise = make_rays(R, seed=1)
         inp = dict(rays_o=rays_o.to(dev), rays_d=rays_d.to(dev), target_s=ts.to(dev), target_d=td.to(dev), first=True)
         w = model._weights()

@@ -41,9 +41,12 @@ def test_hash_indices_bit_exact(cuda_dev):
     assert max_abs(feat, f_o) < 1e-6
 
 
+# rays_per_tile: -1 = tile kernel (k_fused), -2 = grouped persistent kernel (k_fused_g); the
+# library's automatic choice (0) picks between the two by batch size
+@pytest.mark.parametrize('kernel', [-1, -2])
 @pytest.mark.parametrize('R', [1, 5, 257, 1024])
-def test_step_parity(cuda_dev, R):
-    ora, model = coslam_pair(cuda_dev)
+def test_step_parity(cuda_dev, R, kernel):
+    ora, model = coslam_pair(cuda_dev, rays_per_tile=kernel)
     rays_o, rays_d, ts, td, noise = make_rays(R, seed=R)
     rays_o.requires_grad_(True)
     rays_d.requires_grad_(True)
@@ -196,9 +199,10 @@ def test_step_parity_tf32_mode(cuda_dev):
     assert cos > 0.995
 
 
-def test_tracking_pose_only(cuda_dev):
+@pytest.mark.parametrize('kernel', [-1, -2])
+def test_tracking_pose_only(cuda_dev, kernel):
     """freeze_map_grads: only d loss / d rays is produced (tracking)."""
-    ora, model = coslam_pair(cuda_dev)
+    ora, model = coslam_pair(cuda_dev, rays_per_tile=kernel)
     model.freeze_map_grads = True
     rays_o, rays_d, ts, td, noise = make_rays(200, seed=4)
     rays_o.requires_grad_(True)
@@ -216,13 +220,14 @@ def test_tracking_pose_only(cuda_dev):
     assert rel_err(rd.grad, rays_d.grad) < TOL_GRAD
 
 
-def test_cuda_matches_reference_golden(cuda_dev):
+@pytest.mark.parametrize('kernel', [-1, -2])
+def test_cuda_matches_reference_golden(cuda_dev, kernel):
     """CUDA path vs vectors produced by the reference's own JointEncoding class."""
     from helpers import load_golden_coslam, set_coslam_params
     from xrdslam_b200.camera import Camera
     from xrdslam_b200.joint_encoding import JointEncodingConfig
     g = load_golden_coslam()
-    model = JointEncodingConfig().setup(camera=Camera(320., 320., 319.5, 239.5, 640, 480),
+    model = JointEncodingConfig(rays_per_tile=kernel).setup(camera=Camera(320., 320., 319.5, 239.5, 640, 480),
                                         bounding_box=BOUND)
     set_coslam_params(model, g, 'model')
     model.to(cuda_dev)

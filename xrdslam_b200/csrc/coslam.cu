@@ -1887,10 +1887,19 @@ static int fill_grid(GridDev& g, const XrdHashGrid* h) {
 using namespace xrd;
 using namespace xrd::coslam;
 
-// Jacobian cache of the grouped kernel: 2 halves x 8 levels x 6 floats per sample point.
+// Optional Jacobian cache of the grouped kernel (2 halves x 8 levels x 6 floats per sample point):
+// the forward gather stores d feat / d xn so that the backward needs no second gather for the ray
+// gradients.  Measured on B200 (profiles/r02_coslam_kernel_ab.txt) it LOSES 2-4 % against
+// re-gathering (the table is L2-resident, the cache is 384 B/point of extra traffic), so it is
+// off unless XRD_COSLAM_JAC is set; kept for tables that outgrow L2.
 static constexpr size_t kJacBytesPerPoint = 2 * 48 * sizeof(float);
 static constexpr size_t kJacMaxBytes = (size_t)512 << 20;  // beyond this the backward re-gathers
+static bool jac_enabled() {
+  static const bool on = getenv("XRD_COSLAM_JAC") != nullptr;
+  return on;
+}
 static size_t jac_bytes(int n_rays, int n_samples) {
+  if (!jac_enabled()) return 0;
   const size_t b = (size_t)n_rays * n_samples * kJacBytesPerPoint;
   return b <= kJacMaxBytes ? b : 0;
 }
@@ -1983,12 +1992,21 @@ extern "C" int xrd_coslam_step(const XrdRays* rays, const XrdHashGrid* grid,
   }
   P.jac = nullptr;
   const int sms = num_sms();
-  if (cfg->rays_per_tile == 0 && S <= GP) {
+  // Kernel choice (rays_per_tile: 0 = automatic, -1 = tile kernel, -2 = grouped kernel, > 0 = tile
+  // kernel with that many rays per tile).  Automatic: the grouped kernel wins the gradient pass
+  // once every group has >= 1 unit in flight after the first wave (R = 4096: 436 vs 459 us,
+  // 16384: 1461 vs 1607, 65536: 5629 vs 6230); the tile kernel wins small batches (tracking,
+  // R = 1024: 182 vs 204 us) and forward-only rendering (160 vs 182 us at 4096 rays).
+  bool grouped = false;
+  if (S <= GP) {
+    const int units = (R + GP / S - 1) / (GP / S);
+    grouped = cfg->rays_per_tile == -2 || (cfg->rays_per_tile == 0 && grads && units >= 4 * sms);
+  }
+  if (grouped) {
     // grouped persistent kernel (k_fused_g): units of NR rays pulled from a queue
     P.NR = GP / S;
     P.n_tiles = (R + P.NR - 1) / P.NR;
-    static const bool no_jac = getenv("XRD_COSLAM_NO_JAC") != nullptr;  // A/B switch (profiling)
-    P.jac = (grads && (grads->d_rays_o || grads->d_rays_d) && jac_bytes(R, S) && !no_jac)
+    P.jac = (grads && (grads->d_rays_o || grads->d_rays_d) && jac_bytes(R, S))
                 ? reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256 +
                                            align_up((size_t)R * S * sizeof(float), 256))
                 : nullptr;

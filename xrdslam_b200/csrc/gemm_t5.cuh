@@ -18,6 +18,12 @@
 //      4 k-values of a point from 4 rows and writes one 16-byte chunk: conflict-free).
 //   D: 128 lanes x BN fp32 columns of TMEM, two accumulators, so the epilogue of tile i overlaps
 //      the MMAs of tile i+1.
+// Revision 2 (V2 = true, the default): BN = 128 so that the resident weights leave room for a
+// 3-deep TMA / operand ring and a per-warp transposition tile in the epilogue -- every global
+// access of the epilogue (C, relu mask, addend, act_out) is then a 128-byte row segment per warp
+// instruction instead of 32 rows x 16 bytes; the weight staging reads 8 rows x 16 bytes per
+// warp instruction instead of 32 rows x 4 bytes.  Revision 1 stays selectable
+// (xrd_debug_gemm_variant bit 1) for A/B timing.
 // Roles (384 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected
 // lane), warps 4-7 = epilogue (tcgen05.ld 32x32b, bias / activation / mask / addend, 128-byte
 // row stores), warps 8-11 = splitter.  All hand-offs are mbarriers; every wait is bounded (a
@@ -32,7 +38,7 @@ namespace t5 {
 
 constexpr int BM = 128, BK = 16;
 constexpr int NTHREADS = 384;
-constexpr int RAW_STAGES = 2, OP_STAGES = 2;
+constexpr int EPI_LD = 33;  // per-warp transposition tile [32][33] floats (V2 epilogue)
 constexpr uint32_t SPIN_LIMIT = 1u << 27;
 
 struct Params {
@@ -154,9 +160,10 @@ __host__ __device__ constexpr uint32_t make_idesc() {
 
 __device__ __forceinline__ float tf32_big(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
-template <int BN>
+template <int BN, int STAGES, bool V2>
 static __global__ void __launch_bounds__(NTHREADS, 1)
 k_gemm_t5(const __grid_constant__ CUtensorMap tmap_b, const Params P) {
+  constexpr int RAW_STAGES = STAGES, OP_STAGES = STAGES;
   constexpr int RAW_BYTES = BK * BN * 4;  // one TMA box: BK rows x BN points, row-major
   constexpr int OP_BYTES = BK * BN * 4;   // the same tile in the K-major operand layout
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -168,32 +175,52 @@ k_gemm_t5(const __grid_constant__ CUtensorMap tmap_b, const Params P) {
   float* a_small = reinterpret_cast<float*>(smem + a_bytes);
   uint8_t* raw_base = smem + 2 * a_bytes;                       // [RAW_STAGES][RAW_BYTES]
   uint8_t* op_base = raw_base + RAW_STAGES * RAW_BYTES;         // [OP_STAGES][big | small]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(op_base + OP_STAGES * 2 * OP_BYTES);
-  uint64_t* full = bars;            // [RAW_STAGES] TMA bytes landed
-  uint64_t* rawfree = bars + 2;     // [RAW_STAGES] raw tile consumed by the splitter (128 arrivals)
-  uint64_t* split = bars + 4;       // [OP_STAGES]  big / small operand tiles ready (128 arrivals)
-  uint64_t* empty = bars + 6;       // [OP_STAGES]  MMAs that read the operand tiles are complete
-  uint64_t* tfull = bars + 8;       // [2]  accumulator complete
-  uint64_t* tempty = bars + 10;     // [2]  accumulator drained (128 epilogue arrivals)
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 12);
+  float* epi = reinterpret_cast<float*>(op_base + OP_STAGES * 2 * OP_BYTES);  // V2: [4][32][EPI_LD]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(op_base + OP_STAGES * 2 * OP_BYTES +
+                                               (V2 ? 4 * 32 * EPI_LD * 4 : 0));
+  uint64_t* full = bars;                    // [STAGES] TMA bytes landed
+  uint64_t* rawfree = bars + STAGES;        // [STAGES] raw tile consumed by the splitter (128 arrivals)
+  uint64_t* split = bars + 2 * STAGES;      // [STAGES] big / small operand tiles ready (128 arrivals)
+  uint64_t* empty = bars + 3 * STAGES;      // [STAGES] MMAs that read the operand tiles are complete
+  uint64_t* tfull = bars + 4 * STAGES;      // [2]  accumulator complete
+  uint64_t* tempty = bars + 4 * STAGES + 2; // [2]  accumulator drained (128 epilogue arrivals)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 4 * STAGES + 4);
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(full + s, 1); mbar_init(rawfree + s, 128); mbar_init(split + s, 128);
-      mbar_init(empty + s, 1); mbar_init(tfull + s, 1); mbar_init(tempty + s, 128);
+      mbar_init(empty + s, 1);
     }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 128); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_holder, 2 * BN);
   // ---- stage the weights once: A(m,k) -> canonical K-major core-matrix layout, big / small
-  for (int e = tid; e < BM * Kpad; e += NTHREADS) {
-    const int m = e % BM, k = e / BM;
-    float v = 0.f;
-    if (m < G.M && k < G.K) v = G.transA ? G.A[(size_t)k * G.lda + m] : G.A[(size_t)m * G.lda + k];
-    const float big = tf32_big(v);
-    const int off = (k >> 2) * (BM * 4) + m * 4 + (k & 3);
-    a_big[off] = big;
-    a_small[off] = v - big;
+  if (V2) {
+    // lane = (m & 7) | (k & 3) << 3: conflict-free shared-memory writes (32 consecutive floats),
+    // 8 rows x 16 bytes (row-major A) or 4 rows x 32 bytes (transposed A) per global request
+    const int n_e = BM * Kpad;
+    for (int e = tid; e < n_e; e += NTHREADS) {
+      const int hi = e >> 5, lo = e & 31;
+      const int m = ((hi % (BM / 8)) << 3) | (lo & 7);
+      const int k = ((hi / (BM / 8)) << 2) | (lo >> 3);
+      float v = 0.f;
+      if (m < G.M && k < G.K) v = G.transA ? G.A[(size_t)k * G.lda + m] : G.A[(size_t)m * G.lda + k];
+      const float big = tf32_big(v);
+      const int off = (k >> 2) * (BM * 4) + m * 4 + (k & 3);
+      a_big[off] = big;
+      a_small[off] = v - big;
+    }
+  } else {
+    for (int e = tid; e < BM * Kpad; e += NTHREADS) {
+      const int m = e % BM, k = e / BM;
+      float v = 0.f;
+      if (m < G.M && k < G.K) v = G.transA ? G.A[(size_t)k * G.lda + m] : G.A[(size_t)m * G.lda + k];
+      const float big = tf32_big(v);
+      const int off = (k >> 2) * (BM * 4) + m * 4 + (k & 3);
+      a_big[off] = big;
+      a_small[off] = v - big;
+    }
   }
   fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
   tc_fence_before();
@@ -301,6 +328,31 @@ k_gemm_t5(const __grid_constant__ CUtensorMap tmap_b, const Params P) {
         float v[32];
         tmem_ld32(t0 + c * 32, v);
         const int nb = n0 + c * 32;
+        if (V2) {
+          // bias + activation by the row owner, then transpose through the warp's private tile:
+          // lane j then owns column nb + j of the quadrant's 32 rows -> 128-byte row segments
+          float* S = epi + (warp & 3) * (32 * EPI_LD);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) S[lane * EPI_LD + j] = act_apply(v[j] + bias, G.act);
+          __syncwarp();
+          const int col = nb + lane;
+          const bool ok = col < G.N;
+          const int rows = min(32, G.M - q * 32);  // warp-uniform
+#pragma unroll 4
+          for (int r = 0; r < rows; ++r) {
+            const int mr = q * 32 + r;
+            float x = S[r * EPI_LD + lane];
+            if (ok) {
+              if (G.relu_mask && !(G.relu_mask[(size_t)mr * G.ldmask + col] > 0.f)) x = 0.f;
+              if (G.act_out) G.act_out[(size_t)mr * G.ldact + col] = x;
+              if (G.addend) x += G.addend[(size_t)mr * G.ldadd + col];
+              float* cp = G.C + (size_t)mr * G.ldc + col;
+              *cp = G.accumulate ? (*cp + x) : x;
+            }
+          }
+          __syncwarp();  // tile reused by the next chunk; tcgen05.ld is warp-collective
+          continue;
+        }
         if (row_ok && nb < G.N) {
           const int nv = min(32, G.N - nb);
 #pragma unroll
@@ -376,7 +428,7 @@ static inline bool eligible(const GemmArgs& G) {
 
 extern thread_local int g_t5_variant;
 
-template <int BN>
+template <int BN, int STAGES, bool V2>
 static inline cudaError_t launch_bn(const GemmArgs& G, cudaStream_t stream) {
   Params P;
   P.G = G;
@@ -394,22 +446,27 @@ static inline cudaError_t launch_bn(const GemmArgs& G, cudaStream_t stream) {
                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
-  const size_t smem = 2 * (size_t)BM * P.Kpad * 4 + (size_t)RAW_STAGES * BK * BN * 4 +
-                      (size_t)OP_STAGES * 2 * BK * BN * 4 + 256;
+  const size_t smem = 2 * (size_t)BM * P.Kpad * 4 + (size_t)STAGES * 3 * BK * BN * 4 +
+                      (V2 ? 4 * 32 * EPI_LD * 4 : 0) + 256;
+  if (smem > 232448) return cudaErrorInvalidValue;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_t5<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_t5<BN, STAGES, V2>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   int grid = P.n_tiles < num_sms() ? P.n_tiles : num_sms();
-  k_gemm_t5<BN><<<grid, NTHREADS, smem, stream>>>(tm, P);
+  k_gemm_t5<BN, STAGES, V2><<<grid, NTHREADS, smem, stream>>>(tm, P);
   return cudaGetLastError();
 }
 
 static inline cudaError_t launch(const GemmArgs& G, cudaStream_t stream) {
-  // resident weights (big + small) + 2 raw + 2 x 2 operand stages must fit 227 KB
-  return G.K > 128 ? launch_bn<128>(G, stream) : launch_bn<256>(G, stream);
+  // resident weights (big + small, 2 x 128 x Kpad x 4 B) + STAGES x (raw + big + small operand
+  // tiles) (+ the epilogue transposition tiles) must fit 227 KB
+  if (g_t5_variant & 2)  // revision 1 (A/B timing only)
+    return G.K > 128 ? launch_bn<128, 2, false>(G, stream) : launch_bn<256, 2, false>(G, stream);
+  return G.K > 128 ? launch_bn<128, 2, true>(G, stream) : launch_bn<128, 3, true>(G, stream);
 }
 
 }  // namespace t5

@@ -76,7 +76,7 @@ class JointEncodingConfig(ModelConfig):
     # --- B200 path knobs (not in the reference) ---
     seed: int = 0  # Philox seed for in-kernel jitter when no noise is passed
     strict_loss_grad: bool = False  # verify upstream d(total)/d(term) == 1
-    rays_per_tile: int = 0
+    rays_per_tile: int = 0   # 0 automatic, -1 tile kernel (k_fused), -2 grouped kernel (k_fused_g)
     # decoder GEMMs on tensor cores: 0 = 3xTF32 everywhere (fp32-level parity),
     # 1 = 3xTF32 forward + TF32 backward, 2 = TF32 everywhere
     precision: int = 0
