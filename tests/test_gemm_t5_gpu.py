@@ -48,6 +48,7 @@ def run(dev, M, N, K, transA, act, mode, mask=False, addend=False, seed=0):
     (128, 2048, 129, 1, 0),      # backward through sdf_out (transposed weights, K = 129)
     (144, 3000, 128, 1, 0),      # 144 rows = 128 (tcgen05) + 16 (mma.sync)
     (64, 1024, 128, 0, 3),       # M < 128 (zero-padded rows)
+    (32, 3000, 128, 0, 0),       # Point-SLAM 128 -> 32 neighbour layer
     (128, 150000, 128, 0, 1),    # benchmark-sized point count
 ])
 def test_gemm_t5_matches_float64(cuda_dev, M, N, K, transA, act):

@@ -18,12 +18,17 @@
 //      4 k-values of a point from 4 rows and writes one 16-byte chunk: conflict-free).
 //   D: 128 lanes x BN fp32 columns of TMEM, two accumulators, so the epilogue of tile i overlaps
 //      the MMAs of tile i+1.
-// Revision 2 (V2 = true, the default): BN = 128 so that the resident weights leave room for a
-// 3-deep TMA / operand ring and a per-warp transposition tile in the epilogue -- every global
-// access of the epilogue (C, relu mask, addend, act_out) is then a 128-byte row segment per warp
-// instruction instead of 32 rows x 16 bytes; the weight staging reads 8 rows x 16 bytes per
-// warp instruction instead of 32 rows x 4 bytes.  Revision 1 stays selectable
-// (xrd_debug_gemm_variant bit 1) for A/B timing.
+// Revision 2 (V2 = true, the default) came out of the ncu capture of revision 1
+// (profiles/r02_gemm_t5_ncu.txt): the kernel was EPILOGUE-bound -- the MMA warp spent 40 % of its
+// time waiting for a drained accumulator, the epilogue warps stalled on instruction fetch
+// (4 056 SASS instructions: a `switch (act)` with an inlined expf per element, scalar tail-guarded
+// mask / addend loops) and on the tcgen05.ld round trip -- and the weight staging cost 17 of
+// 96 us (32 rows x 4 bytes per load instruction, each load waited for before the next).  Now:
+// the steady-state epilogue is a compact vector path (bias + relu as one FADD + FMNMX, the
+// mask / addend / act_out rows as 16-byte accesses, the next 32 columns' tcgen05.ld in flight
+// while the current ones are processed); tails, unaligned rows and sigmoid take the old path.
+// The weights are staged 8 loads at a time, 8 rows x 16 bytes per instruction.  Revision 1 stays
+// selectable (xrd_debug_gemm_variant bit 1) for A/B timing.
 // Roles (384 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected
 // lane), warps 4-7 = epilogue (tcgen05.ld 32x32b, bias / activation / mask / addend, 128-byte
 // row stores), warps 8-11 = splitter.  All hand-offs are mbarriers; every wait is bounded (a
@@ -38,7 +43,6 @@ namespace t5 {
 
 constexpr int BM = 128, BK = 16;
 constexpr int NTHREADS = 384;
-constexpr int EPI_LD = 33;  // per-warp transposition tile [32][33] floats (V2 epilogue)
 constexpr uint32_t SPIN_LIMIT = 1u << 27;
 
 struct Params {
@@ -137,6 +141,87 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// the same load split into issue and wait, so that a second load can be in flight while the
+// first one's registers are consumed; the wait names the registers as in/out operands so that no
+// use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]),
+                 "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]),
+                 "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]),
+                 "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]),
+                 "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
+// steady-state epilogue of one 32-column chunk of row m (all row pointers 16-byte aligned, the
+// chunk entirely inside N): C = [mask](max(acc + bias, floor)) [+ addend], act_out before addend
+__device__ __forceinline__ void epi_fast(const GemmArgs& G, const uint32_t (&r)[32], int m, int nb,
+                                         float bias, float floorv) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[j]) + bias, floorv);
+  if (G.act == ACT_SOFTPLUS100) {
+    // nn.Softplus(beta = 100) on the SFU (ex2 / lg2): log(1 + e^{100 v}) / 100 with an absolute
+    // error below 3e-8 (the accurate expf / log1pf pair is ~40 instructions per element and
+    // thrashes the instruction cache when unrolled 32 times)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float t = v[j] * 100.f;
+      v[j] = (t > 20.f) ? v[j] : __logf(1.f + __expf(t)) * 0.01f;
+    }
+  }
+  if (G.relu_mask) {
+    const float4* mk = reinterpret_cast<const float4*>(G.relu_mask + (size_t)m * G.ldmask + nb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 k4 = mk[j];
+      if (!(k4.x > 0.f)) v[4 * j] = 0.f;
+      if (!(k4.y > 0.f)) v[4 * j + 1] = 0.f;
+      if (!(k4.z > 0.f)) v[4 * j + 2] = 0.f;
+      if (!(k4.w > 0.f)) v[4 * j + 3] = 0.f;
+    }
+  }
+  if (G.act_out) {
+    float4* ao = reinterpret_cast<float4*>(G.act_out + (size_t)m * G.ldact + nb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ao[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+  if (G.addend) {
+    const float4* ad = reinterpret_cast<const float4*>(G.addend + (size_t)m * G.ldadd + nb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 a4 = ad[j];
+      v[4 * j] += a4.x; v[4 * j + 1] += a4.y; v[4 * j + 2] += a4.z; v[4 * j + 3] += a4.w;
+    }
+  }
+  float4* cp = reinterpret_cast<float4*>(G.C + (size_t)m * G.ldc + nb);
+  if (G.accumulate) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 c4 = cp[j];
+      cp[j] = make_float4(c4.x + v[4 * j], c4.y + v[4 * j + 1], c4.z + v[4 * j + 2], c4.w + v[4 * j + 3]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+}
+
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading / stride
 // byte offsets (16-byte units), Blackwell version field = 1, layout type (0 = no swizzle,
 // 2 = 128-byte swizzle) in bits [61,64)
@@ -175,9 +260,7 @@ k_gemm_t5(const __grid_constant__ CUtensorMap tmap_b, const Params P) {
   float* a_small = reinterpret_cast<float*>(smem + a_bytes);
   uint8_t* raw_base = smem + 2 * a_bytes;                       // [RAW_STAGES][RAW_BYTES]
   uint8_t* op_base = raw_base + RAW_STAGES * RAW_BYTES;         // [OP_STAGES][big | small]
-  float* epi = reinterpret_cast<float*>(op_base + OP_STAGES * 2 * OP_BYTES);  // V2: [4][32][EPI_LD]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(op_base + OP_STAGES * 2 * OP_BYTES +
-                                               (V2 ? 4 * 32 * EPI_LD * 4 : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(op_base + OP_STAGES * 2 * OP_BYTES);
   uint64_t* full = bars;                    // [STAGES] TMA bytes landed
   uint64_t* rawfree = bars + STAGES;        // [STAGES] raw tile consumed by the splitter (128 arrivals)
   uint64_t* split = bars + 2 * STAGES;      // [STAGES] big / small operand tiles ready (128 arrivals)
@@ -198,18 +281,34 @@ k_gemm_t5(const __grid_constant__ CUtensorMap tmap_b, const Params P) {
   // ---- stage the weights once: A(m,k) -> canonical K-major core-matrix layout, big / small
   if (V2) {
     // lane = (m & 7) | (k & 3) << 3: conflict-free shared-memory writes (32 consecutive floats),
-    // 8 rows x 16 bytes (row-major A) or 4 rows x 32 bytes (transposed A) per global request
+    // 8 rows x 16 bytes (row-major A) or 4 rows x 32 bytes (transposed A) per global request;
+    // 8 independent loads in flight per thread
     const int n_e = BM * Kpad;
-    for (int e = tid; e < n_e; e += NTHREADS) {
-      const int hi = e >> 5, lo = e & 31;
-      const int m = ((hi % (BM / 8)) << 3) | (lo & 7);
-      const int k = ((hi / (BM / 8)) << 2) | (lo >> 3);
-      float v = 0.f;
-      if (m < G.M && k < G.K) v = G.transA ? G.A[(size_t)k * G.lda + m] : G.A[(size_t)m * G.lda + k];
-      const float big = tf32_big(v);
-      const int off = (k >> 2) * (BM * 4) + m * 4 + (k & 3);
-      a_big[off] = big;
-      a_small[off] = v - big;
+    for (int e0 = tid; e0 < n_e; e0 += NTHREADS * 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = e0 + u * NTHREADS;
+        const int hi = e >> 5, lo = e & 31;
+        const int m = ((hi % (BM / 8)) << 3) | (lo & 7);
+        const int k = ((hi / (BM / 8)) << 2) | (lo >> 3);
+        v[u] = 0.f;
+        if (e < n_e && m < G.M && k < G.K)
+          v[u] = G.transA ? G.A[(size_t)k * G.lda + m] : G.A[(size_t)m * G.lda + k];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = e0 + u * NTHREADS;
+        if (e < n_e) {
+          const int hi = e >> 5, lo = e & 31;
+          const int m = ((hi % (BM / 8)) << 3) | (lo & 7);
+          const int k = ((hi / (BM / 8)) << 2) | (lo >> 3);
+          const float big = tf32_big(v[u]);
+          const int off = (k >> 2) * (BM * 4) + m * 4 + (k & 3);
+          a_big[off] = big;
+          a_small[off] = v[u] - big;
+        }
+      }
     }
   } else {
     for (int e = tid; e < BM * Kpad; e += NTHREADS) {
@@ -316,6 +415,10 @@ k_gemm_t5(const __grid_constant__ CUtensorMap tmap_b, const Params P) {
     const bool row_ok = m < G.M;
     const float bias = (row_ok && G.bias) ? G.bias[m] : 0.f;
     const bool vec = ((G.ldc & 3) == 0) && ((((uintptr_t)G.C) & 15) == 0);
+    auto row16 = [](const float* p, int ld) { return !p || (((ld & 3) == 0) && ((((uintptr_t)p) & 15) == 0)); };
+    const bool fast = vec && G.act != ACT_SIGMOID && row16(G.relu_mask, G.ldmask) &&  // NONE / RELU / SOFTPLUS100
+                      row16(G.addend, G.ldadd) && row16(G.act_out, G.ldact);
+    const float floorv = (G.act == ACT_RELU) ? 0.f : -INFINITY;  // relu as max(v, 0), none as max(v, -inf)
     int lt = 0;
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++lt) {
       const int acc = lt & 1;
@@ -323,36 +426,29 @@ k_gemm_t5(const __grid_constant__ CUtensorMap tmap_b, const Params P) {
       tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * BN;
       const int n0 = tile * BN;
+      if (V2 && fast && n0 + BN <= G.N) {
+        // steady state: full tile, 16-byte aligned rows, no sigmoid.  Two register buffers: the
+        // tcgen05.ld of the next 32 columns is in flight while this chunk is processed.
+        uint32_t ra[32], rb[32];
+        tmem_ld32_issue(t0, ra);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; c += 2) {
+          tmem_ld32_wait(ra);
+          tmem_ld32_issue(t0 + (c + 1) * 32, rb);
+          if (row_ok) epi_fast(G, ra, m, n0 + c * 32, bias, floorv);
+          tmem_ld32_wait(rb);
+          if (c + 2 < BN / 32) tmem_ld32_issue(t0 + (c + 2) * 32, ra);
+          if (row_ok) epi_fast(G, rb, m, n0 + (c + 1) * 32, bias, floorv);
+        }
+        tc_fence_before();
+        mbar_arrive(tempty + acc);
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         float v[32];
         tmem_ld32(t0 + c * 32, v);
         const int nb = n0 + c * 32;
-        if (V2) {
-          // bias + activation by the row owner, then transpose through the warp's private tile:
-          // lane j then owns column nb + j of the quadrant's 32 rows -> 128-byte row segments
-          float* S = epi + (warp & 3) * (32 * EPI_LD);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) S[lane * EPI_LD + j] = act_apply(v[j] + bias, G.act);
-          __syncwarp();
-          const int col = nb + lane;
-          const bool ok = col < G.N;
-          const int rows = min(32, G.M - q * 32);  // warp-uniform
-#pragma unroll 4
-          for (int r = 0; r < rows; ++r) {
-            const int mr = q * 32 + r;
-            float x = S[r * EPI_LD + lane];
-            if (ok) {
-              if (G.relu_mask && !(G.relu_mask[(size_t)mr * G.ldmask + col] > 0.f)) x = 0.f;
-              if (G.act_out) G.act_out[(size_t)mr * G.ldact + col] = x;
-              if (G.addend) x += G.addend[(size_t)mr * G.ldadd + col];
-              float* cp = G.C + (size_t)mr * G.ldc + col;
-              *cp = G.accumulate ? (*cp + x) : x;
-            }
-          }
-          __syncwarp();  // tile reused by the next chunk; tcgen05.ld is warp-collective
-          continue;
-        }
         if (row_ok && nb < G.N) {
           const int nv = min(32, G.N - nb);
 #pragma unroll
@@ -422,7 +518,7 @@ static inline EncodeTiledFn encode_fn() {
 
 // shapes this kernel takes (everything else stays on k_gemm_tc / k_gemm)
 static inline bool eligible(const GemmArgs& G) {
-  return G.M >= 64 && G.M <= BM && G.K >= 16 && G.K <= 144 && G.N >= 512 && (G.ldb & 3) == 0 &&
+  return G.M >= 16 && G.M <= BM && G.K >= 16 && G.K <= 144 && G.N >= 512 && (G.ldb & 3) == 0 &&
          ((((uintptr_t)G.B) & 15) == 0) && encode_fn() != nullptr;
 }
 
@@ -447,7 +543,7 @@ static inline cudaError_t launch_bn(const GemmArgs& G, cudaStream_t stream) {
                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
   const size_t smem = 2 * (size_t)BM * P.Kpad * 4 + (size_t)STAGES * 3 * BK * BN * 4 +
-                      (V2 ? 4 * 32 * EPI_LD * 4 : 0) + 256;
+                      256;
   if (smem > 232448) return cudaErrorInvalidValue;
   static bool attr_set = false;
   if (!attr_set) {
@@ -466,7 +562,7 @@ static inline cudaError_t launch(const GemmArgs& G, cudaStream_t stream) {
   // tiles) (+ the epilogue transposition tiles) must fit 227 KB
   if (g_t5_variant & 2)  // revision 1 (A/B timing only)
     return G.K > 128 ? launch_bn<128, 2, false>(G, stream) : launch_bn<256, 2, false>(G, stream);
-  return G.K > 128 ? launch_bn<128, 2, true>(G, stream) : launch_bn<128, 3, true>(G, stream);
+  return G.K > 128 ? launch_bn<128, 2, true>(G, stream) : launch_bn<256, 2, true>(G, stream);
 }
 
 }  // namespace t5
@@ -488,12 +584,12 @@ static inline cudaError_t launch_gemm(const GemmArgs& G, cudaStream_t stream) {
   if (G.M <= 0 || G.N <= 0) return cudaSuccess;
   if (g_gemm_mode == 1) {
     if (t5::eligible(G)) return t5::launch(G, stream);
-    if (G.M > t5::BM) {  // e.g. 144 = 128 (tcgen05) + 16 (mma.sync)
+    if (G.M > t5::BM) {  // e.g. 144 = 128 + 16 rows: two launches
       GemmArgs top = gemm_rows(G, 0, t5::BM);
       if (t5::eligible(top)) {
         cudaError_t e = t5::launch(top, stream);
         if (e != cudaSuccess) return e;
-        return launch_gemm_legacy(gemm_rows(G, t5::BM, G.M - t5::BM), stream);
+        return launch_gemm(gemm_rows(G, t5::BM, G.M - t5::BM), stream);
       }
     }
   }
