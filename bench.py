@@ -455,16 +455,16 @@ def run_ours(args):
                              'fwd/loss/bwd, smoothness, pose grads, Adam)' +
                              ((' with the 2 NCCL all-reduces captured inside it' if getattr(sess, 'single_graph', True)
                                else ' in 3 captured segments around 2 NCCL all-reduces') if world > 1 else '') +
-                             ', loss.item()')
+                             ', async D2H of the loss')
                     if use_graph else
                     ('CoSLAM.get_loss (host pinned ray bank, random.sample, H2D) -> '
                      'loss.backward -> all-reduce -> Optimizers.optimizer_step_all -> loss.item()')},
             'gpu_launches': K * ((11 if world == 1 else 12) if use_graph else 9) + (K // 5 if use_graph else 0),
             'gpu_launches_note': ('per step (one graph): pose::k_fwd, rays::k_fwd, k_sample, '
-                                  'k_fused<true>, k_finalize, k_smooth_fwd, k_smooth_bwd, '
+                                  'k_fused_g<true>, k_finalize, k_smooth_fwd, k_smooth_bwd, '
                                   'k_smooth_finalize, rays::k_bwd, pose::k_bwd, k_adam (+ k_adam on '
                                   'the poses every 5th step)') if use_graph else
-                                 ('per step: rays::k_fwd, k_sample, k_fused<true>, k_finalize, '
+                                 ('per step: rays::k_fwd, k_sample, k_fused_g<true>, k_finalize, '
                                   'k_smooth_fwd/bwd/finalize, rays::k_bwd, k_adam x2 (torch glue '
                                   'not counted)'),
             'clocks': clk, 'roofline': roofline, 'cpu_baseline': cpu,
