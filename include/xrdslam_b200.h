@@ -669,6 +669,18 @@ int xrd_debug_gemm(int M, int N, int K, const float* A, int lda, int transA, con
                    const float* relu_mask, int ldmask, const float* addend, int ldadd,
                    void* stream);
 
+/* ... plus act_out[m][n] (the masked activation before the addend) and accumulate (C += ). */
+int xrd_debug_gemm_ex(int M, int N, int K, const float* A, int lda, int transA, const float* B,
+                      int ldb, float* C, int ldc, const float* bias, int act,
+                      const float* relu_mask, int ldmask, const float* addend, int ldadd,
+                      float* act_out, int ldact, int accumulate, void* stream);
+
+/* The weight-gradient kernel of the per-point MLPs (unit tests): out[j][i] += sum_p B[j][p] A[i][p]
+ * over P points (rows of Pp floats), B[j][p] dropped where bit (j & 31) of mask[j / 32][p] is
+ * clear (mask may be NULL), bias[j] += sum_p B[j][p] (bias may be NULL).  DEVICE pointers. */
+int xrd_debug_dw(int nA, int nB, int P, int Pp, const float* A, const float* B,
+                 const uint32_t* mask, float* out, float* bias, void* stream);
+
 size_t xrd_pointslam_workspace_bytes(int n_rays, int n_surface, int stage, int with_grads);
 
 int xrd_pointslam_step(const XrdRays* rays, const XrdPointIndex* index,

@@ -282,6 +282,10 @@ SYMBOLS = {
     'xrd_debug_gemm_variant': (C.c_int, [C.c_int]),
     'xrd_debug_gemm': (C.c_int, [C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, vp,
                                  C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp]),
+    'xrd_debug_gemm_ex': (C.c_int, [C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, vp,
+                                    C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int,
+                                    C.c_int, vp]),
+    'xrd_debug_dw': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
     'xrd_pointslam_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     'xrd_pointslam_step': (C.c_int, [
         C.POINTER(XrdRays), C.POINTER(XrdPointIndex), C.POINTER(XrdPointFeats),
