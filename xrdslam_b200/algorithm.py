@@ -157,6 +157,11 @@ class Algorithm():
         with self.lock:
             return self.gt_c2w_list_ori
 
+    def save_eval(self, out_dir, idx):
+        """The trajectory checkpoint `ds-eval` reads (tracker.py:269-278, 410-420)."""
+        from .io_formats import save_eval_tar
+        return save_eval_tar(self, out_dir, idx)
+
     def is_separate_LR(self):
         with self.lock:
             return self.config.separate_LR
