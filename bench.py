@@ -533,7 +533,8 @@ def pick_threads(step):
     only adds contention.  Calibrate once on one step each."""
     cores = os.cpu_count() or 1
     best, best_t = cores, None
-    for n in sorted({min(cores, c) for c in (8, 16, 32, cores)}):
+    t_all = time.perf_counter()
+    for n in sorted({min(cores, c) for c in (8, 16, 32, cores)}, reverse=True):
         torch.set_num_threads(n)
         step()
         t0 = time.perf_counter()
@@ -541,6 +542,8 @@ def pick_threads(step):
         dt = time.perf_counter() - t0
         if best_t is None or dt < best_t:
             best, best_t = n, dt
+        if time.perf_counter() - t_all > 20.0:  # slow ports (Point-SLAM: ~15 s per step): bound
+            break                               # the calibration, keep the best count seen so far
     torch.set_num_threads(best)
     return best
 

@@ -123,10 +123,12 @@ def test_gemm_t5_act_out_and_accumulate(cuda_dev):
             lib.xrd_debug_gemm_mode(1)
         act = torch.relu(A.double() @ B.double()[:, :N] + bias.double()[:, None])
         act = torch.where(mk[:, :N] > 0, act, torch.zeros_like(act))
-        assert (AO[:, :N].double() - act).abs().max().item() < 5e-6, mode
+        e_ao = (AO[:, :N].double() - act).abs().max().item()
+        assert e_ao < 5e-6 * max(1.0, act.abs().max().item()), ('act_out', mode, e_ao)
         ref = c0[:, :N].double().to(cuda_dev) + act + ad[:, :N].double()
-        assert (C[:, :N].double() - ref).abs().max().item() < 5e-6, mode
-        assert torch.equal(C[:, N:].cpu(), c0[:, N:])   # columns >= N untouched
+        e_c = (C[:, :N].double() - ref).abs().max().item()
+        assert e_c < 5e-6 * max(1.0, ref.abs().max().item()), ('C', mode, e_c)
+        assert torch.equal(C[:, N:].cpu(), c0[:, N:]), ('pad', mode)   # columns >= N untouched
 
 
 @pytest.mark.parametrize('nA,nB,P,masked', [
@@ -158,7 +160,9 @@ def test_weight_gradient_kernels_match_float64(cuda_dev, nA, nB, P, masked):
     ref_b = Bm.sum(1)
     out0 = torch.randn(nB, nA, generator=g)
     b0 = torch.randn(nB, generator=g)
-    tol = 1e-5 * P ** 0.5   # fp32 accumulation of P unit-variance products; one dropped point ~ 1
+    # fp32 accumulation of P unit-variance products (|dW| ~ sqrt(P); the tensor-core accumulator
+    # truncates): 4e-5 relative to that scale; one dropped or doubled point would be ~ 1
+    tol = 4e-5 * P ** 0.5
     for mode in (1, 0):
         out, bias = out0.clone().to(cuda_dev), b0.clone().to(cuda_dev)
         A_d, B_d = A.to(cuda_dev), B.to(cuda_dev)
