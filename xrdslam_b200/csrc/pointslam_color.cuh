@@ -188,6 +188,14 @@ __global__ void __launch_bounds__(128) k_nb_build_bwd(const ColorP C) {
   for (int i = threadIdx.x; i < 3 * CE; i += blockDim.x) sBe[i] = C.dec.B[i];
   __syncthreads();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  // d B_rel partial sums stay in registers (3 x CR per thread) and are reduced per warp at the
+  // end: one shared-memory atomic per (warp, entry) instead of one per (thread, neighbour, entry)
+  // -- every thread of the CTA used to hammer the same 30 shared-memory words
+  float dB[3][CR];
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+#pragma unroll
+    for (int m = 0; m < CR; ++m) dB[d][m] = 0.f;
   if (p < C.K.P) {
     float q[3];
     query_point(C.K, p, q);
@@ -216,7 +224,7 @@ __global__ void __launch_bounds__(128) k_nb_build_bwd(const ColorP C) {
           if (da == 0.f) continue;
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
-            if (C.d_B_rel) atomicAdd(&sdB[d * CR + m], TWO_PI * rel[d] * da);
+            dB[d][m] += TWO_PI * rel[d] * da;
             g[d] -= TWO_PI * sB[d * CR + m] * da;  // rel = x - p
           }
         }
@@ -236,6 +244,13 @@ __global__ void __launch_bounds__(128) k_nb_build_bwd(const ColorP C) {
     }
   }
   if (C.d_B_rel) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+      for (int m = 0; m < CR; ++m) {
+        const float v = warp_sum(dB[d][m]);
+        if ((threadIdx.x & 31) == 0 && v != 0.f) atomicAdd(&sdB[d * CR + m], v);
+      }
     __syncthreads();
     for (int i = threadIdx.x; i < 3 * CR; i += blockDim.x)
       if (sdB[i] != 0.f) atomicAdd(C.d_B_rel + i, sdB[i]);
