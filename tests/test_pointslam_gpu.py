@@ -142,8 +142,11 @@ def test_pointslam_step_vs_oracle(cuda_dev, is_mapping):
     td[7::11] = 0
     radius = torch.rand(R, generator=gen) * 0.06 + 0.04
     rf = torch.randn(32, generator=gen) * 0.01
+    # rand_feat (Q6: the feature of sample points without neighbours) is an explicit input on
+    # both sides; without it the model draws from the global generator and the comparison
+    # depends on which tests ran before
     g = dict(rays_o=np.zeros((R, 3), np.float32), rays_d=rd.numpy(), target_d=td.numpy(),
-             radius=radius.numpy())
+             radius=radius.numpy(), rand_feat=rf.numpy())
     out, ld, ro, rdg = _run(model, g, is_mapping, cuda_dev)
     ro_o = torch.zeros(R, 3, requires_grad=True)
     rd_o = rd.clone().requires_grad_(True)
