@@ -237,7 +237,14 @@ class MappingGraphSession:
         cur = torch.cuda.current_stream(dev)
         self._part_a(cur.cuda_stream)
         if self.world == 1:
-            self._part_b(cur.cuda_stream)
+            # smoothness (a 31^3 lattice, independent of the rays) on a forked branch of the
+            # graph: it only needs the zeroed gradient bucket and overlaps the sample + fused pass
+            side = self._side
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                self._part_smooth(side.cuda_stream)
+            self._part_b(cur.cuda_stream, smooth=False, pose=True)
+            cur.wait_stream(side)
         else:
             side = self._side
             side.wait_stream(cur)
@@ -259,7 +266,7 @@ class MappingGraphSession:
             # then capture
             self.rows[:, 2] = -1.0
             self.rows[:, 6] = 1.0
-            self._side = torch.cuda.Stream(dev) if self.world > 1 else None
+            self._side = torch.cuda.Stream(dev)
             self._iteration(with_adam=False)
             torch.cuda.synchronize(dev)
             try:
