@@ -207,7 +207,12 @@ class MappingGraphSession:
             n, ptr(self.rot), ptr(self.d_poses), ptr(self.fixed), ptr(self.d_rot_it),
             ptr(self.d_trans_it), stream))
 
-    def _part_c(self, stream, with_adam):
+    def _part_pose_acc(self):
+        if self.ba:
+            self.d_rot += self.d_rot_it
+            self.d_trans += self.d_trans_it
+
+    def _part_c(self, stream, with_adam, pose_acc=True):
         """Adam on table + decoder, pose-gradient accumulation (accum_step), total loss."""
         lib = _cabi.lib()
         if with_adam:
@@ -222,9 +227,8 @@ class MappingGraphSession:
             descs = [a]
         arr = (XrdAdamTensor * len(descs))(*descs)
         check('xrd_adam_step', lib.xrd_adam_step(arr, len(descs), 0, stream))
-        if self.ba:
-            self.d_rot += self.d_rot_it
-            self.d_trans += self.d_trans_it
+        if pose_acc:
+            self._part_pose_acc()
         self.loss_total = self.flat[-8:-3].sum()
 
     def _iteration(self, with_adam):
@@ -243,8 +247,18 @@ class MappingGraphSession:
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 self._part_smooth(side.cuda_stream)
-            self._part_b(cur.cuda_stream, smooth=False, pose=True)
+            self._part_b(cur.cuda_stream, smooth=False, pose=False)
+            # second fork: the pose-gradient chain (ray -> pose -> axis-angle reduction and its
+            # accumulation) next to Adam on the table and the decoder, which do not depend on it
+            side2 = self._side2
+            side2.wait_stream(cur)
+            with torch.cuda.stream(side2):
+                self._part_pose(side2.cuda_stream)
+                self._part_pose_acc()
             cur.wait_stream(side)
+            self._part_c(cur.cuda_stream, with_adam=with_adam, pose_acc=False)
+            cur.wait_stream(side2)
+            return
         else:
             side = self._side
             side.wait_stream(cur)
@@ -267,6 +281,7 @@ class MappingGraphSession:
             self.rows[:, 2] = -1.0
             self.rows[:, 6] = 1.0
             self._side = torch.cuda.Stream(dev)
+            self._side2 = torch.cuda.Stream(dev)
             self._iteration(with_adam=False)
             torch.cuda.synchronize(dev)
             try:
